@@ -1,0 +1,294 @@
+// norm.cu -- normalisation kernels over row-major [rows, C] activations.
+// GroupNorm over a cloud (reference model/kpconv/modules.py:45-49), affine-free InstanceNorm
+// (model/imagenet.py:123, model/network.py:42-43), train-mode BatchNorm (model/imagenet.py:381-394) are the
+// same computation here: statistics per (frame, group of channels) over the R rows of the frame.
+// HBM-bound elementwise work: coalesced float loads along channels, fp64 statistics, two deterministic
+// passes (partials -> apply), no atomics.
+#include "common.cuh"
+
+namespace cofi {
+
+constexpr int kStatChunks = 64;  // row chunks per frame for the partial statistics
+
+// partials layout: [frames][kStatChunks][C][2] doubles (sum, sumsq)
+__global__ void __launch_bounds__(256)
+norm_stats_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C, double* __restrict__ partials) {
+    const int frame = blockIdx.z;
+    const int chunk = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t rows_per = (R + kStatChunks - 1) / kStatChunks;
+    const int64_t r0 = chunk * rows_per;
+    const int64_t r1 = (r0 + rows_per < R) ? r0 + rows_per : R;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    const float* p = x + ((int64_t)frame * R) * ldx + c;
+    for (int64_t r = r0; r < r1; ++r) {
+        const double v = (double)__ldg(p + r * ldx);
+        s += v;
+        ss += v * v;
+    }
+    double* o = partials + (((int64_t)frame * kStatChunks + chunk) * C + c) * 2;
+    o[0] = s;
+    o[1] = ss;
+}
+
+// one block per (frame, group): reduce partials -> mean, rstd
+__global__ void __launch_bounds__(128)
+norm_finalize_kernel(const double* __restrict__ partials, int64_t R, int C, int G, float eps,
+                     float2* __restrict__ mean_rstd, float* __restrict__ mean_out, float* __restrict__ var_out) {
+    const int frame = blockIdx.y, g = blockIdx.x;
+    const int gs = C / G;
+    double s = 0.0, ss = 0.0;
+    for (int t = threadIdx.x; t < kStatChunks * gs; t += blockDim.x) {
+        const int chunk = t / gs, c = g * gs + (t - chunk * gs);
+        const double* o = partials + (((int64_t)frame * kStatChunks + chunk) * C + c) * 2;
+        s += o[0];
+        ss += o[1];
+    }
+    __shared__ double sh[2][4];
+    s = warp_sum_d(s);
+    ss = warp_sum_d(ss);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        sh[0][w] = s;
+        sh[1][w] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+        ss = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+        const double n = (double)R * gs;
+        const double mean = s / n;
+        double var = ss / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double rstd = 1.0 / sqrt(var + (double)eps);
+        mean_rstd[(int64_t)frame * G + g] = make_float2((float)mean, (float)rstd);
+        if (mean_out) mean_out[(int64_t)frame * G + g] = (float)mean;
+        if (var_out) var_out[(int64_t)frame * G + g] = (float)var;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+norm_apply_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C, int G,
+                  const float2* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, const float* __restrict__ residual, int64_t ldr, int act,
+                  float* __restrict__ y, int64_t ldy, int64_t total_rows) {
+    const int gs = C / G;
+    const int64_t total = total_rows * C;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / C;
+        const int c = (int)(t - row * C);
+        const int64_t frame = row / R;
+        const float2 ms = __ldg(mean_rstd + frame * G + c / gs);
+        float v = (__ldg(x + row * ldx + c) - ms.x) * ms.y;
+        if (gamma) v = v * __ldg(gamma + c) + __ldg(beta + c);
+        if (residual) v += __ldg(residual + row * ldr + c);
+        y[row * ldy + c] = apply_act(v, act);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+affine_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C, const float* __restrict__ scale,
+                   const float* __restrict__ shift, const float* __restrict__ residual, int64_t ldr, int act,
+                   float* __restrict__ y, int64_t ldy) {
+    const int64_t total = rows * C;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / C;
+        const int c = (int)(t - row * C);
+        float v = __ldg(x + row * ldx + c);
+        if (scale) v = v * __ldg(scale + c) + __ldg(shift + c);
+        if (residual) v += __ldg(residual + row * ldr + c);
+        y[row * ldy + c] = apply_act(v, act);
+    }
+}
+
+// one warp per row; C <= 32*kLNMax
+constexpr int kLNMax = 64;  // up to 2048 channels
+__global__ void __launch_bounds__(128)
+layer_norm_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act,
+                       const float* __restrict__ residual, int64_t ldr, float* __restrict__ y, int64_t ldy) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* p = x + row * ldx;
+    double s = 0.0;
+    for (int c = lane; c < C; c += 32) s += (double)__ldg(p + c);
+    s = warp_sum_d(s);
+    const double mean = s / C;
+    double ss = 0.0;
+    for (int c = lane; c < C; c += 32) {
+        const double d = (double)__ldg(p + c) - mean;
+        ss += d * d;
+    }
+    ss = warp_sum_d(ss);
+    const float rstd = (float)(1.0 / sqrt(ss / C + (double)eps));
+    const float meanf = (float)mean;
+    for (int c = lane; c < C; c += 32) {
+        float v = (__ldg(p + c) - meanf) * rstd;
+        if (gamma) v = v * __ldg(gamma + c) + __ldg(beta + c);
+        v = apply_act(v, act);
+        if (residual) v += __ldg(residual + row * ldr + c);
+        y[row * ldy + c] = v;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+l2norm_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C, const float* __restrict__ add,
+                   int64_t ldadd, float* __restrict__ y, int64_t ldy) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* p = x + row * ldx;
+    double ss = 0.0;
+    for (int c = lane; c < C; c += 32) {
+        const double v = (double)__ldg(p + c);
+        ss += v * v;
+    }
+    ss = warp_sum_d(ss);
+    // F.normalize: x / max(||x||, eps), eps = 1e-12
+    const float denom = fmaxf((float)sqrt(ss), 1e-12f);
+    for (int c = lane; c < C; c += 32) {
+        float v = __ldg(p + c) / denom;
+        if (add) v += __ldg(add + row * ldadd + c);
+        y[row * ldy + c] = v;
+    }
+}
+
+// column sums of squares over the L rows of each frame -> partial [frames][chunks][C] then scale
+__global__ void __launch_bounds__(256)
+colsq_kernel(const float* __restrict__ x, int64_t ldx, int64_t L, int C, double* __restrict__ partials) {
+    const int frame = blockIdx.z, chunk = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t rows_per = (L + kStatChunks - 1) / kStatChunks;
+    const int64_t r0 = chunk * rows_per;
+    const int64_t r1 = (r0 + rows_per < L) ? r0 + rows_per : L;
+    if (c >= C) return;
+    double ss = 0.0;
+    const float* p = x + ((int64_t)frame * L) * ldx + c;
+    for (int64_t r = r0; r < r1; ++r) {
+        const double v = (double)__ldg(p + r * ldx);
+        ss += v * v;
+    }
+    partials[((int64_t)frame * kStatChunks + chunk) * C + c] = ss;
+}
+
+__global__ void __launch_bounds__(256)
+colnorm_apply_kernel(const float* __restrict__ x, int64_t ldx, int64_t L, int C, int64_t total_rows,
+                     const double* __restrict__ partials, float* __restrict__ y, int64_t ldy) {
+    // each block handles a tile of rows for all channels; column norms recomputed per thread (C small)
+    const int64_t total = total_rows * C;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / C;
+        const int c = (int)(t - row * C);
+        const int64_t frame = row / L;
+        double ss = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < kStatChunks; ++k) ss += partials[((int64_t)frame * kStatChunks + k) * C + c];
+        const float denom = fmaxf((float)sqrt(ss), 1e-12f);
+        y[row * ldy + c] = __ldg(x + row * ldx + c) / denom;
+    }
+}
+
+}  // namespace cofi
+
+using namespace cofi;
+
+static unsigned ew_blocks(int64_t total, int threads) {
+    int64_t b = ceil_div(total, threads);
+    const int64_t cap = 148 * 16;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" int64_t cofi_norm_rows_workspace(int frames, int C) {
+    // partial sums + (mean, rstd) table
+    return (int64_t)frames * kStatChunks * C * 2 * sizeof(double) + (int64_t)frames * C * sizeof(float2) + 256;
+}
+
+extern "C" int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int frames, int G, const float* gamma,
+                              const float* beta, float eps, const float* residual, int64_t ldr, int act, float* y,
+                              int64_t ldy, void* partials, float* mean_out, float* var_out, void* stream) {
+    COFI_REQUIRE(x && y && partials, "cofi_norm_rows: null pointer");
+    COFI_REQUIRE(R > 0 && C > 0 && frames > 0 && G > 0 && C % G == 0, "cofi_norm_rows: bad shape R=%lld C=%d G=%d",
+                 (long long)R, C, G);
+    COFI_REQUIRE((gamma == nullptr) == (beta == nullptr), "cofi_norm_rows: gamma and beta go together");
+    COFI_REQUIRE(((uintptr_t)partials % 16) == 0, "cofi_norm_rows: workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* part = reinterpret_cast<double*>(partials);
+    float2* mr = reinterpret_cast<float2*>(part + (int64_t)frames * kStatChunks * C * 2);
+    {
+        const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32));
+        dim3 grid((unsigned)ceil_div(C, threads), kStatChunks, frames);
+        norm_stats_kernel<<<grid, threads, 0, st>>>(x, ldx, R, C, part);
+        int rc = check_launch("cofi_norm_rows(stats)");
+        if (rc) return rc;
+    }
+    {
+        dim3 grid(G, frames);
+        norm_finalize_kernel<<<grid, 128, 0, st>>>(part, R, C, G, eps, mr, mean_out, var_out);
+        int rc = check_launch("cofi_norm_rows(finalize)");
+        if (rc) return rc;
+    }
+    const int64_t rows = R * frames;
+    norm_apply_kernel<<<ew_blocks(rows * C, 256), 256, 0, st>>>(x, ldx, R, C, G, mr, gamma, beta, residual, ldr, act,
+                                                                y, ldy, rows);
+    return check_launch("cofi_norm_rows(apply)");
+}
+
+extern "C" int cofi_affine_rows(const float* x, int64_t ldx, int64_t rows, int C, const float* scale,
+                                const float* shift, const float* residual, int64_t ldr, int act, float* y,
+                                int64_t ldy, void* stream) {
+    COFI_REQUIRE(x && y, "cofi_affine_rows: null pointer");
+    COFI_REQUIRE((scale == nullptr) == (shift == nullptr), "cofi_affine_rows: scale and shift go together");
+    if (rows == 0) return COFI_OK;
+    affine_rows_kernel<<<ew_blocks(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, scale, shift,
+                                                                                  residual, ldr, act, y, ldy);
+    return check_launch("cofi_affine_rows");
+}
+
+extern "C" int cofi_layer_norm_rows(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma,
+                                    const float* beta, float eps, int act, const float* residual, int64_t ldr,
+                                    float* y, int64_t ldy, void* stream) {
+    COFI_REQUIRE(x && y, "cofi_layer_norm_rows: null pointer");
+    COFI_REQUIRE(C > 0 && C <= 32 * kLNMax, "cofi_layer_norm_rows: C=%d out of range", C);
+    COFI_REQUIRE((gamma == nullptr) == (beta == nullptr), "cofi_layer_norm_rows: gamma and beta go together");
+    if (rows == 0) return COFI_OK;
+    const int wpb = 4;
+    layer_norm_rows_kernel<<<(unsigned)ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        x, ldx, rows, C, gamma, beta, eps, act, residual, ldr, y, ldy);
+    return check_launch("cofi_layer_norm_rows");
+}
+
+extern "C" int cofi_l2norm_rows(const float* x, int64_t ldx, int64_t rows, int C, const float* add, int64_t ldadd,
+                                float* y, int64_t ldy, void* stream) {
+    COFI_REQUIRE(x && y && C > 0, "cofi_l2norm_rows: bad argument");
+    if (rows == 0) return COFI_OK;
+    const int wpb = 4;
+    l2norm_rows_kernel<<<(unsigned)ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, add,
+                                                                                            ldadd, y, ldy);
+    return check_launch("cofi_l2norm_rows");
+}
+
+extern "C" int64_t cofi_colnorm_workspace(int frames, int C) {
+    return (int64_t)frames * kStatChunks * C * sizeof(double);
+}
+
+extern "C" int cofi_colnorm_rows(const float* x, int64_t ldx, int64_t L, int C, int frames, void* colsq, float* y,
+                                 int64_t ldy, void* stream) {
+    COFI_REQUIRE(x && y && colsq, "cofi_colnorm_rows: null pointer");
+    COFI_REQUIRE(L > 0 && C > 0 && frames > 0, "cofi_colnorm_rows: bad shape");
+    COFI_REQUIRE(((uintptr_t)colsq % 8) == 0, "cofi_colnorm_rows: workspace must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* part = reinterpret_cast<double*>(colsq);  // frames*kStatChunks*C doubles
+    const int threads = C >= 128 ? 128 : (C >= 64 ? 64 : 32);
+    dim3 grid((unsigned)ceil_div(C, threads), kStatChunks, frames);
+    colsq_kernel<<<grid, threads, 0, st>>>(x, ldx, L, C, part);
+    int rc = check_launch("cofi_colnorm_rows(colsq)");
+    if (rc) return rc;
+    const int64_t rows = L * frames;
+    colnorm_apply_kernel<<<ew_blocks(rows * C, 256), 256, 0, st>>>(x, ldx, L, C, rows, part, y, ldy);
+    return check_launch("cofi_colnorm_rows(apply)");
+}

@@ -1,0 +1,209 @@
+/* cofi_b200.h -- C ABI of libcofi_b200.so: hand-written sm_100a kernels for CoFiI2P's coarse-to-fine
+ * correspondence hot path.
+ *
+ * The reference (WHU-USI3DV/CoFiI2P @ ed90edf) is pure PyTorch and has no FFI of its own; every entry
+ * point below replaces the ATen call sequence of the cited reference lines (paths relative to the
+ * reference repository).  Conventions:
+ *   - every pointer is a DEVICE pointer unless marked host; the caller (PyTorch) allocates all outputs
+ *     and workspaces; the library is stateless apart from a per-process cache of TMA descriptors;
+ *   - every function returns 0 on success or a negative COFI_E* code and never throws;
+ *     cofi_last_error() returns a thread-local message for the last failure;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it and capturable in
+ *     CUDA graphs (no allocation, no synchronisation inside);
+ *   - matrices are row-major fp32 with an explicit leading dimension (elements); index tables are int64
+ *     exactly as the reference's dataset produces them (model/kpconv/preprocess_data.py:82-99);
+ *   - "frames": B independent frames stacked along the row axis with equal row counts per frame
+ *     (the reference is batch-1; B>1 is the batched entry point of BASELINE config 2).  Index tables hold
+ *     frame-local indices; index == rows_per_frame of the source means "shadow neighbour" (zero feature,
+ *     point at infinity), as in model/kpconv/kpconv.py:91,103.
+ */
+#ifndef COFI_B200_H
+#define COFI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COFI_OK 0
+#define COFI_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
+#define COFI_ECUDA (-2)   /* CUDA runtime / driver error at launch */
+#define COFI_EUNSUPPORTED (-3)
+
+/* activation codes shared by the epilogues */
+#define COFI_ACT_NONE 0
+#define COFI_ACT_RELU 1
+#define COFI_ACT_LRELU01 2 /* LeakyReLU(0.1), model/kpconv/modules.py:82,149,218 */
+#define COFI_ACT_SIGMOID 3
+
+/* GEMM engines */
+#define COFI_GEMM_FP32 0   /* SIMT fp32 FMA: exact-order parity engine */
+#define COFI_GEMM_TF32 1   /* tcgen05 kind::tf32, fp32 operands read by TMA, fp32 accumulate in TMEM */
+#define COFI_GEMM_TF32X3 2 /* tcgen05 3xTF32 split (hi*hi + hi*lo + lo*hi): fp32-grade accuracy on tensor cores */
+
+int cofi_version(void);
+const char* cofi_last_error(void);
+/* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
+int64_t cofi_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Point stream (model/kpconv)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* packed[i] = (x, y, z, flag) with flag = 1.0 if sum_c feats[i,c] > 0 else 0.0.
+ * Pre-pass of KPConv's neighbour count (model/kpconv/kpconv.py:113-114) folded into the coordinate table
+ * so the neighbour gather is a single 16-byte load.  rows = total rows (all frames). */
+int cofi_pack_points(const float* points, const float* feats, int64_t ldf, int C, int64_t rows,
+                     float* packed /* [rows,4] */, void* stream);
+
+/* Fused neighbour gather + kernel-point influence + aggregation of rigid KPConv
+ * (model/kpconv/kpconv.py:91-105 and :113-115):
+ *   w[m,h,k]   = max(0, 1 - |(s[nbr[m,h]] - q[m]) - kp[k]| / sigma)
+ *   agg[m,k,c] = sum_h w[m,h,k] * feats[nbr[m,h], c]          (written as [M, K*C] row-major)
+ *   cnt[m]     = max(1, #{h : sum_c feats[nbr[m,h],c] > 0})   (as float)
+ * The weight application agg[M,K*C] x W[K*C,Cout] (:108-110), the division by cnt (:116) and the bias
+ * (:119-120) are one cofi_gemm call with `rowdiv = cnt`.  No tensor cores here: influences are sparse,
+ * zero weights are skipped exactly. */
+int cofi_kpconv_aggregate(const float* feats, int64_t ldf, int C,
+                          const float* s_packed /* [frames*Ns,4] from cofi_pack_points */,
+                          const float* q_points /* [frames*Mq,3] */,
+                          const int64_t* nbr /* [frames*Mq,H] */, int H,
+                          int64_t Mq, int64_t Ns, int frames,
+                          const float* kernel_points /* [K,3] */, int K, float sigma,
+                          float* agg /* [frames*Mq, K*C] */, float* cnt /* [frames*Mq] */, void* stream);
+
+/* out[m,c] = max_h x[nbr[m,h], c] with shadow rows = 0 (model/kpconv/functional.py:53-66). */
+int cofi_maxpool_rows(const float* x, int64_t ldx, int C, const int64_t* nbr, int H,
+                      int64_t Mq, int64_t Ns, int frames, float* out, int64_t ldo, void* stream);
+
+/* out[i, 0:C] = x[idx[i*idx_stride], 0:C] (shadow -> 0), or x[i] when idx == NULL.
+ * nearest_upsample reads only column 0 of its [N,128] table (model/kpconv/functional.py:18-20):
+ * idx_stride = 128.  `out` may point into a wider concat buffer (ldo) -> torch.cat of
+ * model/kpconv/kp_backbone.py:112,117,122 costs no extra pass. */
+int cofi_gather_rows(const float* x, int64_t ldx, int C, const int64_t* idx, int64_t idx_stride,
+                     int64_t Mq, int64_t Ns, int frames, float* out, int64_t ldo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Dense contractions
+ * ------------------------------------------------------------------------------------------------- */
+
+/* C[M,N] = act( (A[M,K] * W[N,K]^T) / rowdiv[m] + bias[n] + (accumulate ? C : 0) )
+ * W is K-major, i.e. nn.Linear's weight as stored (model/kpconv/modules.py:78,108; transformer.py:26-36;
+ * network.py:29); KPConv's [K*C,Cout] weights are passed pre-transposed by the host.
+ * rowdiv, bias may be NULL.  engine: COFI_GEMM_*.  K, lda, ldw must be multiples of 4. */
+int cofi_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+              int64_t M, int N, int K, const float* bias, const float* rowdiv, int accumulate, int act,
+              int engine, void* stream);
+
+/* NHWC convolution as implicit GEMM (model/imagenet.py:26-34,142-143,377-394):
+ *   y[b,ho,wo,co] = sum_{kh,kw,ci} x[b, ho*stride+kh-pad, wo*stride+kw-pad, ci] * w[co, kh, kw, ci]
+ * w is [Cout, KH*KW*Cin] (host repacks the reference's [Cout,Cin,KH,KW]).  Cin % 4 == 0.
+ * Optional per-channel affine + residual + activation epilogue = eval-mode BatchNorm folded
+ * (model/imagenet.py:398-411): y = act(conv*scale[co] + shift[co] + residual). */
+int cofi_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW,
+                     int stride, int pad, const float* scale, const float* shift, const float* residual,
+                     int act, float* y, int engine, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Normalisations (all statistics in fp64)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Grouped normalisation over the rows of each frame: x is [frames*R, C]; statistics per (frame, group)
+ * over R rows x (C/G) channels, biased variance, eps inside the sqrt.
+ *   GroupNorm(32) over a cloud   (model/kpconv/modules.py:45-49)        G = 32, gamma/beta given
+ *   affine-free InstanceNorm     (model/imagenet.py:123; network.py:42-43) G = C, gamma = beta = NULL
+ *   train-mode BatchNorm         (model/imagenet.py:381-394)             frames = 1, G = C
+ * y = act( (x-mean)*rstd*gamma + beta + residual ).  `partials` is a caller workspace of
+ * cofi_norm_rows_workspace(frames, C) bytes.  If mean_out/var_out != NULL (size frames*G) the batch
+ * statistics are also written (BatchNorm running-stat update is done by the host). */
+int64_t cofi_norm_rows_workspace(int frames, int C);
+int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int frames, int G, const float* gamma,
+                   const float* beta, float eps, const float* residual, int64_t ldr, int act, float* y,
+                   int64_t ldy, void* partials, float* mean_out, float* var_out, void* stream);
+
+/* y = act(x*scale[c] + shift[c] + residual): eval-mode BatchNorm as a per-channel affine. */
+int cofi_affine_rows(const float* x, int64_t ldx, int64_t rows, int C, const float* scale, const float* shift,
+                     const float* residual, int64_t ldr, int act, float* y, int64_t ldy, void* stream);
+
+/* Row LayerNorm (eps 1e-5) + activation + optional residual added AFTER the norm:
+ * y = act(LN(x)*gamma+beta) + residual  (model/network.py:29; model/transformer/transformer.py:58,62-64). */
+int cofi_layer_norm_rows(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta,
+                         float eps, int act, const float* residual, int64_t ldr, float* y, int64_t ldy,
+                         void* stream);
+
+/* y = x / max(|x|_2, 1e-12) per row (+ add[row,:] if add != NULL): F.normalize(dim=channel)
+ * (model/network.py:82,84,90,125,126,130) fused with the positional-encoding add (:113-114). */
+int cofi_l2norm_rows(const float* x, int64_t ldx, int64_t rows, int C, const float* add, int64_t ldadd,
+                     float* y, int64_t ldy, void* stream);
+
+/* Column L2 normalisation over the L rows of each frame: F.normalize(q) with default dim=1 normalises Q
+ * over the SEQUENCE axis (model/transformer/transformer.py:53).  In place allowed. `work` is a caller
+ * workspace of cofi_colnorm_workspace(frames, C) bytes (8-byte aligned). */
+int64_t cofi_colnorm_workspace(int frames, int C);
+int cofi_colnorm_rows(const float* x, int64_t ldx, int64_t L, int C, int frames, void* work, float* y,
+                      int64_t ldy, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Image stream helpers (model/imagenet.py)
+ * ------------------------------------------------------------------------------------------------- */
+int cofi_nchw_to_nhwc(const float* x, int B, int C, int H, int W, int Cpad, float* y, void* stream);
+int cofi_nhwc_to_nchw(const float* x, int B, int H, int W, int C, float* y, void* stream);
+/* MaxPool2d(3, stride 2, pad 1) (model/imagenet.py:145,204) */
+int cofi_maxpool2d_3x3s2_nhwc(const float* x, int B, int H, int W, int C, float* y, void* stream);
+/* y = cat(bilinear_x2(x1, align_corners=False), x2) along channels (model/imagenet.py:433,441-443) */
+int cofi_upsample2x_cat_nhwc(const float* x1, int B, int H, int W, int C1, const float* x2, int C2, float* y,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * I2P transformer (model/transformer)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* PositionEmbeddingCoordsSine (model/transformer/position_encoding.py:29-50): scale 2*pi, temperature 1e4,
+ * interleaved sin/cos, zero pad to d_model. coords [rows, n_dim] fp32. Accurate sinf/cosf (arguments reach
+ * hundreds of radians). */
+int cofi_posenc_sine(const float* coords, int64_t rows, int n_dim, int d_model,
+                     const float* dim_t /* [d_model/n_dim/2*2] = 1e4^(2*(i/2)/npf), built by the host with torch.pow */,
+                     float* out, void* stream);
+
+/* Multi-head softmax attention, out = softmax(scale * Q K^T) V per (frame, head)
+ * (model/transformer/linear_attention.py:69-77).  q [frames*L, heads*D], k,v [frames*S, heads*D]. D == 32. */
+int cofi_attention(const float* q, const float* k, const float* v, int64_t L, int64_t S, int frames, int heads,
+                   int D, float scale, float* out, int engine, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Matching (model/network.py:167-264, evaluation/eval_all.py:99-105)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Fused similarity + row arg-min; the [Npt,Npx] matrix is never materialised.
+ * For every point row p: d[x] = 1 - sum_c pt[p,c]*px[x,c]; best_idx[p] = argmin_x d (lowest index on ties),
+ * best_val[p] = min.  (model/network.py:174-179).  pt [frames*Npt, C], px [frames*Npx, C]. */
+int cofi_sim_argmin(const float* pt, int64_t ldpt, const float* px, int64_t ldpx, int64_t Npt, int64_t Npx, int C,
+                    int frames, int64_t* best_idx, float* best_val, int engine, void* stream);
+
+/* Test-mode selection loop of model/network.py:146-151 + :169,:184-186 in one kernel, per frame:
+ * find the first threshold t in thresholds[0..nthr) with at least `min_count` points satisfying
+ * score >= t AND the border mask on their matched pixel (2<=x<=W-2, 2<=y<=H-2 for the 20x64 grid);
+ * emit those point indices in ascending order.  out_count[frame*2+0] = n, out_count[frame*2+1] = index of the
+ * threshold used; out_index[frame*Npt ..]; out_xy[frame*2*Npt ..] laid out as [2][Npt] (x=col, y=row, fp32). */
+int cofi_select_matches(const float* score, const int64_t* best_idx, int64_t Npt, int frames, int gridH, int gridW,
+                        const float* thresholds, int nthr, int min_count, int32_t* out_count, int64_t* out_index,
+                        float* out_xy, void* stream);
+
+/* point2node (model/network.py:250-264): idx[i] = argmin_j clamp(|p_i|^2 + |n_j|^2 - 2 p_i.n_j, 1e-12). */
+int cofi_nn_argmin(const float* points, int64_t n, const float* nodes, int64_t M, int64_t* idx, void* stream);
+
+/* extract_patch (model/network.py:206-226): out[i,c,dy,dx] = map[b, floor(cy-2)+dy, floor(cx-2)+dx, c],
+ * map NHWC [B,H,W,C], centres [2,n] as fp32 (x row 0, y row 1), out [n,C,4,4].  Out-of-range windows
+ * return COFI_EINVAL semantics via `err_flag` (device int set to 1), mirroring the reference's assert. */
+int cofi_extract_patch(const float* map, int H, int W, int C, int b, const float* centers, int64_t n, float* out,
+                       int32_t* err_flag, void* stream);
+
+/* Caller-side fine match (evaluation/eval_all.py:99-105): argmax over the 16 patch pixels of the cosine
+ * similarity with the point feature; patch [n,C,16], pc [n,C] -> idx [n]. */
+int cofi_fine_match(const float* patch, const float* pc, int64_t n, int C, int64_t* idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COFI_B200_H */
