@@ -225,3 +225,26 @@ def frame_to(frame: Dict, device) -> Dict:
             return {k: mv(v) for k, v in x.items()}
         return x
     return mv(frame)
+
+
+def stack_frames(frames: List[Dict]) -> Dict:
+    """Stack B frames of equal size along the row axis (index tables stay frame-local): the batched input of
+    `CoFiI2P.forward_batch` / the inference engine."""
+    B = len(frames)
+    d0 = frames[0]["pc_data_dict"]
+    L = len(d0["points"])
+    pc = {
+        "points": [torch.cat([f["pc_data_dict"]["points"][i] for f in frames], 0) for i in range(L)],
+        "neighbors": [torch.cat([f["pc_data_dict"]["neighbors"][i] for f in frames], 0) for i in range(L)],
+        "subsampling": [torch.cat([f["pc_data_dict"]["subsampling"][i] for f in frames], 0) for i in range(L - 1)],
+        "upsampling": [torch.cat([f["pc_data_dict"]["upsampling"][i] for f in frames], 0) for i in range(L - 1)],
+        "feats": torch.cat([f["pc_data_dict"]["feats"] for f in frames], 0),
+        "lengths": d0["lengths"],
+    }
+    return {
+        "frames": B,
+        "pc_data_dict": pc,
+        "img": torch.cat([f["img"] for f in frames], 0),
+        "fine_center_kpt_coors": [f["fine_center_kpt_coors"] for f in frames],
+        "fine_pc_inline_index": [f["fine_pc_inline_index"] for f in frames],
+    }

@@ -1,0 +1,12 @@
+"""reference model/kpconv/functional.py:5-21,53-66 on the B200 kernels."""
+from ... import ops
+
+
+def nearest_upsample(x, upsample_indices, frames: int = 1, out=None):
+    """Only column 0 of the [n2, max_num] table is read (the tables are distance-ordered)."""
+    return ops.gather_rows(x, upsample_indices, idx_stride=upsample_indices.shape[1], frames=frames, out=out,
+                           rows_out=upsample_indices.shape[0])
+
+
+def maxpool(x, neighbor_indices, frames: int = 1):
+    return ops.maxpool_rows(x, neighbor_indices, frames)

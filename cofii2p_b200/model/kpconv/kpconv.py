@@ -1,0 +1,52 @@
+"""Rigid KPConv on the B200 kernels (reference model/kpconv/kpconv.py:10-122)."""
+import math
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from .kernel_points import load_kernels
+
+
+class KPConv(nn.Module):
+    """Same parameters/buffers as the reference: `weights` [K,Cin,Cout], `bias` [Cout] or None,
+    buffer `kernel_points` [K,3]."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, radius, sigma, bias=False, dimension=3,
+                 inf=1e6, eps=1e-9):
+        super().__init__()
+        self.kernel_size, self.in_channels, self.out_channels = kernel_size, in_channels, out_channels
+        self.radius, self.sigma, self.dimension, self.inf, self.eps = radius, sigma, dimension, inf, eps
+        self.weights = nn.Parameter(torch.zeros(kernel_size, in_channels, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+        self.register_buffer("kernel_points",
+                             torch.from_numpy(load_kernels(radius, kernel_size, dimension=dimension, fixed="center")).float())
+        self._wt = None
+        self._wt_version = None
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weights, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in, _ = nn.init._calculate_fan_in_and_fan_out(self.weights)
+            bound = 1 / math.sqrt(fan_in)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def packed_weight(self):
+        """[Cout, K*Cin]: the K-major operand of the weight-apply GEMM (cached per parameter version)."""
+        v = (self.weights._version, self.weights.data_ptr())
+        if self._wt is None or self._wt_version != v:
+            with torch.no_grad():
+                self._wt = self.weights.detach().reshape(-1, self.out_channels).t().contiguous()
+            self._wt_version = v
+        return self._wt
+
+    def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1):
+        """s_feats [B*N,Cin], q_points [B*M,3], s_points [B*N,3], neighbor_indices [B*M,H] -> [B*M,Cout]."""
+        packed = ops.pack_points(s_points, s_feats)
+        agg, cnt = ops.kpconv_aggregate(s_feats, packed, q_points, neighbor_indices, self.kernel_points, self.sigma,
+                                        frames)
+        return ops.gemm(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt)

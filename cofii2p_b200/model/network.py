@@ -1,0 +1,275 @@
+"""CoFiI2P top-level network on the B200 kernels (reference model/network.py:14-274).
+
+Drop-in surface: `CoFiI2P(opt)`, `forward(pc_data_dict, img, fine_center_kpt_coors, fine_xy,
+fine_pc_inline_index, mode)` returning the reference's 8-tuple (same shapes / dtypes / Nones), the same 430
+`state_dict` keys, plus the helpers `fine_process`, `extract_patch`, `point2node`, `square_distance`,
+`CoFiI2P_wrapper`.  Additions: `forward_batch` (B frames stacked along rows, BASELINE config 2) and
+`fine_match` (the caller-side 16-way arg-max of evaluation/eval_all.py:99-105).
+
+All tensors must live on a CUDA device; there is no CPU path (the CPU restatement is `oracle/restate.py`,
+test infrastructure only).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .imagenet import ImageEncoder, ImageUpSample, ResidualConv  # noqa: F401  (ResidualConv: reference import surface)
+from .kpconv.kp_backbone import KPConvFPN
+from .transformer.position_encoding import PositionEmbeddingCoordsSine, PositionEmbeddingLearned
+from .transformer.transformer import LocalFeatureTransformer
+
+
+def _thresholds(device) -> torch.Tensor:
+    """0.9, 0.88, ... as the reference's python-float loop produces them (network.py:146-151), cast to fp32 the
+    way `tensor >= python_float` does."""
+    vals, t = [], 0.9
+    while t > -1.0:
+        vals.append(t)
+        t -= 0.02
+    return torch.tensor(vals, dtype=torch.float32, device=device)
+
+
+class CoFiI2P(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.pe_H = int(opt.img_H / 8)
+        self.pe_W = int(opt.img_W / 8)
+        self.img_encoder = ImageEncoder()
+        self.pc_encoder = KPConvFPN(input_dim=4, output_dim=64, init_dim=64, kernel_size=15, init_radius=4.25 * 0.1,
+                                    init_sigma=2 * 0.1, norm=opt.norm, group_norm=32)
+        self.H_fine_res = int(round(opt.img_H / opt.img_fine_resolution_scale))
+        self.W_fine_res = int(round(opt.img_W / opt.img_fine_resolution_scale))
+        self.pc_feature_layer = nn.Sequential(nn.Linear(2048, 1024, bias=False), nn.LayerNorm(1024), nn.ReLU(),
+                                              nn.Linear(1024, 512, bias=False), nn.LayerNorm(512), nn.ReLU(),
+                                              nn.Linear(512, 128, bias=False))
+        # dead in the reference too (never called, network.py:31,120); kept for the state_dict
+        self.img_feature_layer = nn.Sequential(nn.Conv2d(128, 128, 1, bias=False), nn.InstanceNorm2d(128), nn.ReLU(),
+                                               nn.Conv2d(128, 128, 1, bias=False), nn.InstanceNorm2d(128), nn.ReLU(),
+                                               nn.Conv2d(128, 128, 1, bias=False))
+        self.img_pos_encoding = PositionEmbeddingCoordsSine(2, 128)
+        self.pc_pos_encoding = PositionEmbeddingCoordsSine(3, 128)
+        self.transformer = LocalFeatureTransformer(D_MODEL=128, NHEAD=4, LAYER_NAMES=["self", "cross"] * 4,
+                                                   ATTENTION="full")
+        self.fine_img_pos_encoding = PositionEmbeddingLearned(2, 64)
+        self.fine_pc_pos_encoding = PositionEmbeddingLearned(3, 64)
+        self.img_upsample_1 = ImageUpSample(128 + 64, 128)
+        self.img_upsample_2 = ImageUpSample(128 + 64, 64)
+        self.pc_score_layer = nn.Sequential(nn.Conv1d(128, 128, 1, bias=False), nn.InstanceNorm1d(128), nn.ReLU(),
+                                            nn.Conv1d(128, 64, 1, bias=False), nn.InstanceNorm1d(64), nn.ReLU(),
+                                            nn.Conv1d(64, 1, 1, bias=False), nn.Sigmoid())
+        self.img_score_layer = nn.Sequential(nn.Conv2d(128, 128, 1, bias=False), nn.InstanceNorm2d(128), nn.ReLU(),
+                                             nn.Conv2d(128, 64, 1, bias=False), nn.InstanceNorm2d(64), nn.ReLU(),
+                                             nn.Conv2d(64, 1, 1, bias=False), nn.Sigmoid())
+        self._img_pos = {}
+        self._thr = {}
+
+    # ------------------------------------------------------------------------------------------ pieces
+    def _pc_feature(self, x):
+        """Linear-LN-ReLU-Linear-LN-ReLU-Linear (reference network.py:29)."""
+        l = self.pc_feature_layer
+        x = ops.layer_norm_rows(ops.gemm(x, l[0].weight), l[1].weight, l[1].bias, l[1].eps, act=ops.ACT_RELU)
+        x = ops.layer_norm_rows(ops.gemm(x, l[3].weight), l[4].weight, l[4].bias, l[4].eps, act=ops.ACT_RELU)
+        return ops.gemm(x, l[6].weight)
+
+    @staticmethod
+    def _score_head(seq, tokens, frames):
+        """1x1 conv -> affine-free InstanceNorm -> ReLU (x2) -> 1x1 conv -> sigmoid on [B*N, C] tokens
+        (reference network.py:42-43)."""
+        w0 = seq[0].weight.reshape(seq[0].weight.shape[0], -1)
+        w3 = seq[3].weight.reshape(seq[3].weight.shape[0], -1)
+        w6 = seq[6].weight.reshape(seq[6].weight.shape[0], -1)
+        x = ops.norm_rows(ops.gemm(tokens, w0), frames, w0.shape[0], eps=seq[1].eps, act=ops.ACT_RELU)
+        x = ops.norm_rows(ops.gemm(x, w3), frames, w3.shape[0], eps=seq[4].eps, act=ops.ACT_RELU)
+        return ops.gemm(x, w6, act=ops.ACT_SIGMOID)
+
+    def _image_pos(self, device):
+        key = str(device)
+        if key not in self._img_pos:
+            gy, gx = torch.meshgrid(torch.arange(0, self.pe_H), torch.arange(0, self.pe_W), indexing="ij")
+            xy = torch.stack([gy, gx], -1).reshape(-1, 2).to(torch.float32).to(device)  # (row, col), network.py:104
+            self._img_pos[key] = self.img_pos_encoding(xy)
+        return self._img_pos[key]
+
+    def core(self, pc_data_dict: Dict, img: torch.Tensor, frames: int = 1, taps: Optional[Dict] = None) -> Dict:
+        """The static-shape part of forward (everything before the mode-dependent matching); CUDA-graph
+        capturable.  Returns token-layout tensors:
+          img_norm [B*HW,128], pc_norm [B*N4,128], img_score [B*HW,1], pc_score [B*N4,1],
+          up2 NHWC [B,H/2,W/2,64] (L2-normalised), pc_decode_3 [B*N1,64] (L2-normalised)."""
+        B = frames
+        pcs = self.pc_encoder(pc_data_dict, frames, taps)
+        s2, s4, s8 = self.img_encoder.forward_nhwc(img)
+        hw = self.pe_H * self.pe_W
+        pc_decode_3 = ops.l2norm_rows(pcs[0])                                            # network.py:82
+        pc_pos = self.pc_pos_encoding(pc_data_dict["points"][-1])                         # :107
+        f_pc = ops.l2norm_rows(self._pc_feature(pcs[3]), add=pc_pos)                      # :84,:114
+        img_pos = self._image_pos(img.device)
+        if B > 1:
+            img_pos = img_pos.repeat(B, 1)
+        s8n = ops.l2norm_rows(s8.reshape(B * hw, 128))                                    # :90 (feeds decoder too)
+        f_img = ops.l2norm_rows(s8.reshape(B * hw, 128), add=img_pos)                     # :113
+        f_img, f_pc = self.transformer(f_img, f_pc, frames)                               # :115
+        pc_score = self._score_head(self.pc_score_layer, f_pc, frames)                    # :123
+        img_score = self._score_head(self.img_score_layer, f_img, frames)                 # :124
+        pc_norm = ops.l2norm_rows(f_pc)                                                   # :125
+        img_norm = ops.l2norm_rows(f_img)                                                 # :126
+        up4 = self.img_upsample_1.forward_nhwc(s8n.view(B, self.pe_H, self.pe_W, 128), s4)   # :129
+        up2 = self.img_upsample_2.forward_nhwc(up4, s2)                                   # :130
+        Bh, Hh, Wh, Ch = up2.shape
+        up2n = ops.l2norm_rows(up2.reshape(-1, Ch)).view(Bh, Hh, Wh, Ch)
+        if taps is not None:
+            taps.update(img_s2=s2, img_s4=s4, img_s8=s8, tr_img=f_img, tr_pc=f_pc, img_up4=up4, img_up2=up2n,
+                        pc_decode_3=pc_decode_3)
+        return dict(img_norm=img_norm, pc_norm=pc_norm, img_score=img_score, pc_score=pc_score, up2=up2n,
+                    pc_decode_3=pc_decode_3)
+
+    # ------------------------------------------------------------------------------------------ matching tails
+    def _tail_val(self, core: Dict, b: int, n1: int, kpt_coors, inline_index):
+        fine_pc = ops.gather_rows(core["pc_decode_3"][b * n1:(b + 1) * n1], inline_index.to(torch.int64).contiguous())
+        err = torch.zeros(1, dtype=torch.int32, device=kpt_coors.device)
+        patch = ops.extract_patch(core["up2"], b, kpt_coors.to(torch.float32), err)
+        return patch, fine_pc, err
+
+    def _tail_test(self, core: Dict, b: int, pc_data_dict: Dict, frames: int):
+        """Test-mode matching (reference network.py:145-161): threshold loop + argmin + border mask in one
+        kernel, one host sync to learn n, then point2node / extract_patch / gathers."""
+        dev = core["pc_norm"].device
+        n4 = core["pc_norm"].shape[0] // frames
+        n1 = core["pc_decode_3"].shape[0] // frames
+        hw = self.pe_H * self.pe_W
+        key = str(dev)
+        if key not in self._thr:
+            self._thr[key] = _thresholds(dev)
+        pcn = core["pc_norm"][b * n4:(b + 1) * n4]
+        imn = core["img_norm"][b * hw:(b + 1) * hw]
+        best, _ = ops.sim_argmin(pcn, imn, 1)
+        cnt, oidx, oxy = ops.select_matches(core["pc_score"][b * n4:(b + 1) * n4], best, 1, self.pe_H, self.pe_W,
+                                            self._thr[key], 4, xy_scale=4.0)
+        n = int(cnt[0, 0].item())  # the one host sync of the frame (the reference syncs 4x per key point)
+        if n < 4:
+            raise RuntimeError("fewer than 4 matches survive every threshold (the reference would loop forever)")
+        sel = oidx[0, :n].contiguous()
+        fine_center_xy = oxy[0, :, :n].contiguous()                                      # coarse_xy * 4, :156
+        pts4 = pc_data_dict["points"][-1][b * n4:(b + 1) * n4]
+        pts1 = pc_data_dict["points"][1][b * n1:(b + 1) * n1]
+        coarse_pc_points = ops.gather_rows(pts4, sel)                                     # :152
+        cidx = ops.nn_argmin(coarse_pc_points, pts1)                                      # :153
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        patch = ops.extract_patch(core["up2"], b, fine_center_xy, err).view(n, -1, 16)    # :157-158
+        fine_pc = ops.gather_rows(core["pc_decode_3"][b * n1:(b + 1) * n1], cidx)         # :161
+        return patch, fine_pc, fine_center_xy, coarse_pc_points, sel, err
+
+    def _public(self, core: Dict, b: int, frames: int):
+        """token layout -> the reference's output layout for frame b."""
+        hw = self.pe_H * self.pe_W
+        n4 = core["pc_norm"].shape[0] // frames
+        imn = core["img_norm"][b * hw:(b + 1) * hw].view(1, self.pe_H, self.pe_W, 128)
+        img_feature_norm = ops.nhwc_to_nchw(imn)                                          # [1,128,20,64]
+        pc_feature_norm = ops.nhwc_to_nchw(core["pc_norm"][b * n4:(b + 1) * n4].view(1, 1, n4, 128)).view(128, n4)
+        img_score = core["img_score"][b * hw:(b + 1) * hw].view(1, 1, self.pe_H, self.pe_W)
+        pc_score = core["pc_score"][b * n4:(b + 1) * n4].view(1, 1, n4)
+        return img_feature_norm, pc_feature_norm, img_score, pc_score
+
+    # ------------------------------------------------------------------------------------------ public API
+    def forward(self, pc_data_dict, img, fine_center_kpt_coors, fine_xy, fine_pc_inline_index, mode, taps=None):
+        if not img.is_cuda:
+            raise RuntimeError("cofii2p_b200.CoFiI2P runs on CUDA tensors only (no CPU fallback)")
+        core = self.core(pc_data_dict, img, 1, taps)
+        n1 = core["pc_decode_3"].shape[0]
+        img_feature_norm, pc_feature_norm, img_score, pc_score = self._public(core, 0, 1)
+        if mode in ("train", "val"):
+            patch, fine_pc, err = self._tail_val(core, 0, n1, fine_center_kpt_coors, fine_pc_inline_index)
+            fine_center_xy, coarse_pc_points = None, None
+        elif mode == "test":
+            patch, fine_pc, fine_center_xy, coarse_pc_points, _, err = self._tail_test(core, 0, pc_data_dict, 1)
+        else:
+            raise ValueError(mode)
+        if int(err.item()) != 0:
+            raise AssertionError("extract_patch: a 4x4 window falls outside the feature map "
+                                 "(reference asserts patch.shape == (B,C,4,4), model/network.py:222)")
+        return (img_feature_norm, pc_feature_norm, img_score, pc_score, patch, fine_pc, fine_center_xy,
+                coarse_pc_points)
+
+    def forward_batch(self, batch: Dict, mode: str = "val"):
+        """B frames stacked along rows (see cofii2p_b200.frames.stack_frames). Returns a list of 8-tuples."""
+        B = batch["frames"]
+        core = self.core(batch["pc_data_dict"], batch["img"], B)
+        n1 = core["pc_decode_3"].shape[0] // B
+        outs, errs = [], []
+        for b in range(B):
+            pub = self._public(core, b, B)
+            if mode in ("train", "val"):
+                patch, fine_pc, err = self._tail_val(core, b, n1, batch["fine_center_kpt_coors"][b],
+                                                     batch["fine_pc_inline_index"][b])
+                outs.append(pub + (patch, fine_pc, None, None))
+            else:
+                patch, fine_pc, xy, pts, _, err = self._tail_test(core, b, batch["pc_data_dict"], B)
+                outs.append(pub + (patch, fine_pc, xy, pts))
+            errs.append(err)
+        if int(torch.stack(errs).sum().item()) != 0:
+            raise AssertionError("extract_patch: a 4x4 window falls outside the feature map")
+        return outs
+
+
+# ---------------------------------------------------------------------------------------------- helpers
+def fine_process(coarse_pc_score, coarse_pc_feature, coarse_img_feature, thrs=0.9):
+    """reference model/network.py:167-187 with the reference's tensor layouts:
+    score [1,1,N], pc feature [C,N], img feature [1,C,H,W] -> (coarse_xy [2,n], pc_inline_index [n])."""
+    _, C, H, W = coarse_img_feature.shape
+    px = ops.nchw_to_nhwc(coarse_img_feature).view(H * W, C)
+    pt = coarse_pc_feature.t().contiguous()
+    best, _ = ops.sim_argmin(pt, px, 1)
+    thr = torch.tensor([thrs], dtype=torch.float32, device=px.device)
+    cnt, oidx, oxy = ops.select_matches(torch.squeeze(coarse_pc_score), best, 1, H, W, thr, 0)
+    n = int(cnt[0, 0].item())
+    return oxy[0, :, :n].contiguous(), oidx[0, :n].contiguous()
+
+
+def extract_patch(feature_map, center_points, size=4):
+    """reference model/network.py:206-226: feature_map [B,C,H,W], center_points [2,n] -> [n,B,C,4,4]."""
+    assert size == 4
+    B = feature_map.shape[0]
+    fm = ops.nchw_to_nhwc(feature_map)
+    err = torch.zeros(1, dtype=torch.int32, device=fm.device)
+    outs = [ops.extract_patch(fm, b, center_points.to(torch.float32), err) for b in range(B)]
+    assert int(err.item()) == 0, "patch window outside the feature map"
+    return torch.stack(outs, 1)
+
+
+def square_distance(src, tgt, normalize=False):
+    """reference model/network.py:228-247 (kept for API compatibility; tiny, plain tensor algebra)."""
+    dist = -2.0 * torch.matmul(src, tgt.permute(0, 2, 1).contiguous())
+    if normalize:
+        dist += 2
+    else:
+        dist += torch.sum(src ** 2, dim=-1).unsqueeze(-1)
+        dist += torch.sum(tgt ** 2, dim=-1).unsqueeze(-2)
+    return torch.clamp(dist, min=1e-12, max=None)
+
+
+def point2node(nodes, points):
+    """reference model/network.py:250-264: nearest node of each point, fused arg-min kernel."""
+    return ops.nn_argmin(points, nodes)
+
+
+def fine_match(fine_img_feature_patch, fine_pc_inline_feature, fine_center_xy):
+    """Caller-side fine matching of evaluation/eval_all.py:99-105 (incl. its x += idx//4, y += idx%4 quirk)."""
+    idx = ops.fine_match(fine_img_feature_patch, fine_pc_inline_feature)
+    x = fine_center_xy[0] - 2 + torch.div(idx, 4, rounding_mode="floor")
+    y = fine_center_xy[1] - 2 + idx % 4
+    return idx, torch.stack([x, y], 0)
+
+
+class CoFiI2P_wrapper(nn.Module):
+    """model wrapper for efficiency analysis (reference model/network.py:267-274)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.cofii2p = CoFiI2P(opt)
+
+    def forward(self, inputs):
+        return self.cofii2p.forward(*inputs)

@@ -1,0 +1,74 @@
+"""LoFTR-style I2P transformer (reference model/transformer/transformer.py:15-103) on the B200 kernels.
+Tokens are row-major [B*L, C]; batch handling is by frame segments."""
+import copy
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from .linear_attention import FullAttention
+
+
+class LoFTREncoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, attention="full"):
+        super().__init__()
+        assert attention == "full", "the reference instantiates ATTENTION='full' (model/network.py:35)"
+        self.dim, self.nhead = d_model // nhead, nhead
+        self.q_proj = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        self.attention = FullAttention()
+        self.merge = nn.Linear(d_model, d_model, bias=False)
+        self.mlp = nn.Sequential(nn.Linear(d_model * 2, d_model * 2, bias=False), nn.ReLU(True),
+                                 nn.Linear(d_model * 2, d_model, bias=False))
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def forward(self, x, source, frames: int = 1):
+        """x [B*L,C], source [B*S,C] -> [B*L,C]."""
+        C = x.shape[1]
+        # F.normalize(q) with default dim=1 == L2 over the sequence axis per (head, channel) (reference :53)
+        q = ops.colnorm_rows(ops.gemm(x, self.q_proj.weight), frames)
+        k = ops.gemm(source, self.k_proj.weight)
+        v = ops.gemm(source, self.v_proj.weight)
+        msg = self.attention(q, k, v, frames, self.nhead)
+        cat = torch.empty((x.shape[0], 2 * C), dtype=torch.float32, device=x.device)
+        ops.gather_rows(x, None, frames=1, out=cat[:, :C])
+        # message = norm1(merge(message)) lands in the right half of the concat buffer
+        m = ops.layer_norm_rows(ops.gemm(msg, self.merge.weight), self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        ops.gather_rows(m, None, frames=1, out=cat[:, C:])
+        h = ops.gemm(cat, self.mlp[0].weight, act=ops.ACT_RELU)
+        h = ops.gemm(h, self.mlp[2].weight)
+        # x + norm2(h)
+        return ops.layer_norm_rows(h, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=x)
+
+
+class LocalFeatureTransformer(nn.Module):
+    def __init__(self, D_MODEL, NHEAD, LAYER_NAMES, ATTENTION):
+        super().__init__()
+        self.d_model, self.nhead, self.layer_names = D_MODEL, NHEAD, LAYER_NAMES
+        layer = LoFTREncoderLayer(D_MODEL, NHEAD, ATTENTION)
+        self.layers = nn.ModuleList([copy.deepcopy(layer) for _ in range(len(self.layer_names))])
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def forward(self, feat0, feat1, frames: int = 1):
+        """feat0 [B*L,C] (image tokens), feat1 [B*S,C] (point tokens). 3-D [1,L,C] inputs are accepted too."""
+        squeeze = feat0.dim() == 3
+        if squeeze:
+            assert feat0.shape[0] == 1 and feat1.shape[0] == 1
+            feat0, feat1 = feat0[0], feat1[0]
+        assert self.d_model == feat0.size(-1), "the feature number of src and transformer must be equal"
+        for layer, name in zip(self.layers, self.layer_names):
+            if name == "self":
+                feat0 = layer(feat0, feat0, frames)
+                feat1 = layer(feat1, feat1, frames)
+            elif name == "cross":
+                feat0 = layer(feat0, feat1, frames)
+                feat1 = layer(feat1, feat0, frames)  # attends to the already-updated image stream
+            else:
+                raise KeyError(name)
+        if squeeze:
+            return feat0.unsqueeze(0), feat1.unsqueeze(0)
+        return feat0, feat1

@@ -1,0 +1,361 @@
+"""Tensor-level wrappers over the C ABI (include/cofi_b200.h).
+
+PyTorch is used here for device memory and streams only: every wrapper allocates its output with
+`torch.empty`, passes raw device pointers + sizes + the current CUDA stream to libcofi_b200.so and returns
+the output tensor.  There is no fallback of any kind: CPU tensors raise, a missing library raises at import.
+All launches are CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as _libmod
+
+_lib = _libmod.load()
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
+ENGINE_FP32, ENGINE_TF32, ENGINE_TF32X3 = 0, 1, 2
+_ENGINES = {"fp32": ENGINE_FP32, "tf32": ENGINE_TF32, "tf32x3": ENGINE_TF32X3}
+_engine = ENGINE_FP32
+
+
+def set_engine(name: str) -> None:
+    """Select the contraction engine for GEMM/conv/attention/similarity: 'fp32' (SIMT, exact-order parity
+    engine), 'tf32' (tcgen05 kind::tf32), 'tf32x3' (tcgen05 3xTF32 split, fp32-grade)."""
+    global _engine
+    _engine = _ENGINES[name]
+
+
+def get_engine() -> str:
+    return {v: k for k, v in _ENGINES.items()}[_engine]
+
+
+def _chk(rc: int, name: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (code {rc}): {_libmod.last_error()}")
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (cofii2p_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    return t
+
+
+def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (cofii2p_b200 has no CPU path)")
+    if t.dtype != torch.int64:
+        raise RuntimeError(f"{name}: expected int64, got {t.dtype}")
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+def _rows(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """2-D fp32 row-major view with unit inner stride; returns (tensor, leading dimension)."""
+    _f32(t, name)
+    if t.dim() != 2:
+        raise RuntimeError(f"{name}: expected a 2-D tensor, got {tuple(t.shape)}")
+    if t.stride(1) != 1 and t.shape[1] != 1:
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    if ld < t.shape[1]:
+        t = t.contiguous()
+        ld = t.shape[1]
+    return t, ld
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------ point stream
+def pack_points(points: torch.Tensor, feats: torch.Tensor) -> torch.Tensor:
+    points = _f32(points, "points").contiguous()
+    feats, ldf = _rows(feats, "feats")
+    rows = points.shape[0]
+    out = torch.empty((rows, 4), dtype=torch.float32, device=points.device)
+    _chk(_lib.cofi_pack_points(_p(points), _p(feats), ldf, feats.shape[1], rows, _p(out), _st()), "cofi_pack_points")
+    return out
+
+
+def kpconv_aggregate(feats, s_packed, q_points, nbr, kernel_points, sigma: float, frames: int = 1):
+    feats, ldf = _rows(feats, "feats")
+    q_points = _f32(q_points, "q_points").contiguous()
+    nbr = _i64(nbr, "nbr")
+    kernel_points = _f32(kernel_points, "kernel_points").contiguous()
+    total_q, H = nbr.shape
+    Mq = total_q // frames
+    Ns = s_packed.shape[0] // frames
+    C, K = feats.shape[1], kernel_points.shape[0]
+    agg = torch.empty((total_q, K * C), dtype=torch.float32, device=feats.device)
+    cnt = torch.empty((total_q,), dtype=torch.float32, device=feats.device)
+    _chk(_lib.cofi_kpconv_aggregate(_p(feats), ldf, C, _p(s_packed), _p(q_points), _p(nbr), H, Mq, Ns, frames,
+                                    _p(kernel_points), K, float(sigma), _p(agg), _p(cnt), _st()),
+         "cofi_kpconv_aggregate")
+    return agg, cnt
+
+
+def maxpool_rows(x, nbr, frames: int = 1):
+    x, ldx = _rows(x, "x")
+    nbr = _i64(nbr, "nbr")
+    total_q, H = nbr.shape
+    out = torch.empty((total_q, x.shape[1]), dtype=torch.float32, device=x.device)
+    _chk(_lib.cofi_maxpool_rows(_p(x), ldx, x.shape[1], _p(nbr), H, total_q // frames, x.shape[0] // frames, frames,
+                                _p(out), out.stride(0), _st()), "cofi_maxpool_rows")
+    return out
+
+
+def gather_rows(x, idx: Optional[torch.Tensor], idx_stride: int = 1, frames: int = 1, out: Optional[torch.Tensor] = None,
+                rows_out: Optional[int] = None):
+    """out[i,:C] = x[idx[i*idx_stride]] per frame (idx None -> identity copy). `out` may be a column slice of a
+    wider buffer."""
+    x, ldx = _rows(x, "x")
+    C = x.shape[1]
+    if idx is not None:
+        if not idx.is_cuda or idx.dtype != torch.int64:
+            raise RuntimeError("gather_rows: idx must be a CUDA int64 tensor")
+        total_q = rows_out if rows_out is not None else (idx.numel() // idx_stride)
+    else:
+        total_q = x.shape[0]
+    if out is None:
+        out = torch.empty((total_q, C), dtype=torch.float32, device=x.device)
+    if out.stride(1) != 1:
+        raise RuntimeError("gather_rows: out must have unit inner stride")
+    _chk(_lib.cofi_gather_rows(_p(x), ldx, C, _p(idx), idx_stride, total_q // frames, x.shape[0] // frames, frames,
+                               _p(out), out.stride(0), _st()), "cofi_gather_rows")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ contractions
+def gemm(a, w, bias=None, rowdiv=None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
+         accumulate: bool = False, engine: Optional[int] = None):
+    """act((a @ w.T) / rowdiv[:,None] + bias (+ out if accumulate)); w is [N,K] (nn.Linear layout)."""
+    a, lda = _rows(a, "a")
+    w, ldw = _rows(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise RuntimeError(f"gemm: K mismatch {a.shape} x {w.shape}")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ldc = out.stride(0) if M > 1 else max(N, out.stride(0))
+    _chk(_lib.cofi_gemm(_p(a), lda, _p(w), ldw, _p(out), ldc, M, N, K, _p(bias), _p(rowdiv), int(accumulate), act,
+                        _engine if engine is None else engine, _st()), "cofi_gemm")
+    return out
+
+
+def conv2d_nhwc(x, w_packed, kh: int, kw: int, stride: int, pad: int, scale=None, shift=None, residual=None,
+                act: int = ACT_NONE, engine: Optional[int] = None):
+    """x [B,H,W,Cin] fp32 contiguous, w_packed [Cout, kh*kw*Cin]."""
+    _f32(x, "x")
+    x = x.contiguous()
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    Ho = (H + 2 * pad - kh) // stride + 1
+    Wo = (W + 2 * pad - kw) // stride + 1
+    y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        residual = residual.contiguous()
+    _chk(_lib.cofi_conv2d_nhwc(_p(x), B, H, W, Cin, _p(w_packed), Cout, kh, kw, stride, pad, _p(scale), _p(shift),
+                               _p(residual), act, _p(y), _engine if engine is None else engine, _st()),
+         "cofi_conv2d_nhwc")
+    return y
+
+
+# ------------------------------------------------------------------------------------------ normalisations
+def norm_rows(x, frames: int, groups: int, gamma=None, beta=None, eps: float = 1e-5, residual=None,
+              act: int = ACT_NONE, want_stats: bool = False):
+    x, ldx = _rows(x, "x")
+    rows, C = x.shape
+    R = rows // frames
+    y = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+    ws = _ws(_lib.cofi_norm_rows_workspace(frames, C), x.device)
+    mean = var = None
+    if want_stats:
+        mean = torch.empty((frames, groups), dtype=torch.float32, device=x.device)
+        var = torch.empty((frames, groups), dtype=torch.float32, device=x.device)
+    ldr = 0
+    if residual is not None:
+        residual, ldr = _rows(residual, "residual")
+    _chk(_lib.cofi_norm_rows(_p(x), ldx, R, C, frames, groups, _p(gamma), _p(beta), float(eps), _p(residual), ldr, act,
+                             _p(y), C, _p(ws), _p(mean), _p(var), _st()), "cofi_norm_rows")
+    if want_stats:
+        return y, mean, var
+    return y
+
+
+def affine_rows(x, scale=None, shift=None, residual=None, act: int = ACT_NONE):
+    x, ldx = _rows(x, "x")
+    rows, C = x.shape
+    y = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+    ldr = 0
+    if residual is not None:
+        residual, ldr = _rows(residual, "residual")
+    _chk(_lib.cofi_affine_rows(_p(x), ldx, rows, C, _p(scale), _p(shift), _p(residual), ldr, act, _p(y), C, _st()),
+         "cofi_affine_rows")
+    return y
+
+
+def layer_norm_rows(x, gamma, beta, eps: float = 1e-5, act: int = ACT_NONE, residual=None):
+    x, ldx = _rows(x, "x")
+    rows, C = x.shape
+    y = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+    ldr = 0
+    if residual is not None:
+        residual, ldr = _rows(residual, "residual")
+    _chk(_lib.cofi_layer_norm_rows(_p(x), ldx, rows, C, _p(gamma), _p(beta), float(eps), act, _p(residual), ldr,
+                                   _p(y), C, _st()), "cofi_layer_norm_rows")
+    return y
+
+
+def l2norm_rows(x, add=None, out: Optional[torch.Tensor] = None):
+    x, ldx = _rows(x, "x")
+    rows, C = x.shape
+    if out is None:
+        out = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+    ldadd = 0
+    if add is not None:
+        add, ldadd = _rows(add, "add")
+    _chk(_lib.cofi_l2norm_rows(_p(x), ldx, rows, C, _p(add), ldadd, _p(out), out.stride(0), _st()), "cofi_l2norm_rows")
+    return out
+
+
+def colnorm_rows(x, frames: int = 1):
+    x, ldx = _rows(x, "x")
+    rows, C = x.shape
+    y = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+    ws = _ws(_lib.cofi_colnorm_workspace(frames, C), x.device)
+    _chk(_lib.cofi_colnorm_rows(_p(x), ldx, rows // frames, C, frames, _p(ws), _p(y), C, _st()), "cofi_colnorm_rows")
+    return y
+
+
+# ------------------------------------------------------------------------------------------ image helpers
+def nchw_to_nhwc(x, cpad: Optional[int] = None):
+    _f32(x, "x")
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    cpad = C if cpad is None else cpad
+    y = torch.empty((B, H, W, cpad), dtype=torch.float32, device=x.device)
+    _chk(_lib.cofi_nchw_to_nhwc(_p(x), B, C, H, W, cpad, _p(y), _st()), "cofi_nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x):
+    _f32(x, "x")
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    _chk(_lib.cofi_nhwc_to_nchw(_p(x), B, H, W, C, _p(y), _st()), "cofi_nhwc_to_nchw")
+    return y
+
+
+def maxpool2d_3x3s2_nhwc(x):
+    _f32(x, "x")
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=torch.float32, device=x.device)
+    _chk(_lib.cofi_maxpool2d_3x3s2_nhwc(_p(x), B, H, W, C, _p(y), _st()), "cofi_maxpool2d_3x3s2_nhwc")
+    return y
+
+
+def upsample2x_cat_nhwc(x1, x2):
+    _f32(x1, "x1")
+    _f32(x2, "x2")
+    x1, x2 = x1.contiguous(), x2.contiguous()
+    B, H, W, C1 = x1.shape
+    C2 = x2.shape[3]
+    if tuple(x2.shape[:3]) != (B, 2 * H, 2 * W):
+        raise RuntimeError(f"upsample2x_cat_nhwc: shape mismatch {tuple(x1.shape)} vs {tuple(x2.shape)}")
+    y = torch.empty((B, 2 * H, 2 * W, C1 + C2), dtype=torch.float32, device=x1.device)
+    _chk(_lib.cofi_upsample2x_cat_nhwc(_p(x1), B, H, W, C1, _p(x2), C2, _p(y), _st()), "cofi_upsample2x_cat_nhwc")
+    return y
+
+
+# ------------------------------------------------------------------------------------------ transformer
+def posenc_sine(coords, d_model: int, dim_t: torch.Tensor):
+    coords = _f32(coords, "coords").contiguous()
+    rows, n_dim = coords.shape
+    out = torch.empty((rows, d_model), dtype=torch.float32, device=coords.device)
+    _chk(_lib.cofi_posenc_sine(_p(coords), rows, n_dim, d_model, _p(dim_t), _p(out), _st()), "cofi_posenc_sine")
+    return out
+
+
+def attention(q, k, v, frames: int, heads: int, scale: float, engine: Optional[int] = None):
+    q, k, v = _f32(q, "q").contiguous(), _f32(k, "k").contiguous(), _f32(v, "v").contiguous()
+    L, S = q.shape[0] // frames, k.shape[0] // frames
+    D = q.shape[1] // heads
+    out = torch.empty_like(q)
+    _chk(_lib.cofi_attention(_p(q), _p(k), _p(v), L, S, frames, heads, D, float(scale), _p(out),
+                             _engine if engine is None else engine, _st()), "cofi_attention")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ matching
+def sim_argmin(pt, px, frames: int = 1, engine: Optional[int] = None):
+    pt, ldpt = _rows(pt, "pt")
+    px, ldpx = _rows(px, "px")
+    Npt, Npx = pt.shape[0] // frames, px.shape[0] // frames
+    idx = torch.empty((pt.shape[0],), dtype=torch.int64, device=pt.device)
+    val = torch.empty((pt.shape[0],), dtype=torch.float32, device=pt.device)
+    _chk(_lib.cofi_sim_argmin(_p(pt), ldpt, _p(px), ldpx, Npt, Npx, pt.shape[1], frames, _p(idx), _p(val),
+                              ENGINE_FP32 if engine is None else engine, _st()), "cofi_sim_argmin")
+    return idx, val
+
+
+def select_matches(score, best_idx, frames: int, grid_h: int, grid_w: int, thresholds: torch.Tensor, min_count: int = 4,
+                   xy_scale: float = 1.0):
+    score = _f32(score, "score").contiguous().view(-1)
+    best_idx = _i64(best_idx, "best_idx")
+    Npt = score.numel() // frames
+    cnt = torch.empty((frames, 2), dtype=torch.int32, device=score.device)
+    oidx = torch.empty((frames, Npt), dtype=torch.int64, device=score.device)
+    oxy = torch.empty((frames, 2, Npt), dtype=torch.float32, device=score.device)
+    _chk(_lib.cofi_select_matches(_p(score), _p(best_idx), Npt, frames, grid_h, grid_w, _p(thresholds),
+                                  thresholds.numel(), min_count, float(xy_scale), _p(cnt), _p(oidx), _p(oxy), _st()),
+         "cofi_select_matches")
+    return cnt, oidx, oxy
+
+
+def nn_argmin(points, nodes):
+    points, nodes = _f32(points, "points").contiguous(), _f32(nodes, "nodes").contiguous()
+    n = points.shape[0]
+    idx = torch.empty((n,), dtype=torch.int64, device=points.device)
+    _chk(_lib.cofi_nn_argmin(_p(points), n, _p(nodes), nodes.shape[0], _p(idx), _st()), "cofi_nn_argmin")
+    return idx
+
+
+def extract_patch(map_nhwc, b: int, centers, err_flag: Optional[torch.Tensor] = None):
+    """map [B,H,W,C]; centers [2,n] fp32 (x row 0, y row 1) -> [n,C,4,4]."""
+    _f32(map_nhwc, "map")
+    map_nhwc = map_nhwc.contiguous()
+    centers = _f32(centers, "centers").contiguous()
+    _, H, W, C = map_nhwc.shape
+    n = centers.shape[1]
+    out = torch.empty((n, C, 4, 4), dtype=torch.float32, device=map_nhwc.device)
+    _chk(_lib.cofi_extract_patch(_p(map_nhwc), H, W, C, b, _p(centers), n, _p(out), _p(err_flag), _st()),
+         "cofi_extract_patch")
+    return out
+
+
+def fine_match(patch, pc):
+    """patch [n,C,16] (or [n,C,4,4]), pc [n,C] -> argmax index [n] int64 (evaluation/eval_all.py:99-102)."""
+    patch = _f32(patch, "patch").contiguous()
+    pc = _f32(pc, "pc").contiguous()
+    n, C = pc.shape
+    idx = torch.empty((n,), dtype=torch.int64, device=pc.device)
+    _chk(_lib.cofi_fine_match(_p(patch), _p(pc), n, C, _p(idx), _st()), "cofi_fine_match")
+    return idx

@@ -187,8 +187,8 @@ int cofi_sim_argmin(const float* pt, int64_t ldpt, const float* px, int64_t ldpx
  * emit those point indices in ascending order.  out_count[frame*2+0] = n, out_count[frame*2+1] = index of the
  * threshold used; out_index[frame*Npt ..]; out_xy[frame*2*Npt ..] laid out as [2][Npt] (x=col, y=row, fp32). */
 int cofi_select_matches(const float* score, const int64_t* best_idx, int64_t Npt, int frames, int gridH, int gridW,
-                        const float* thresholds, int nthr, int min_count, int32_t* out_count, int64_t* out_index,
-                        float* out_xy, void* stream);
+                        const float* thresholds, int nthr, int min_count, float xy_scale /* out_xy = pixel * xy_scale;
+                        network.py:156 multiplies by 4 */, int32_t* out_count, int64_t* out_index, float* out_xy, void* stream);
 
 /* point2node (model/network.py:250-264): idx[i] = argmin_j clamp(|p_i|^2 + |n_j|^2 - 2 p_i.n_j, 1e-12). */
 int cofi_nn_argmin(const float* points, int64_t n, const float* nodes, int64_t M, int64_t* idx, void* stream);

@@ -1,0 +1,106 @@
+"""End-to-end parity of `CoFiI2P.forward` on the CUDA path: (1) against the CPU oracle run on the same box at
+4096 points, (2) against golden outputs of the real reference (tests/golden, produced by oracle/make_golden.py)
+at 4096 and at the full 20480-point KITTI size.  Tolerance: 1e-3 relative (north star), indices exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import get_frame, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+NAMES = ["img_feature_norm", "pc_feature_norm", "coarse_img_score", "coarse_pc_score", "fine_img_feature_patch",
+         "fine_pc_inline_feature", "fine_center_xy", "coarse_pc_points"]
+
+
+def _run(model, frame, mode, taps=None):
+    from cofii2p_b200.frames import frame_to
+    from cofii2p_b200 import ops
+    ops.set_engine("fp32")
+    f = frame_to(frame, "cuda")
+    with torch.no_grad():
+        return model(f["pc_data_dict"], f["img"], f["fine_center_kpt_coors"], f["fine_xy"],
+                     f["fine_pc_inline_index"], mode, taps=taps)
+
+
+def test_forward_vs_oracle_same_box(cuda_model, seeded_sd):
+    from oracle import restate
+    frame = get_frame(0, 4096)
+    for mode in ("val", "test"):
+        with torch.no_grad():
+            ref = restate.forward(seeded_sd, frame["pc_data_dict"], frame["img"], frame["fine_center_kpt_coors"],
+                                  frame["fine_xy"], frame["fine_pc_inline_index"], mode)
+        got = _run(cuda_model, frame, mode)
+        for nm, a, b in zip(NAMES, got, ref):
+            if b is None:
+                assert a is None
+                continue
+            assert tuple(a.shape) == tuple(b.shape), (nm, a.shape, b.shape)
+            assert rel_err(a, b) < TOL, (mode, nm, rel_err(a, b))
+
+
+@pytest.mark.parametrize("seed,num_pc", [(0, 4096), (1, 4096), (0, 20480)])
+def test_forward_vs_reference_golden(cuda_model, seed, num_pc):
+    z = np.load(os.path.join(GOLD, f"frame_s{seed}_n{num_pc}.npz"))
+    frame = get_frame(seed, num_pc)
+    taps = {}
+    val = _run(cuda_model, frame, "val", taps)
+    test = _run(cuda_model, frame, "test")
+    for i, nm in enumerate(NAMES):
+        if val[i] is not None:
+            g = torch.from_numpy(z["val/" + nm])
+            assert tuple(val[i].shape) == tuple(g.shape)
+            assert rel_err(val[i], g) < TOL, ("val", nm, rel_err(val[i], g))
+    for i, nm in enumerate(NAMES[4:], 4):
+        g = torch.from_numpy(z["test/" + nm])
+        assert tuple(test[i].shape) == tuple(g.shape), (nm, test[i].shape, g.shape)
+        assert rel_err(test[i], g) < TOL, ("test", nm, rel_err(test[i], g))
+    # the selected correspondences (pixel centres, super-points) must be identical
+    assert torch.equal(test[6].cpu(), torch.from_numpy(z["test/fine_center_xy"]))
+    assert torch.equal(test[7].cpu(), torch.from_numpy(z["test/coarse_pc_points"]))
+    # strided samples of intermediates localise a failure
+    tapmap = {"pc_encoder.encoder1_2": "encoder1_2", "pc_encoder.encoder2_3": "encoder2_3",
+              "pc_encoder.encoder3_3": "encoder3_3", "pc_encoder.encoder4_3": "encoder4_3",
+              "pc_encoder.encoder5_3": "encoder5_3", "pc_encoder.decoder4": "decoder4",
+              "pc_encoder.decoder3": "decoder3", "pc_encoder.decoder2": "decoder2"}
+    for gname, tname in tapmap.items():
+        g = torch.from_numpy(z["tap/" + gname])
+        t = taps[tname].reshape(-1)
+        step = max(1, t.numel() // 4096)
+        assert rel_err(t[::step][:4096], g) < TOL, (gname, rel_err(t[::step][:4096], g))
+
+
+def test_forward_batch_matches_single(cuda_model):
+    from cofii2p_b200.frames import frame_to, stack_frames
+    from cofii2p_b200 import ops
+    ops.set_engine("fp32")
+    frames = [get_frame(s, 4096) for s in (0, 1)]
+    batch = frame_to(stack_frames(frames), "cuda")
+    with torch.no_grad():
+        outs = cuda_model.forward_batch(batch, "val")
+    for f, o in zip(frames, outs):
+        single = _run(cuda_model, f, "val")
+        for a, b in zip(o, single):
+            if b is None:
+                assert a is None
+            else:
+                assert rel_err(a, b) < 1e-6
+    with torch.no_grad():
+        outs_t = cuda_model.forward_batch(batch, "test")
+    for f, o in zip(frames, outs_t):
+        single = _run(cuda_model, f, "test")
+        assert torch.equal(o[6], single[6]) and torch.equal(o[7], single[7])
+
+
+def test_fine_match_and_eval_tail(cuda_model):
+    """pixel<->point assembly of evaluation/eval_all.py:99-105 on the test-mode outputs vs the oracle."""
+    from cofii2p_b200.model import network as net
+    from oracle import restate
+    frame = get_frame(0, 4096)
+    out = _run(cuda_model, frame, "test")
+    idx, xy = net.fine_match(out[4], out[5], out[6])
+    ridx, rxy = restate.fine_match(out[4].cpu(), out[5].cpu(), out[6].cpu())
+    assert torch.equal(idx.cpu(), ridx) and torch.equal(xy.cpu(), rxy)
