@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- I2P frames/s of the CoFiI2P coarse-to-fine correspondence hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: oracle port of the reference forward
+
+A "step" is one pass of the hot path over one batch of B=8 synthetic KITTI-shaped frames per GPU
+(BASELINE.json configs[1]: 3x160x512 image + 20480-point cloud with 5-level KNN-128 tables), `val`-style
+forward (encoders + transformer + heads + decoder + patch/feature gathers).  Inference shards by frames: with N
+GPUs every rank runs its own B frames, no data-path collective ("replicas only", weak scaling).  One JSON line
+is printed by rank 0; see DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "I2P frames/sec (20480 pts, 160x512 img)"
+UNIT = "frames/s"
+ARGS = ("pc_data_dict", "img", "fine_center_kpt_coors", "fine_xy", "fine_pc_inline_index")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cofi", choices=["cofi", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--num-pc", type=int, default=20480)
+    ap.add_argument("--engine", default=os.environ.get("COFI_ENGINE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=2, help="timed frames of the CPU baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(device):
+    from cofii2p_b200.model.network import CoFiI2P
+    from cofii2p_b200.options import Options_KITTI
+    from cofii2p_b200.weights import seeded_state_dict
+    m = CoFiI2P(Options_KITTI())
+    sd = seeded_state_dict(m, 0)
+    m.load_state_dict(sd, strict=True)
+    return m.to(device).eval(), sd
+
+
+def cpu_forward_baseline(sd, num_pc, n_frames, mode="val"):
+    """The reference forward (oracle port, incl. the dead layer3/layer4 work the reference executes) on the host
+    cores with all threads: bounded sample of the same workload, one frame per forward as the reference runs."""
+    from cofii2p_b200.frames import make_frame
+    from oracle import restate
+    torch.set_num_threads(os.cpu_count())
+    frames = [make_frame(100 + i, num_pc=num_pc, cache_dir="/tmp/cofi_frames",
+                         device="cuda" if torch.cuda.is_available() else "cpu") for i in range(n_frames + 1)]
+    times = []
+    with torch.no_grad():
+        for i, f in enumerate(frames):
+            t = time.perf_counter()
+            restate.forward(sd, *[f[k] for k in ARGS], mode, run_dead=True)
+            dt = time.perf_counter() - t
+            if i > 0:  # first frame = warm-up
+                times.append(dt)
+    return times
+
+
+# ------------------------------------------------------------------------------------------------ arms
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cofii2p_b200.model.network import CoFiI2P
+    from cofii2p_b200.options import Options_KITTI
+    from cofii2p_b200.weights import seeded_state_dict
+    from cofii2p_b200.frames import make_frame
+    from oracle import restate
+    m = CoFiI2P(Options_KITTI())
+    sd = seeded_state_dict(m, 0)
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    frames = [make_frame(100 + i, num_pc=args.num_pc, cache_dir="/tmp/cofi_frames", device=dev)
+              for i in range(min(args.steps + args.warmup, 4))]
+    with torch.no_grad():
+        for i in range(args.warmup):
+            f = frames[i % len(frames)]
+            restate.forward(sd, *[f[k] for k in ARGS], "val", run_dead=True)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            f = frames[(args.warmup + i) % len(frames)]
+            restate.forward(sd, *[f[k] for k in ARGS], "val", run_dead=True)
+        dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "reference CoFiI2P.forward(val) on CPU, one 20480-pt frame per step "
+                               "(bounded sample of configs[1])", "num_pc": args.num_pc, "frames_per_step": 1},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} frames, oracle/restate.py forward incl. dead layer3/4, "
+                                   f"torch {torch.__version__} CPU, {torch.get_num_threads()} threads"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_cofi(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from cofii2p_b200 import lib, ops
+    from cofii2p_b200.engine import InferenceEngine
+    from cofii2p_b200.frames import make_frame, stack_frames
+
+    ops.set_engine(args.engine)
+    model, sd = build_model(dev)
+    B = args.batch
+    frames = [make_frame(rank * B + i, num_pc=args.num_pc, cache_dir="/tmp/cofi_frames", device=f"cuda:{local}")
+              for i in range(B)]
+    batch = stack_frames(frames)
+    eng = InferenceEngine(model, batch, mode="val", use_graph=not args.no_graph)
+    host = eng.host_buffers(batch)
+    stream = eng.stream
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput (inputs already in HBM) -------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        eng.run()
+    clocks = ClockSampler(local)
+    ms_total = timed(eng.run, args.steps)
+    clk = clocks.stop()
+    frames_total = world * B * args.steps
+    value = frames_total / (ms_total / 1000.0)
+
+    # ---- end to end: pinned host buffers -> H2D -> forward -> D2H --------------------------------------
+    io = {"in": 0, "out": 0}
+
+    def e2e_step():
+        io["in"] = eng.upload(host)
+        eng.run()
+        io["out"] = eng.download()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = frames_total / (ms_e2e / 1000.0)
+    eng.results()  # validates the err flag / keeps the API honest
+
+    # ---- roofline of the dominant kernel family: eager pass bracketed by CUDA events per launch --------
+    hbm, tf_burst, tf_sust, peaks_src = measured_peaks()
+    with torch.no_grad(), torch.cuda.stream(stream):
+        eng._step_eager()
+        torch.cuda.synchronize(dev)
+        ops.profile_start()
+        for _ in range(2):
+            eng._step_eager()
+        prof = ops.profile_stop()
+    tot_ms = sum(d["ms"] for d in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    name, d = top
+    tensor_ops = ("cofi_gemm", "cofi_conv2d_nhwc", "cofi_attention", "cofi_sim_argmin")
+    if name in tensor_ops:
+        ach = d["flops"] / (d["ms"] / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust}
+    else:
+        ach = d["bytes"] / (d["ms"] / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(name)
+    roof.update({"traffic": traffic, "kernel": name, "launches_profiled": d["calls"],
+                 "avg_launch_us": 1000.0 * d["ms"] / d["calls"], "share_of_step": d["ms"] / tot_ms,
+                 "peak_source": peaks_src + (" (bf16 dense sustained; tf32 nominal peak is half of bf16)"
+                                             if name in tensor_ops else " (copy bandwidth)"),
+                 "by_kernel_ms_per_step": {k: round(v["ms"] / 2, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}})
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.engine], "data": "synthetic",
+        "config": {"workload": "configs[1]: single-GPU inference, batch=8 synthetic KITTI frames (3x160x512 img, "
+                               "20480x3 cloud, 5-level KNN-128 tables), val-style forward",
+                   "frames_per_gpu_per_step": B, "num_pc": args.num_pc, "engine": args.engine,
+                   "cuda_graph": not args.no_graph, "parallelism": f"replicas x{world}",
+                   "l2": "inputs larger than L2 (index tables 0.49 GB per step vs 126 MB L2)"},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io["in"], "d2h_bytes_per_step": io["out"],
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": eng.launches_per_step * args.steps,
+        "launches_per_step": eng.launches_per_step,
+        "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        times = cpu_forward_baseline(sd, args.num_pc, args.cpu_frames)
+        fps = len(times) / sum(times)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{len(times)} frames (after 1 warm-up) of the same 20480-pt workload, "
+                                          f"oracle/restate.py forward(val) incl. dead layer3/4, {torch.get_num_threads()} threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cofi(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,5 +16,5 @@ for f in *.cu; do
   objs="$objs $o"
 done
 wait
-$NVCC -shared -o $OUT $objs -lcuda -lcudart
+$NVCC -shared -o $OUT $objs -lcudart
 echo "built $(realpath $OUT)"

@@ -179,6 +179,9 @@ int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, flo
                    int K, const Epilogue& ep, int engine, cudaStream_t st);
 bool gemm_tc_supported(int64_t lda, int64_t ldw, int64_t ldc, int64_t M, int N, int K, const void* A, const void* W,
                        const void* C);
+bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW, int pad,
+                   float* y, const Epilogue& ep, int engine, cudaStream_t st);
 
 }  // namespace cofi
 
@@ -213,7 +216,8 @@ extern "C" int cofi_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, co
     COFI_REQUIRE(Cin % 4 == 0, "cofi_conv2d_nhwc: Cin=%d must be a multiple of 4 (pad the input)", Cin);
     COFI_REQUIRE((scale == nullptr) == (shift == nullptr), "cofi_conv2d_nhwc: scale and shift go together");
     COFI_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0, "cofi_conv2d_nhwc: 16-byte alignment");
-    (void)engine;  // tensor-core conv engine dispatches here once enabled
     Epilogue ep{nullptr, nullptr, scale, shift, residual, Cout, 0, act};
+    if ((engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3) && conv_tc_supported(B, H, W, Cin, Cout, KH, KW, stride, pad))
+        return conv_tc_launch(x, B, H, W, Cin, w, Cout, KH, KW, pad, y, ep, engine, (cudaStream_t)stream);
     return conv_simt_launch(x, B, H, W, Cin, w, Cout, KH, KW, stride, pad, y, ep, (cudaStream_t)stream);
 }

@@ -1,16 +1,457 @@
-// gemm_tc.cu -- tcgen05 tensor-core engines (placeholder until the TMA/TMEM kernels land in this file).
+// gemm_tc.cu -- tcgen05 tensor-core contraction engine (COFI_GEMM_TF32 / COFI_GEMM_TF32X3) for every dense
+// contraction of the hot path: nn.Linear layers, KPConv weight-apply, stride-1 NHWC convolutions.
+//
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T ),   A, W fp32 in HBM, both K-major.
+//
+// Structure (one 128 x BN output tile per CTA, warp-specialised):
+//   warp 0     TMA producer: cp.async.bulk.tensor loads of a 128x32 fp32 A tile and a BNx32 fp32 W tile per
+//              k-block into a 3-4 stage shared-memory ring (SWIZZLE_128B, 128-byte rows), mbarrier complete_tx.
+//              Convolutions use a 4-D tensor map over the NHWC activation: the A tile of a (kh,kw,ci-chunk)
+//              k-block is the box {32 ch, 64 w, 2 h, 1 b} at the shifted coordinate; TMA's out-of-bounds zero
+//              fill implements the padding, so im2col never exists.
+//   warp 1     MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) four times
+//              per k-block on UMMA shared-memory descriptors; fp32 accumulator lives in TMEM (BN columns);
+//              tcgen05.commit releases ring slots and finally signals the epilogue.
+//   warps 2-5  epilogue: tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused rowdiv / per-channel
+//              affine / bias / residual / accumulate / activation, 128-byte vector stores.
+//   warps 6-9  (TF32X3 only) operand splitters: rewrite each landed tile in place as hi = tf32-truncated value and
+//              write lo = x - hi into a second buffer; the issuer then runs hi*hi + lo*hi + hi*lo (3xTF32), which
+//              restores fp32-grade accuracy on the tensor cores.  The split is element-wise, hence swizzle-agnostic.
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace cofi {
-struct Epilogue;
-bool gemm_tc_supported(int64_t, int64_t, int64_t, int64_t, int, int, const void*, const void*, const void*) {
-    return false;
+
+struct Epilogue {  // must match gemm_simt.cu
+    const float* bias;
+    const float* rowdiv;
+    const float* colscale;
+    const float* colshift;
+    const float* residual;
+    int64_t ldres;
+    int accumulate;
+    int act;
+};
+
+namespace tc {
+
+// ------------------------------------------------------------------------------------- TMA descriptor cache
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
 }
-int gemm_tc_launch(const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int, int, const Epilogue&,
-                   int, cudaStream_t) {
-    set_error("tensor-core GEMM engine not built");
-    return COFI_EUNSUPPORTED;
+
+struct Key {
+    uint64_t v[12];
+    bool operator==(const Key& o) const {
+        for (int i = 0; i < 12; ++i)
+            if (v[i] != o.v[i]) return false;
+        return true;
+    }
+};
+struct KeyHash {
+    size_t operator()(const Key& k) const {
+        uint64_t h = 1469598103934665603ull;
+        for (int i = 0; i < 12; ++i) h = (h ^ k.v[i]) * 1099511628211ull;
+        return (size_t)h;
+    }
+};
+
+const CUtensorMap* get_tmap_f32(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                const uint32_t* box) {
+    static std::mutex mu;
+    static std::unordered_map<Key, CUtensorMap*, KeyHash> cache;
+    Key k{};
+    k.v[0] = (uint64_t)(uintptr_t)base;
+    k.v[1] = (uint64_t)rank;
+    for (int i = 0; i < rank; ++i) {
+        k.v[2 + i] = dims[i];
+        k.v[6 + i] = ((uint64_t)box[i] << 40) | (i > 0 ? strides_bytes[i - 1] : 0);
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(k);
+    if (it != cache.end()) return it->second;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return nullptr;
+    }
+    if (cache.size() > 8192) {  // pointers churn only outside CUDA graphs; bound the cache
+        for (auto& kv : cache) delete kv.second;
+        cache.clear();
+    }
+    CUtensorMap* m = new CUtensorMap;
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+    }
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        delete m;
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu box %u %u", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        return nullptr;
+    }
+    cache.emplace(k, m);
+    return m;
 }
+
+// ---------------------------------------------------------------------------------------------- kernel
+constexpr int TM = 128;   // tile rows (UMMA M)
+constexpr int TK = 32;    // fp32 elements per k-block = 128 bytes = one swizzle row
+constexpr int A_BYTES = TM * TK * 4;
+constexpr int CONV_TW = 64, CONV_TH = 2;  // conv A tile = 2 image rows x 64 pixels
+
+struct Params {
+    float* C;
+    int64_t ldc;
+    int64_t M;
+    int N;
+    int num_kb;
+    Epilogue ep;
+    // convolution geometry (CONV only)
+    int Ho, Wo, Cin, cpt /* 32-channel chunks per tap */, KW, pad, tiles_w, tiles_per_img;
+};
+
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t b = __float_as_uint(x);
+    b += 0x00000FFFu + ((b >> 13) & 1u);
+    return __uint_as_float(b & 0xFFFFE000u);
+}
+
+template <int BN, bool X3>
+struct Cfg {
+    static constexpr int B_BYTES = BN * TK * 4;
+    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int NS = (BN == 128) ? 3 : 4;
+    static constexpr int RING = STAGE * NS * (X3 ? 2 : 1);
+    static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int THREADS = X3 ? 320 : 192;
+};
+
+template <int BN, bool CONV, bool X3>
+__global__ void __launch_bounds__(Cfg<BN, X3>::THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    using C = Cfg<BN, X3>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* lo_base = smem + C::STAGE * C::NS;  // X3 only
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RING);
+    uint64_t* full = bars;                 // [NS]
+    uint64_t* empty = bars + C::NS;        // [NS]
+    uint64_t* ready = bars + 2 * C::NS;    // [NS] (X3)
+    uint64_t* tmem_full = bars + 3 * C::NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::NS + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * BN;
+    // tile origin
+    int64_t m0 = 0;
+    int cb = 0, ch0 = 0, cw0 = 0;
+    if (CONV) {
+        cb = blockIdx.x / p.tiles_per_img;
+        const int t = blockIdx.x - cb * p.tiles_per_img;
+        ch0 = (t / p.tiles_w) * CONV_TH;
+        cw0 = (t % p.tiles_w) * CONV_TW;
+    } else {
+        m0 = (int64_t)blockIdx.x * TM;
+    }
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < C::NS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&ready[s], 4);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % C::NS;
+                const uint32_t ph = (uint32_t)(kb / C::NS) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_expect_tx(&full[s], C::STAGE);
+                uint8_t* a_dst = smem + s * C::STAGE;
+                uint8_t* b_dst = a_dst + A_BYTES;
+                if (CONV) {
+                    const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
+                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    tma_load_4d(&tmA, &full[s], a_dst, cc * TK, cw0 + kw - p.pad, ch0 + kh - p.pad, cb);
+                    tma_load_2d(&tmB, &full[s], b_dst, tap * p.Cin + cc * TK, n0);
+                } else {
+                    tma_load_2d(&tmA, &full[s], a_dst, kb * TK, (int)m0);
+                    tma_load_2d(&tmB, &full[s], b_dst, kb * TK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(2 /*tf32*/, TM, BN);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % C::NS;
+                const uint32_t ph = (uint32_t)(kb / C::NS) & 1u;
+                mbar_wait(X3 ? &ready[s] : &full[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * C::STAGE);
+                const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < TK / 8; ++k) {
+                    const uint64_t ad = umma_desc_k128(a_addr + k * 32);
+                    const uint64_t bd = umma_desc_k128(b_addr + k * 32);
+                    mma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    if (X3) {
+                        const uint32_t alo = smem_u32(lo_base + s * C::STAGE);
+                        const uint64_t ald = umma_desc_k128(alo + k * 32);
+                        const uint64_t bld = umma_desc_k128(alo + A_BYTES + k * 32);
+                        mma_tf32(tmem_base, ald, bd, idesc, 1u);
+                        mma_tf32(tmem_base, ad, bld, idesc, 1u);
+                    }
+                }
+                tc_commit(&empty[s]);
+            }
+            tc_commit(tmem_full);
+        }
+    } else if (warp < 6) {
+        // ================================ epilogue ====================================
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;
+        int64_t grow;
+        bool row_ok;
+        if (CONV) {
+            const int hl = r / CONV_TW, wl = r - hl * CONV_TW;
+            grow = ((int64_t)cb * p.Ho + ch0 + hl) * p.Wo + cw0 + wl;
+            row_ok = true;  // tiles divide the image exactly (checked on the host)
+        } else {
+            grow = m0 + r;
+            row_ok = grow < p.M;
+        }
+        const Epilogue& ep = p.ep;
+        const float rd = (ep.rowdiv && row_ok) ? __ldg(ep.rowdiv + grow) : 1.0f;
+        float* crow = p.C + grow * p.ldc;
+        const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+            tmem_ld_wait();
+            const int nb = n0 + c0;
+            if (row_ok && nb < p.N) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = nb + j;
+                    float x = __uint_as_float(acc[j]);
+                    if (n < p.N) {
+                        if (ep.rowdiv) x = x / rd;
+                        if (ep.colscale) x = x * __ldg(ep.colscale + n) + __ldg(ep.colshift + n);
+                        if (ep.bias) x += __ldg(ep.bias + n);
+                        if (ep.residual) x += __ldg(ep.residual + grow * ep.ldres + n);
+                        if (ep.accumulate) x += crow[n];
+                        x = apply_act(x, ep.act);
+                    }
+                    v[j] = x;
+                }
+                if (vec_ok && nb + 32 <= p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(crow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < p.N) crow[nb + j] = v[j];
+                }
+            }
+            __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next chunk
+        }
+        tc_fence_before();
+    } else if (X3) {
+        // ================================ operand splitters (3xTF32) ==================
+        const int t = threadIdx.x - 192;  // 0..127
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int s = kb % C::NS;
+            const uint32_t ph = (uint32_t)(kb / C::NS) & 1u;
+            mbar_wait(&full[s], ph);
+            float4* hi = reinterpret_cast<float4*>(smem + s * C::STAGE);
+            float4* lo = reinterpret_cast<float4*>(lo_base + s * C::STAGE);
+#pragma unroll 4
+            for (int i = t; i < C::STAGE / 16; i += 128) {
+                const float4 x = hi[i];
+                float4 h, l;
+                // hi = x rounded to tf32 (nearest-even), lo = (x - hi) rounded to tf32: both are then exact inputs
+                // of the tensor core, so the only error left is the unbiased 2^-23 rounding of lo
+                h.x = rn_tf32(x.x);
+                h.y = rn_tf32(x.y);
+                h.z = rn_tf32(x.z);
+                h.w = rn_tf32(x.w);
+                l.x = rn_tf32(x.x - h.x);
+                l.y = rn_tf32(x.y - h.y);
+                l.z = rn_tf32(x.z - h.z);
+                l.w = rn_tf32(x.w - h.w);
+                hi[i] = h;
+                lo[i] = l;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[s]);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+template <int BN, bool CONV, bool X3>
+static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const Params& p, dim3 grid, cudaStream_t st) {
+    using C = Cfg<BN, X3>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(smem=%d): %s", C::SMEM, cudaGetErrorString(e));
+            return COFI_ECUDA;
+        }
+        attr_done = true;
+    }
+    gemm_tc_kernel<BN, CONV, X3><<<grid, C::THREADS, C::SMEM, st>>>(*a, *b, p);
+    return check_launch(CONV ? "cofi_conv2d_nhwc(tcgen05)" : "cofi_gemm(tcgen05)");
+}
+
+template <bool CONV>
+static int dispatch(const CUtensorMap* a, const CUtensorMap* b, const Params& p, int bn, bool x3, dim3 grid,
+                    cudaStream_t st) {
+    if (x3) {
+        if (bn == 32) return launch_one<32, CONV, true>(a, b, p, grid, st);
+        if (bn == 64) return launch_one<64, CONV, true>(a, b, p, grid, st);
+        return launch_one<128, CONV, true>(a, b, p, grid, st);
+    }
+    if (bn == 32) return launch_one<32, CONV, false>(a, b, p, grid, st);
+    if (bn == 64) return launch_one<64, CONV, false>(a, b, p, grid, st);
+    return launch_one<128, CONV, false>(a, b, p, grid, st);
+}
+
+static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------- GEMM entry
+bool gemm_tc_supported(int64_t lda, int64_t ldw, int64_t ldc, int64_t M, int N, int K, const void* A, const void* W,
+                       const void* C) {
+    (void)ldc;
+    (void)C;
+    if (N < 16 || M < 1 || K < 4) return false;
+    if ((lda & 3) || (ldw & 3) || (K & 3)) return false;
+    if (((uintptr_t)A & 15) || ((uintptr_t)W & 15)) return false;
+    if (M > 0x7fffffffLL) return false;
+    return tc::encode_fn() != nullptr;
+}
+
+int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
+                   int K, const Epilogue& ep, int engine, cudaStream_t st) {
+    using namespace tc;
+    const int bn = pick_bn(N);
+    uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * 4};
+    uint32_t bA[2] = {TK, TM};
+    uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldw * 4};
+    uint32_t bB[2] = {TK, (uint32_t)bn};
+    const CUtensorMap* ta = get_tmap_f32(A, 2, dA, sA, bA);
+    const CUtensorMap* tb = get_tmap_f32(W, 2, dB, sB, bB);
+    if (!ta || !tb) return COFI_ECUDA;
+    Params p{};
+    p.C = C;
+    p.ldc = ldc;
+    p.M = M;
+    p.N = N;
+    p.num_kb = (K + TK - 1) / TK;
+    p.ep = ep;
+    dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
+    return dispatch<false>(ta, tb, p, bn, engine == COFI_GEMM_TF32X3, grid, st);
+}
+
+// ---------------------------------------------------------------------------------------------- conv entry
+bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
+    (void)B;
+    const int Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
+    if (stride != 1) return false;                      // strided convs (3 of 28) stay on the SIMT engine
+    if (Wo % tc::CONV_TW || Ho % tc::CONV_TH) return false;
+    if (Cin % 4 || Cout < 16) return false;
+    return tc::encode_fn() != nullptr;
+}
+
+int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW, int pad,
+                   float* y, const Epilogue& ep, int engine, cudaStream_t st) {
+    using namespace tc;
+    const int Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
+    const int bn = pick_bn(Cout);
+    const int Ktot = KH * KW * Cin;
+    uint64_t dA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t sA[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+    uint32_t bA[4] = {TK, CONV_TW, CONV_TH, 1};
+    uint64_t dB[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sB[1] = {(uint64_t)Ktot * 4};
+    uint32_t bB[2] = {TK, (uint32_t)bn};
+    const CUtensorMap* ta = get_tmap_f32(x, 4, dA, sA, bA);
+    const CUtensorMap* tb = get_tmap_f32(w, 2, dB, sB, bB);
+    if (!ta || !tb) return COFI_ECUDA;
+    Params p{};
+    p.C = y;
+    p.ldc = Cout;
+    p.M = (int64_t)B * Ho * Wo;
+    p.N = Cout;
+    p.cpt = (Cin + TK - 1) / TK;
+    p.num_kb = KH * KW * p.cpt;
+    p.ep = ep;
+    p.Ho = Ho;
+    p.Wo = Wo;
+    p.Cin = Cin;
+    p.KW = KW;
+    p.pad = pad;
+    p.tiles_w = Wo / CONV_TW;
+    p.tiles_per_img = p.tiles_w * (Ho / CONV_TH);
+    dim3 grid((unsigned)(B * p.tiles_per_img), (unsigned)ceil_div(Cout, bn));
+    return dispatch<true>(ta, tb, p, bn, engine == COFI_GEMM_TF32X3, grid, st);
+}
+
+// attention / similarity tensor-core engines land in attention_tc.cu / sim_tc.cu
 bool attention_tc_supported(int64_t, int64_t, int, int) { return false; }
 int attention_tc_launch(const float*, const float*, const float*, int64_t, int64_t, int, int, int, float, float*,
                         cudaStream_t) {

@@ -144,12 +144,21 @@ class ImageEncoder(nn.Module):
         return [ops.nhwc_to_nchw(t) for t in self.forward_nhwc(x)]
 
 
+_FOLD = {}
+
+
 def _bn_fold(bn: nn.BatchNorm2d):
-    """eval-mode BatchNorm as per-channel (scale, shift)."""
+    """eval-mode BatchNorm as per-channel (scale, shift), cached per parameter/buffer version."""
+    v = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+         bn.weight.data_ptr())
+    hit = _FOLD.get(id(bn))
+    if hit is not None and hit[0] == v:
+        return hit[1], hit[2]
     with torch.no_grad():
-        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-        shift = bn.bias - bn.running_mean * scale
-    return scale.contiguous(), shift.contiguous()
+        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).contiguous()
+        shift = (bn.bias - bn.running_mean * scale).contiguous()
+    _FOLD[id(bn)] = (v, scale, shift)
+    return scale, shift
 
 
 def _bn_train(bn: nn.BatchNorm2d, y_nhwc, act, residual=None):

@@ -109,7 +109,10 @@ class CoFiI2P(nn.Module):
         f_pc = ops.l2norm_rows(self._pc_feature(pcs[3]), add=pc_pos)                      # :84,:114
         img_pos = self._image_pos(img.device)
         if B > 1:
-            img_pos = img_pos.repeat(B, 1)
+            key = (str(img.device), B)
+            if key not in self._img_pos:
+                self._img_pos[key] = img_pos.repeat(B, 1)
+            img_pos = self._img_pos[key]
         s8n = ops.l2norm_rows(s8.reshape(B * hw, 128))                                    # :90 (feeds decoder too)
         f_img = ops.l2norm_rows(s8.reshape(B * hw, 128), add=img_pos)                     # :113
         f_img, f_pc = self.transformer(f_img, f_pc, frames)                               # :115

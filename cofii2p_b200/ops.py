@@ -38,6 +38,53 @@ def _chk(rc: int, name: str) -> None:
         raise RuntimeError(f"{name} failed (code {rc}): {_libmod.last_error()}")
 
 
+# Optional per-op profiling (bench.py's roofline leg): when enabled every C-ABI call is bracketed by CUDA
+# events on the launching stream and annotated with the algorithmic flops / bytes of that launch.
+_prof = None
+_prof_meta = (0.0, 0.0)
+
+
+def profile_start() -> None:
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    """-> {op: dict(calls, ms, flops, bytes)} (synchronises)."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, fl, by in rec:
+        d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += fl
+        d["bytes"] += by
+    return out
+
+
+def _meta(flops: float = 0.0, nbytes: float = 0.0) -> None:
+    """Algorithmic work of the NEXT _call (consumed by the profiler only)."""
+    global _prof_meta
+    _prof_meta = (float(flops), float(nbytes))
+
+
+def _call(name: str, *args) -> None:
+    global _prof_meta
+    if _prof is None:
+        rc = getattr(_lib, name)(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(_lib, name)(*args)
+        e1.record()
+        _prof.append((name, e0, e1) + _prof_meta)
+    _prof_meta = (0.0, 0.0)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (code {rc}): {_libmod.last_error()}")
+
+
 def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (cofii2p_b200 has no CPU path)")
@@ -88,7 +135,7 @@ def pack_points(points: torch.Tensor, feats: torch.Tensor) -> torch.Tensor:
     feats, ldf = _rows(feats, "feats")
     rows = points.shape[0]
     out = torch.empty((rows, 4), dtype=torch.float32, device=points.device)
-    _chk(_lib.cofi_pack_points(_p(points), _p(feats), ldf, feats.shape[1], rows, _p(out), _st()), "cofi_pack_points")
+    _call("cofi_pack_points", _p(points), _p(feats), ldf, feats.shape[1], rows, _p(out), _st())
     return out
 
 
@@ -103,9 +150,12 @@ def kpconv_aggregate(feats, s_packed, q_points, nbr, kernel_points, sigma: float
     C, K = feats.shape[1], kernel_points.shape[0]
     agg = torch.empty((total_q, K * C), dtype=torch.float32, device=feats.device)
     cnt = torch.empty((total_q,), dtype=torch.float32, device=feats.device)
-    _chk(_lib.cofi_kpconv_aggregate(_p(feats), ldf, C, _p(s_packed), _p(q_points), _p(nbr), H, Mq, Ns, frames,
-                                    _p(kernel_points), K, float(sigma), _p(agg), _p(cnt), _st()),
-         "cofi_kpconv_aggregate")
+    # compulsory HBM bytes (aggregate stage): indices + features + packed coords + queries + output
+    _meta(2.0 * total_q * K * H * C,
+          8.0 * total_q * H + 4.0 * feats.shape[0] * C + 16.0 * s_packed.shape[0] + 12.0 * total_q
+          + 4.0 * total_q * K * C + 4.0 * total_q)
+    _call("cofi_kpconv_aggregate", _p(feats), ldf, C, _p(s_packed), _p(q_points), _p(nbr), H, Mq, Ns, frames,
+                                    _p(kernel_points), K, float(sigma), _p(agg), _p(cnt), _st())
     return agg, cnt
 
 
@@ -114,8 +164,8 @@ def maxpool_rows(x, nbr, frames: int = 1):
     nbr = _i64(nbr, "nbr")
     total_q, H = nbr.shape
     out = torch.empty((total_q, x.shape[1]), dtype=torch.float32, device=x.device)
-    _chk(_lib.cofi_maxpool_rows(_p(x), ldx, x.shape[1], _p(nbr), H, total_q // frames, x.shape[0] // frames, frames,
-                                _p(out), out.stride(0), _st()), "cofi_maxpool_rows")
+    _call("cofi_maxpool_rows", _p(x), ldx, x.shape[1], _p(nbr), H, total_q // frames, x.shape[0] // frames, frames,
+                                _p(out), out.stride(0), _st())
     return out
 
 
@@ -135,8 +185,8 @@ def gather_rows(x, idx: Optional[torch.Tensor], idx_stride: int = 1, frames: int
         out = torch.empty((total_q, C), dtype=torch.float32, device=x.device)
     if out.stride(1) != 1:
         raise RuntimeError("gather_rows: out must have unit inner stride")
-    _chk(_lib.cofi_gather_rows(_p(x), ldx, C, _p(idx), idx_stride, total_q // frames, x.shape[0] // frames, frames,
-                               _p(out), out.stride(0), _st()), "cofi_gather_rows")
+    _call("cofi_gather_rows", _p(x), ldx, C, _p(idx), idx_stride, total_q // frames, x.shape[0] // frames, frames,
+                               _p(out), out.stride(0), _st())
     return out
 
 
@@ -153,8 +203,9 @@ def gemm(a, w, bias=None, rowdiv=None, act: int = ACT_NONE, out: Optional[torch.
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     ldc = out.stride(0) if M > 1 else max(N, out.stride(0))
-    _chk(_lib.cofi_gemm(_p(a), lda, _p(w), ldw, _p(out), ldc, M, N, K, _p(bias), _p(rowdiv), int(accumulate), act,
-                        _engine if engine is None else engine, _st()), "cofi_gemm")
+    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
+    _call("cofi_gemm", _p(a), lda, _p(w), ldw, _p(out), ldc, M, N, K, _p(bias), _p(rowdiv), int(accumulate), act,
+                        _engine if engine is None else engine, _st())
     return out
 
 
@@ -170,9 +221,9 @@ def conv2d_nhwc(x, w_packed, kh: int, kw: int, stride: int, pad: int, scale=None
     y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
     if residual is not None:
         residual = residual.contiguous()
-    _chk(_lib.cofi_conv2d_nhwc(_p(x), B, H, W, Cin, _p(w_packed), Cout, kh, kw, stride, pad, _p(scale), _p(shift),
-                               _p(residual), act, _p(y), _engine if engine is None else engine, _st()),
-         "cofi_conv2d_nhwc")
+    _meta(2.0 * B * Ho * Wo * Cout * kh * kw * Cin, 4.0 * (x.numel() + w_packed.numel() + y.numel()))
+    _call("cofi_conv2d_nhwc", _p(x), B, H, W, Cin, _p(w_packed), Cout, kh, kw, stride, pad, _p(scale), _p(shift),
+                               _p(residual), act, _p(y), _engine if engine is None else engine, _st())
     return y
 
 
@@ -191,8 +242,9 @@ def norm_rows(x, frames: int, groups: int, gamma=None, beta=None, eps: float = 1
     ldr = 0
     if residual is not None:
         residual, ldr = _rows(residual, "residual")
-    _chk(_lib.cofi_norm_rows(_p(x), ldx, R, C, frames, groups, _p(gamma), _p(beta), float(eps), _p(residual), ldr, act,
-                             _p(y), C, _p(ws), _p(mean), _p(var), _st()), "cofi_norm_rows")
+    _meta(8.0 * rows * C, 4.0 * rows * C * (3 + (residual is not None)))
+    _call("cofi_norm_rows", _p(x), ldx, R, C, frames, groups, _p(gamma), _p(beta), float(eps), _p(residual), ldr, act,
+                             _p(y), C, _p(ws), _p(mean), _p(var), _st())
     if want_stats:
         return y, mean, var
     return y
@@ -205,8 +257,7 @@ def affine_rows(x, scale=None, shift=None, residual=None, act: int = ACT_NONE):
     ldr = 0
     if residual is not None:
         residual, ldr = _rows(residual, "residual")
-    _chk(_lib.cofi_affine_rows(_p(x), ldx, rows, C, _p(scale), _p(shift), _p(residual), ldr, act, _p(y), C, _st()),
-         "cofi_affine_rows")
+    _call("cofi_affine_rows", _p(x), ldx, rows, C, _p(scale), _p(shift), _p(residual), ldr, act, _p(y), C, _st())
     return y
 
 
@@ -217,8 +268,8 @@ def layer_norm_rows(x, gamma, beta, eps: float = 1e-5, act: int = ACT_NONE, resi
     ldr = 0
     if residual is not None:
         residual, ldr = _rows(residual, "residual")
-    _chk(_lib.cofi_layer_norm_rows(_p(x), ldx, rows, C, _p(gamma), _p(beta), float(eps), act, _p(residual), ldr,
-                                   _p(y), C, _st()), "cofi_layer_norm_rows")
+    _call("cofi_layer_norm_rows", _p(x), ldx, rows, C, _p(gamma), _p(beta), float(eps), act, _p(residual), ldr,
+                                   _p(y), C, _st())
     return y
 
 
@@ -230,7 +281,7 @@ def l2norm_rows(x, add=None, out: Optional[torch.Tensor] = None):
     ldadd = 0
     if add is not None:
         add, ldadd = _rows(add, "add")
-    _chk(_lib.cofi_l2norm_rows(_p(x), ldx, rows, C, _p(add), ldadd, _p(out), out.stride(0), _st()), "cofi_l2norm_rows")
+    _call("cofi_l2norm_rows", _p(x), ldx, rows, C, _p(add), ldadd, _p(out), out.stride(0), _st())
     return out
 
 
@@ -239,7 +290,7 @@ def colnorm_rows(x, frames: int = 1):
     rows, C = x.shape
     y = torch.empty((rows, C), dtype=torch.float32, device=x.device)
     ws = _ws(_lib.cofi_colnorm_workspace(frames, C), x.device)
-    _chk(_lib.cofi_colnorm_rows(_p(x), ldx, rows // frames, C, frames, _p(ws), _p(y), C, _st()), "cofi_colnorm_rows")
+    _call("cofi_colnorm_rows", _p(x), ldx, rows // frames, C, frames, _p(ws), _p(y), C, _st())
     return y
 
 
@@ -250,7 +301,7 @@ def nchw_to_nhwc(x, cpad: Optional[int] = None):
     B, C, H, W = x.shape
     cpad = C if cpad is None else cpad
     y = torch.empty((B, H, W, cpad), dtype=torch.float32, device=x.device)
-    _chk(_lib.cofi_nchw_to_nhwc(_p(x), B, C, H, W, cpad, _p(y), _st()), "cofi_nchw_to_nhwc")
+    _call("cofi_nchw_to_nhwc", _p(x), B, C, H, W, cpad, _p(y), _st())
     return y
 
 
@@ -259,7 +310,7 @@ def nhwc_to_nchw(x):
     x = x.contiguous()
     B, H, W, C = x.shape
     y = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
-    _chk(_lib.cofi_nhwc_to_nchw(_p(x), B, H, W, C, _p(y), _st()), "cofi_nhwc_to_nchw")
+    _call("cofi_nhwc_to_nchw", _p(x), B, H, W, C, _p(y), _st())
     return y
 
 
@@ -268,7 +319,7 @@ def maxpool2d_3x3s2_nhwc(x):
     x = x.contiguous()
     B, H, W, C = x.shape
     y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=torch.float32, device=x.device)
-    _chk(_lib.cofi_maxpool2d_3x3s2_nhwc(_p(x), B, H, W, C, _p(y), _st()), "cofi_maxpool2d_3x3s2_nhwc")
+    _call("cofi_maxpool2d_3x3s2_nhwc", _p(x), B, H, W, C, _p(y), _st())
     return y
 
 
@@ -281,7 +332,7 @@ def upsample2x_cat_nhwc(x1, x2):
     if tuple(x2.shape[:3]) != (B, 2 * H, 2 * W):
         raise RuntimeError(f"upsample2x_cat_nhwc: shape mismatch {tuple(x1.shape)} vs {tuple(x2.shape)}")
     y = torch.empty((B, 2 * H, 2 * W, C1 + C2), dtype=torch.float32, device=x1.device)
-    _chk(_lib.cofi_upsample2x_cat_nhwc(_p(x1), B, H, W, C1, _p(x2), C2, _p(y), _st()), "cofi_upsample2x_cat_nhwc")
+    _call("cofi_upsample2x_cat_nhwc", _p(x1), B, H, W, C1, _p(x2), C2, _p(y), _st())
     return y
 
 
@@ -290,7 +341,7 @@ def posenc_sine(coords, d_model: int, dim_t: torch.Tensor):
     coords = _f32(coords, "coords").contiguous()
     rows, n_dim = coords.shape
     out = torch.empty((rows, d_model), dtype=torch.float32, device=coords.device)
-    _chk(_lib.cofi_posenc_sine(_p(coords), rows, n_dim, d_model, _p(dim_t), _p(out), _st()), "cofi_posenc_sine")
+    _call("cofi_posenc_sine", _p(coords), rows, n_dim, d_model, _p(dim_t), _p(out), _st())
     return out
 
 
@@ -299,8 +350,9 @@ def attention(q, k, v, frames: int, heads: int, scale: float, engine: Optional[i
     L, S = q.shape[0] // frames, k.shape[0] // frames
     D = q.shape[1] // heads
     out = torch.empty_like(q)
-    _chk(_lib.cofi_attention(_p(q), _p(k), _p(v), L, S, frames, heads, D, float(scale), _p(out),
-                             _engine if engine is None else engine, _st()), "cofi_attention")
+    _meta(4.0 * frames * L * S * heads * D, 4.0 * (2 * q.numel() + 2 * k.numel()))
+    _call("cofi_attention", _p(q), _p(k), _p(v), L, S, frames, heads, D, float(scale), _p(out),
+                             _engine if engine is None else engine, _st())
     return out
 
 
@@ -311,8 +363,9 @@ def sim_argmin(pt, px, frames: int = 1, engine: Optional[int] = None):
     Npt, Npx = pt.shape[0] // frames, px.shape[0] // frames
     idx = torch.empty((pt.shape[0],), dtype=torch.int64, device=pt.device)
     val = torch.empty((pt.shape[0],), dtype=torch.float32, device=pt.device)
-    _chk(_lib.cofi_sim_argmin(_p(pt), ldpt, _p(px), ldpx, Npt, Npx, pt.shape[1], frames, _p(idx), _p(val),
-                              ENGINE_FP32 if engine is None else engine, _st()), "cofi_sim_argmin")
+    _meta(2.0 * frames * Npt * Npx * pt.shape[1], 4.0 * (pt.numel() + px.numel()) + 12.0 * pt.shape[0])
+    _call("cofi_sim_argmin", _p(pt), ldpt, _p(px), ldpx, Npt, Npx, pt.shape[1], frames, _p(idx), _p(val),
+                              ENGINE_FP32 if engine is None else engine, _st())
     return idx, val
 
 
@@ -324,9 +377,8 @@ def select_matches(score, best_idx, frames: int, grid_h: int, grid_w: int, thres
     cnt = torch.empty((frames, 2), dtype=torch.int32, device=score.device)
     oidx = torch.empty((frames, Npt), dtype=torch.int64, device=score.device)
     oxy = torch.empty((frames, 2, Npt), dtype=torch.float32, device=score.device)
-    _chk(_lib.cofi_select_matches(_p(score), _p(best_idx), Npt, frames, grid_h, grid_w, _p(thresholds),
-                                  thresholds.numel(), min_count, float(xy_scale), _p(cnt), _p(oidx), _p(oxy), _st()),
-         "cofi_select_matches")
+    _call("cofi_select_matches", _p(score), _p(best_idx), Npt, frames, grid_h, grid_w, _p(thresholds),
+                                  thresholds.numel(), min_count, float(xy_scale), _p(cnt), _p(oidx), _p(oxy), _st())
     return cnt, oidx, oxy
 
 
@@ -334,7 +386,7 @@ def nn_argmin(points, nodes):
     points, nodes = _f32(points, "points").contiguous(), _f32(nodes, "nodes").contiguous()
     n = points.shape[0]
     idx = torch.empty((n,), dtype=torch.int64, device=points.device)
-    _chk(_lib.cofi_nn_argmin(_p(points), n, _p(nodes), nodes.shape[0], _p(idx), _st()), "cofi_nn_argmin")
+    _call("cofi_nn_argmin", _p(points), n, _p(nodes), nodes.shape[0], _p(idx), _st())
     return idx
 
 
@@ -346,8 +398,7 @@ def extract_patch(map_nhwc, b: int, centers, err_flag: Optional[torch.Tensor] = 
     _, H, W, C = map_nhwc.shape
     n = centers.shape[1]
     out = torch.empty((n, C, 4, 4), dtype=torch.float32, device=map_nhwc.device)
-    _chk(_lib.cofi_extract_patch(_p(map_nhwc), H, W, C, b, _p(centers), n, _p(out), _p(err_flag), _st()),
-         "cofi_extract_patch")
+    _call("cofi_extract_patch", _p(map_nhwc), H, W, C, b, _p(centers), n, _p(out), _p(err_flag), _st())
     return out
 
 
@@ -357,5 +408,5 @@ def fine_match(patch, pc):
     pc = _f32(pc, "pc").contiguous()
     n, C = pc.shape
     idx = torch.empty((n,), dtype=torch.int64, device=pc.device)
-    _chk(_lib.cofi_fine_match(_p(patch), _p(pc), n, C, _p(idx), _st()), "cofi_fine_match")
+    _call("cofi_fine_match", _p(patch), _p(pc), n, C, _p(idx), _st())
     return idx

@@ -104,3 +104,29 @@ def test_fine_match_and_eval_tail(cuda_model):
     idx, xy = net.fine_match(out[4], out[5], out[6])
     ridx, rxy = restate.fine_match(out[4].cpu(), out[5].cpu(), out[6].cpu())
     assert torch.equal(idx.cpu(), ridx) and torch.equal(xy.cpu(), rxy)
+
+
+def test_engine_graph_matches_forward(cuda_model):
+    """The CUDA-graph inference engine (static buffers, B=2) reproduces the eager single-frame forward, also after
+    new inputs are uploaded from pinned host memory."""
+    from cofii2p_b200.engine import InferenceEngine
+    from cofii2p_b200.frames import stack_frames
+    from cofii2p_b200 import ops
+    ops.set_engine("fp32")
+    fa = [get_frame(s, 4096) for s in (0, 1)]
+    fb = [get_frame(s, 4096) for s in (1, 0)]
+    eng = InferenceEngine(cuda_model, stack_frames(fa), use_graph=True)
+    assert eng.graph is not None and eng.launches_per_step > 100
+    for frames in (fa, fb):
+        nb = eng.upload(eng.host_buffers(stack_frames(frames)))
+        assert nb > 0
+        eng.run()
+        eng.download()
+        outs = eng.results()
+        for f, o in zip(frames, outs):
+            single = _run(cuda_model, f, "val")
+            for a, b in zip(o, single):
+                if b is None:
+                    assert a is None
+                else:
+                    assert rel_err(a, b) < 1e-6

@@ -1,0 +1,99 @@
+"""tcgen05 engines (TF32 and 3xTF32) against torch fp32 / the CPU oracle.  Tolerances are stated per engine:
+TF32 keeps 10 mantissa bits per operand -> 5e-3 of the output scale per contraction; 3xTF32 -> 2e-5 (fp32-grade)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import get_frame, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = {"tf32": 5e-3, "tf32x3": 2e-5}
+
+
+def tol_for(engine, k):
+    """3xTF32 removes the operand rounding; what is left is the tensor core's truncating fp32 accumulator, whose
+    bias grows linearly with the accumulation length (measured 7.7e-9 * K on B200, tools/err_probe.py)."""
+    return TOL[engine] if engine == "tf32" else 2e-6 + 1.2e-8 * k
+
+
+@pytest.mark.parametrize("engine", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("m,n,k", [(1000, 64, 60), (513, 32, 480), (2000, 128, 32), (300, 1024, 3072), (4096, 2048, 7680),
+                                   (77, 200, 256), (128, 48, 36), (20480, 32, 64), (1280, 256, 128)])
+def test_gemm_tc(engine, m, n, k):
+    from cofii2p_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn((m, k), generator=g)
+    w = torch.randn((n, k), generator=g) / math.sqrt(k)
+    b = torch.randn((n,), generator=g)
+    rd = torch.randint(1, 60, (m,), generator=g).float()
+    ref = F.leaky_relu(F.linear(a.double(), w.double()).float() / rd[:, None] + b, 0.1)
+    ops.set_engine(engine)
+    try:
+        got = ops.gemm(a.cuda(), w.cuda(), bias=b.cuda(), rowdiv=rd.cuda(), act=ops.ACT_LRELU)
+        assert rel_err(got, ref) < tol_for(engine, k), rel_err(got, ref)
+        base = torch.randn((m, n), generator=g)
+        got2 = ops.gemm(a.cuda(), w.cuda(), out=base.clone().cuda(), accumulate=True)
+        assert rel_err(got2, base + F.linear(a.double(), w.double()).float()) < tol_for(engine, k)
+        # strided A (view into a wider buffer) and strided output
+        wide = torch.randn((m, k + 36), generator=g).cuda()
+        outw = torch.zeros((m, n + 8), device="cuda")
+        ops.gemm(wide[:, 4:4 + k], w.cuda(), out=outw[:, 4:4 + n])
+        assert rel_err(outw[:, 4:4 + n], F.linear(wide[:, 4:4 + k].cpu().double(), w.double()).float()) < tol_for(engine, k)
+        assert float(outw[:, :4].abs().max()) == 0 and float(outw[:, 4 + n:].abs().max()) == 0
+    finally:
+        ops.set_engine("fp32")
+
+
+@pytest.mark.parametrize("engine", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("cin,cout,k,pad,h,w", [(64, 64, 3, 1, 20, 64), (128, 128, 3, 1, 20, 64), (192, 128, 3, 1, 40, 128),
+                                                (192, 64, 3, 1, 8, 256), (64, 32, 1, 0, 4, 64)])
+def test_conv_tc(engine, cin, cout, k, pad, h, w):
+    from cofii2p_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout + k + h)
+    x = torch.randn((2, cin, h, w), generator=g)
+    wt = torch.randn((cout, cin, k, k), generator=g) / math.sqrt(cin * k * k)
+    sc, sh = torch.randn((cout,), generator=g), torch.randn((cout,), generator=g)
+    ref_c = F.conv2d(x.double(), wt.double(), None, 1, pad).float()
+    res = torch.randn(ref_c.shape, generator=g)
+    ref = F.relu(ref_c * sc[None, :, None, None] + sh[None, :, None, None] + res)
+    ops.set_engine(engine)
+    try:
+        xn = ops.nchw_to_nhwc(x.cuda())
+        wp = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().cuda()
+        y = ops.conv2d_nhwc(xn, wp, k, k, 1, pad, scale=sc.cuda(), shift=sh.cuda(), residual=ops.nchw_to_nhwc(res.cuda()),
+                            act=ops.ACT_RELU)
+        assert rel_err(ops.nhwc_to_nchw(y), ref) < tol_for(engine, cin * k * k), rel_err(ops.nhwc_to_nchw(y), ref)
+    finally:
+        ops.set_engine("fp32")
+
+
+@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-3), ("tf32", 5e-2)])
+def test_forward_golden_tc(cuda_model, engine, tol):
+    """Full forward on the tensor-core engines vs the real-reference golden (20480 points).
+    3xTF32 must meet the north-star tolerance (1e-3) with identical correspondences; plain TF32 is the throughput
+    mode and is reported with its own (looser) error bound."""
+    import os
+    import numpy as np
+    from cofii2p_b200 import ops
+    from cofii2p_b200.frames import frame_to
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frame_s0_n20480.npz"))
+    f = frame_to(get_frame(0, 20480), "cuda")
+    ops.set_engine(engine)
+    try:
+        with torch.no_grad():
+            val = cuda_model(f["pc_data_dict"], f["img"], f["fine_center_kpt_coors"], f["fine_xy"],
+                             f["fine_pc_inline_index"], "val")
+            test = cuda_model(f["pc_data_dict"], f["img"], f["fine_center_kpt_coors"], f["fine_xy"],
+                              f["fine_pc_inline_index"], "test")
+    finally:
+        ops.set_engine("fp32")
+    names = ["img_feature_norm", "pc_feature_norm", "coarse_img_score", "coarse_pc_score", "fine_img_feature_patch",
+             "fine_pc_inline_feature"]
+    errs = {nm: rel_err(val[i], torch.from_numpy(z["val/" + nm])) for i, nm in enumerate(names)}
+    print(engine, errs)
+    assert max(errs.values()) < tol, errs
+    if engine == "tf32x3":
+        assert torch.equal(test[6].cpu(), torch.from_numpy(z["test/fine_center_xy"]))
+        assert torch.equal(test[7].cpu(), torch.from_numpy(z["test/coarse_pc_points"]))
