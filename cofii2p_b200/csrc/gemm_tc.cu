@@ -17,6 +17,8 @@
 //   warps 6-9  (TF32X3 only) operand splitters: rewrite each landed tile in place as hi = tf32-truncated value and
 //              write lo = x - hi into a second buffer; the issuer then runs hi*hi + lo*hi + hi*lo (3xTF32), which
 //              restores fp32-grade accuracy on the tensor cores.  The split is element-wise, hence swizzle-agnostic.
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -135,6 +137,7 @@ struct Params {
     Epilogue ep;
     // convolution geometry (CONV only)
     int Ho, Wo, Cin, cpt /* 32-channel chunks per tap */, KW, pad, tiles_w, tiles_per_img;
+    int dbg;  // COFI_TC_DEBUG bits (perf triage only): 1 = skip global stores, 2 = skip TMA+MMA
 };
 
 __device__ __forceinline__ float rn_tf32(float x) {
@@ -149,7 +152,7 @@ struct Cfg {
     static constexpr int STAGE = A_BYTES + B_BYTES;
     static constexpr int NS = (BN == 128) ? 3 : 4;
     static constexpr int RING = STAGE * NS * (X3 ? 2 : 1);
-    static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */ + 2 * BN * 4 /* epilogue vectors */;
     static constexpr int THREADS = X3 ? 320 : 192;
 };
 
@@ -166,6 +169,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* ready = bars + 2 * C::NS;    // [NS] (X3)
     uint64_t* tmem_full = bars + 3 * C::NS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::NS + 1);
+    float* s_scale = reinterpret_cast<float*>(smem + C::RING + 256);  // [BN] per-column multiplier
+    float* s_shift = s_scale + BN;                                   // [BN] per-column shift (+bias)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
@@ -200,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg & 2)) {
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 const int s = kb % C::NS;
                 const uint32_t ph = (uint32_t)(kb / C::NS) & 1u;
@@ -221,7 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg & 2)) {
             constexpr uint32_t idesc = umma_idesc(2 /*tf32*/, TM, BN);
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 const int s = kb % C::NS;
@@ -249,7 +254,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp < 6) {
         // ================================ epilogue ====================================
-        mbar_wait(tmem_full, 0);
+        {   // stage the per-column epilogue vectors while the main loop runs
+            const int t = threadIdx.x - 64;  // 0..127
+            if (t < BN) {
+                const int n = n0 + t;
+                float sc = 1.0f, sh = 0.0f;
+                if (n < p.N) {
+                    if (p.ep.colscale) {
+                        sc = __ldg(p.ep.colscale + n);
+                        sh = __ldg(p.ep.colshift + n);
+                    }
+                    if (p.ep.bias) sh += __ldg(p.ep.bias + n);
+                }
+                s_scale[t] = sc;
+                s_shift[t] = sh;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (!(p.dbg & 2)) mbar_wait(tmem_full, 0);
         tc_fence_after();
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;
@@ -264,39 +286,115 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             row_ok = grow < p.M;
         }
         const Epilogue& ep = p.ep;
-        const float rd = (ep.rowdiv && row_ok) ? __ldg(ep.rowdiv + grow) : 1.0f;
+        const bool has_rd = ep.rowdiv != nullptr, has_res = ep.residual != nullptr, has_acc = ep.accumulate != 0;
+        const float rd = (has_rd && row_ok) ? __ldg(ep.rowdiv + grow) : 1.0f;
         float* crow = p.C + grow * p.ldc;
+        const float* rrow = has_res ? ep.residual + grow * ep.ldres : nullptr;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        float* stage = reinterpret_cast<float*>(smem) + q * (32 * 36);  // ring is idle once tmem_full fired
+        const bool rvec_ok = has_res && ((ep.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t acc[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
             tmem_ld_wait();
             const int nb = n0 + c0;
-            if (row_ok && nb < p.N) {
+            if (row_ok && nb < p.N && !(p.dbg & 4)) {
+                const bool full = nb + 32 <= p.N;
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = nb + j;
-                    float x = __uint_as_float(acc[j]);
-                    if (n < p.N) {
-                        if (ep.rowdiv) x = x / rd;
-                        if (ep.colscale) x = x * __ldg(ep.colscale + n) + __ldg(ep.colshift + n);
-                        if (ep.bias) x += __ldg(ep.bias + n);
-                        if (ep.residual) x += __ldg(ep.residual + grow * ep.ldres + n);
-                        if (ep.accumulate) x += crow[n];
-                        x = apply_act(x, ep.act);
-                    }
-                    v[j] = x;
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                if (has_rd) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] / rd;
                 }
-                if (vec_ok && nb + 32 <= p.N) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(crow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
+                for (int j = 0; j < 32; j += 4) {  // per-column scale/shift(+bias) staged in shared memory
+                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
+                    v[j] = fmaf(v[j], sc.x, sh.x);
+                    v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+                    v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+                    v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+                }
+                if (has_res) {
+                    if (rvec_ok && full) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nb + j < p.N) crow[nb + j] = v[j];
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + nb + j));
+                            v[j] += r4.x;
+                            v[j + 1] += r4.y;
+                            v[j + 2] += r4.z;
+                            v[j + 3] += r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.N) v[j] += __ldg(rrow + nb + j);
+                    }
+                }
+                if (has_acc) {
+                    if (vec_ok && full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(crow + nb + j);
+                            v[j] += r4.x;
+                            v[j + 1] += r4.y;
+                            v[j + 2] += r4.z;
+                            v[j + 3] += r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.N) v[j] += crow[nb + j];
+                    }
+                }
+                if (ep.act == COFI_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                } else if (ep.act == COFI_ACT_LRELU01) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * 0.1f;
+                } else if (ep.act == COFI_ACT_SIGMOID) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+                }
+                // fallthrough to the staged store below
+                float* st = stage + lane * 36;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(st + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            __syncwarp();
+            // transposed write-out: 8 lanes cover the 32 columns (128 B) of one row, 4 rows per instruction, so every
+            // store instruction writes four full 128-byte lines (the per-thread-row layout would scatter 16-byte pieces)
+            if (nb < p.N && !(p.dbg & 5)) {
+                const bool full = nb + 32 <= p.N;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + (lane >> 3), cc = (lane & 7) * 4;
+                    const int rt = q * 32 + rr;  // row inside the 128-row tile
+                    int64_t g2;
+                    bool ok2;
+                    if (CONV) {
+                        const int hl = rt / CONV_TW, wl = rt - hl * CONV_TW;
+                        g2 = ((int64_t)cb * p.Ho + ch0 + hl) * p.Wo + cw0 + wl;
+                        ok2 = true;
+                    } else {
+                        g2 = m0 + rt;
+                        ok2 = g2 < p.M;
+                    }
+                    if (!ok2) continue;
+                    const float4 val = *reinterpret_cast<const float4*>(stage + rr * 36 + cc);
+                    float* dst = p.C + g2 * p.ldc + nb + cc;
+                    if (vec_ok && full) {
+                        *reinterpret_cast<float4*>(dst) = val;
+                    } else {
+                        if (nb + cc < p.N) dst[0] = val.x;
+                        if (nb + cc + 1 < p.N) dst[1] = val.y;
+                        if (nb + cc + 2 < p.N) dst[2] = val.z;
+                        if (nb + cc + 3 < p.N) dst[3] = val.w;
+                    }
                 }
             }
             __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next chunk
@@ -370,6 +468,15 @@ static int dispatch(const CUtensorMap* a, const CUtensorMap* b, const Params& p,
     return launch_one<128, CONV, false>(a, b, p, grid, st);
 }
 
+static int tc_debug() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("COFI_TC_DEBUG");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
 
 }  // namespace tc
@@ -404,6 +511,7 @@ int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, flo
     p.N = N;
     p.num_kb = (K + TK - 1) / TK;
     p.ep = ep;
+    p.dbg = tc_debug();
     dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
     return dispatch<false>(ta, tb, p, bn, engine == COFI_GEMM_TF32X3, grid, st);
 }

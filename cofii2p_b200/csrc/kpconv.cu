@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128)
 kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, const float4* __restrict__ s_packed,
                         const float* __restrict__ q_points, const int64_t* __restrict__ nbr, int H, int64_t Mq,
                         int64_t Ns, int64_t total_q, const float* __restrict__ kernel_points, int K, float sigma,
-                        float* __restrict__ agg, float* __restrict__ cnt_out) {
+                        float reach2, float* __restrict__ agg, float* __restrict__ cnt_out) {
     __shared__ float skp[kMaxKP * 3];
     if (threadIdx.x < K * 3) skp[threadIdx.x] = kernel_points[threadIdx.x];
     __syncthreads();
@@ -72,17 +72,18 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
     for (int j = 0; j < 4; ++j) {
         const int h = j * 32 + lane;
         int64_t id = (h < H) ? __ldg(nbr + m * H + h) : Ns;
+        idx[j] = -1;
+        rx[j] = ry[j] = rz[j] = 0.0f;
         if (id >= 0 && id < Ns) {
             const float4 p = __ldg(sp + id);
             rx[j] = p.x - qx;  // neighbours - q_points, reference kpconv.py:93
             ry[j] = p.y - qy;
             rz[j] = p.z - qz;
             cnt += p.w;
-            idx[j] = (int)id;
-        } else {  // shadow neighbour: point at 1e6, zero feature -> zero influence
-            rx[j] = ry[j] = rz[j] = 0.0f;
-            idx[j] = -1;
-        }
+            // exact cull: a neighbour farther from the query than max|kp| + sigma has zero influence for every
+            // kernel point (triangle inequality; the margin absorbs fp32 rounding), so it never enters the k loop
+            if (rx[j] * rx[j] + ry[j] * ry[j] + rz[j] * rz[j] <= reach2) idx[j] = (int)id;
+        }  // else shadow neighbour: point at 1e6, zero feature -> zero influence
     }
     cnt = warp_sum(cnt);
     if (lane == 0) cnt_out[m] = fmaxf(cnt, 1.0f);
@@ -236,8 +237,8 @@ extern "C" int cofi_pack_points(const float* points, const float* feats, int64_t
 
 extern "C" int cofi_kpconv_aggregate(const float* feats, int64_t ldf, int C, const float* s_packed,
                                      const float* q_points, const int64_t* nbr, int H, int64_t Mq, int64_t Ns,
-                                     int frames, const float* kernel_points, int K, float sigma, float* agg,
-                                     float* cnt, void* stream) {
+                                     int frames, const float* kernel_points, int K, float sigma, float kp_reach,
+                                     float* agg, float* cnt, void* stream) {
     COFI_REQUIRE(feats && s_packed && q_points && nbr && kernel_points && agg && cnt,
                  "cofi_kpconv_aggregate: null pointer");
     COFI_REQUIRE(H > 0 && H <= 128, "cofi_kpconv_aggregate: H=%d must be in 1..128", H);
@@ -246,13 +247,16 @@ extern "C" int cofi_kpconv_aggregate(const float* feats, int64_t ldf, int C, con
     COFI_REQUIRE(Mq >= 0 && Ns > 0 && frames > 0 && ldf >= C, "cofi_kpconv_aggregate: bad sizes");
     const int64_t total = Mq * frames;
     if (total == 0) return COFI_OK;
+    // cull radius: (max|kp| + sigma) with a 1e-3 relative margin; kp_reach <= 0 disables the cull
+    const float reach = kp_reach > 0.0f ? (kp_reach + sigma) * 1.001f : 1e18f;
+    const float reach2 = reach * reach;
     const int wpb = 4;
     const dim3 grid((unsigned)ceil_div(total, wpb)), block(wpb * 32);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* sp = reinterpret_cast<const float4*>(s_packed);
 #define LAUNCH(VEC, NCH)                                                                                          \
     kpconv_aggregate_kernel<VEC, NCH><<<grid, block, 0, st>>>(feats, ldf, C, sp, q_points, nbr, H, Mq, Ns, total, \
-                                                              kernel_points, K, sigma, agg, cnt)
+                                                              kernel_points, K, sigma, reach2, agg, cnt)
     if (C <= 32) {
         LAUNCH(1, 1);
     } else if (C == 64) {

@@ -18,7 +18,7 @@ SIGNATURES = {
     "cofi_last_error": (ctypes.c_char_p, []),
     "cofi_launch_count": (_l, []),
     "cofi_pack_points": (_i, [_vp, _vp, _l, _i, _l, _vp, _vp]),
-    "cofi_kpconv_aggregate": (_i, [_vp, _l, _i, _vp, _vp, _vp, _i, _l, _l, _i, _vp, _i, _f, _vp, _vp, _vp]),
+    "cofi_kpconv_aggregate": (_i, [_vp, _l, _i, _vp, _vp, _vp, _i, _l, _l, _i, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "cofi_maxpool_rows": (_i, [_vp, _l, _i, _vp, _i, _l, _l, _i, _vp, _l, _vp]),
     "cofi_gather_rows": (_i, [_vp, _l, _i, _vp, _l, _l, _l, _i, _vp, _l, _vp]),
     "cofi_gemm": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _i, _i, _vp]),

@@ -27,6 +27,7 @@ class KPConv(nn.Module):
                              torch.from_numpy(load_kernels(radius, kernel_size, dimension=dimension, fixed="center")).float())
         self._wt = None
         self._wt_version = None
+        self._reach = None
 
     def reset_parameters(self):
         nn.init.kaiming_uniform_(self.weights, a=math.sqrt(5))
@@ -44,9 +45,16 @@ class KPConv(nn.Module):
             self._wt_version = v
         return self._wt
 
+    def kp_reach(self) -> float:
+        """max_k |kernel_points[k]| (host scalar, cached): lets the kernel cull neighbours that no kernel point reaches."""
+        v = (self.kernel_points._version, self.kernel_points.data_ptr())
+        if self._reach is None or self._reach[0] != v:
+            self._reach = (v, float(self.kernel_points.detach().norm(dim=1).max().item()))
+        return self._reach[1]
+
     def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1):
         """s_feats [B*N,Cin], q_points [B*M,3], s_points [B*N,3], neighbor_indices [B*M,H] -> [B*M,Cout]."""
         packed = ops.pack_points(s_points, s_feats)
         agg, cnt = ops.kpconv_aggregate(s_feats, packed, q_points, neighbor_indices, self.kernel_points, self.sigma,
-                                        frames)
+                                        frames, self.kp_reach())
         return ops.gemm(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt)

@@ -139,7 +139,8 @@ def pack_points(points: torch.Tensor, feats: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def kpconv_aggregate(feats, s_packed, q_points, nbr, kernel_points, sigma: float, frames: int = 1):
+def kpconv_aggregate(feats, s_packed, q_points, nbr, kernel_points, sigma: float, frames: int = 1,
+                     kp_reach: float = 0.0):
     feats, ldf = _rows(feats, "feats")
     q_points = _f32(q_points, "q_points").contiguous()
     nbr = _i64(nbr, "nbr")
@@ -155,7 +156,7 @@ def kpconv_aggregate(feats, s_packed, q_points, nbr, kernel_points, sigma: float
           8.0 * total_q * H + 4.0 * feats.shape[0] * C + 16.0 * s_packed.shape[0] + 12.0 * total_q
           + 4.0 * total_q * K * C + 4.0 * total_q)
     _call("cofi_kpconv_aggregate", _p(feats), ldf, C, _p(s_packed), _p(q_points), _p(nbr), H, Mq, Ns, frames,
-                                    _p(kernel_points), K, float(sigma), _p(agg), _p(cnt), _st())
+                                    _p(kernel_points), K, float(sigma), float(kp_reach), _p(agg), _p(cnt), _st())
     return agg, cnt
 
 

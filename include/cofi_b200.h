@@ -71,6 +71,8 @@ int cofi_kpconv_aggregate(const float* feats, int64_t ldf, int C,
                           const int64_t* nbr /* [frames*Mq,H] */, int H,
                           int64_t Mq, int64_t Ns, int frames,
                           const float* kernel_points /* [K,3] */, int K, float sigma,
+                          float kp_reach /* max_k |kernel_points[k]| (host-computed); neighbours beyond
+                                            kp_reach + sigma are culled exactly; <= 0 disables */,
                           float* agg /* [frames*Mq, K*C] */, float* cnt /* [frames*Mq] */, void* stream);
 
 /* out[m,c] = max_h x[nbr[m,h], c] with shadow rows = 0 (model/kpconv/functional.py:53-66). */

@@ -62,6 +62,10 @@ def test_kpconv(cin, cout, n, m, h, sigma, extent, shadow):
     ref = restate.kpconv(feats, q_pts, s_pts, nbr, w, b, kp, sigma)
     packed = ops.pack_points(s_pts.cuda(), feats.cuda())
     agg, cnt = ops.kpconv_aggregate(feats.cuda(), packed, q_pts.cuda(), nbr.cuda(), kp.cuda(), sigma, 1)
+    # the exact far-neighbour cull must not change a single bit
+    agg2, cnt2 = ops.kpconv_aggregate(feats.cuda(), packed, q_pts.cuda(), nbr.cuda(), kp.cuda(), sigma, 1,
+                                      kp_reach=float(kp.norm(dim=1).max()))
+    assert torch.equal(agg, agg2) and torch.equal(cnt, cnt2)
     wt = w.reshape(-1, cout).t().contiguous().cuda()
     out = ops.gemm(agg, wt, bias=b.cuda(), rowdiv=cnt)
     assert rel_err(out, ref) < TOL
