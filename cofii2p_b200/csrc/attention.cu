@@ -98,7 +98,7 @@ attention_simt_kernel(const float* __restrict__ q, const float* __restrict__ k, 
     }
 }
 
-int attention_tc_launch(const float* q, const float* k, const float* v, int64_t L, int64_t S, int frames, int heads,
+int attention_tc_launch(const float* q, const float* k, const float* vt, int64_t L, int64_t S, int frames, int heads,
                         int D, float scale, float* out, cudaStream_t st);
 bool attention_tc_supported(int64_t L, int64_t S, int heads, int D);
 
@@ -114,9 +114,22 @@ extern "C" int cofi_attention(const float* q, const float* k, const float* v, in
     COFI_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
                      ((uintptr_t)out % 16) == 0,
                  "cofi_attention: 16-byte alignment required");
-    if (engine != COFI_GEMM_FP32 && attention_tc_supported(L, S, heads, D))
-        return attention_tc_launch(q, k, v, L, S, frames, heads, D, scale, out, (cudaStream_t)stream);
+    (void)engine;  // row-major V: fp32 SIMT engine; the tcgen05 engine is cofi_attention_vt (K-major V^T operand)
     dim3 grid((unsigned)ceil_div(L, AT_TQ), heads, frames);
     attention_simt_kernel<<<grid, AT_TQ, 0, (cudaStream_t)stream>>>(q, k, v, L, S, heads, scale, out);
     return check_launch("cofi_attention(fp32)");
+}
+
+extern "C" int cofi_attention_vt(const float* q, const float* k, const float* vt, int64_t L, int64_t S, int frames,
+                                 int heads, int D, float scale, float* out, void* stream) {
+    COFI_REQUIRE(q && k && vt && out, "cofi_attention_vt: null pointer");
+    COFI_REQUIRE(L > 0 && S > 0 && frames > 0 && heads > 0, "cofi_attention_vt: bad shape");
+    COFI_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)vt % 16) == 0 &&
+                     ((uintptr_t)out % 16) == 0,
+                 "cofi_attention_vt: 16-byte alignment required");
+    if (!attention_tc_supported(L, S, heads, D)) {
+        set_error("cofi_attention_vt: unsupported shape (D=%d must be 32, frames*S*4 bytes must be 16-byte aligned)", D);
+        return COFI_EUNSUPPORTED;
+    }
+    return attention_tc_launch(q, k, vt, L, S, frames, heads, D, scale, out, (cudaStream_t)stream);
 }

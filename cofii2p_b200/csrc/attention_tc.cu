@@ -1,0 +1,256 @@
+// attention_tc.cu -- tcgen05 flash attention for the LoFTR encoder layer
+// (reference model/transformer/linear_attention.py:69-77: softmax(Q K^T / sqrt(D)) V per head; D = 32).
+//
+// One CTA = 128 query rows of one (frame, head).  Keys are walked in tiles of 128:
+//   warp 0   TMA producer: Q tile once; per key tile the K tile [128 keys x 32] and the V^T tile
+//            [32 d x 128 keys] (V^T comes straight out of the v_proj GEMM with swapped operands, so both MMA
+//            operands are K-major and use the same SWIZZLE_128B descriptors as the GEMM engine).
+//   warp 1   MMA issuer:  S[128x128] = Q K^T  (kind::tf32, 4 x K=8) into TMEM columns [0,128);
+//            O_t[128x32] = P V  (16 x K=8) into TMEM columns [128,160), fresh accumulator per tile.
+//   warps 2-5 softmax: one query row per thread. tcgen05.ld of the S row, online max / exp / sum in fp32
+//            registers, P written to shared memory in the swizzled K-major operand layout (tf32), then the
+//            tile's O_t is read back from TMEM and folded into the running output in registers with the usual
+//            exp(m_old - m_new) correction -- no TMEM stores and no rescaling of TMEM accumulators.
+// The [L,S,heads] score tensor of the reference never exists; HBM traffic is Q, K, V once per CTA row.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cofi {
+namespace tc {
+
+constexpr int AQ = 128;   // queries per CTA
+constexpr int AK = 128;   // keys per tile
+constexpr int AD = 32;    // head dim
+constexpr int Q_BYTES = AQ * AD * 4;        // 16 KB
+constexpr int K_BYTES = AK * AD * 4;        // 16 KB
+constexpr int VT_BYTES = AD * AK * 4;       // 16 KB = 4 chunks of [32 d rows x 32 keys]
+constexpr int P_BYTES = AQ * AK * 4;        // 64 KB = 4 k-blocks of [128 rows x 32 keys]
+constexpr int KV_STAGES = 2;
+constexpr int ATT_SMEM = Q_BYTES + KV_STAGES * (K_BYTES + VT_BYTES) + P_BYTES + 1024 + 256;
+constexpr int TMEM_COLS = 256;              // S: [0,128)  O_t: [128,160)
+
+struct AttParams {
+    float* out;
+    int64_t L, S;
+    int heads;
+    float scale;
+    int num_tiles;
+};
+
+__global__ void __launch_bounds__(192)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmVt, const AttParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + Q_BYTES;                                   // [stage][K | Vt]
+    uint8_t* sP = sKV + KV_STAGES * (K_BYTES + VT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;            // [2]
+    uint64_t* kv_empty = bars + 3;           // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* o_full = bars + 7;
+    uint64_t* o_free = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.y, frame = blockIdx.z;
+    const int64_t q0 = (int64_t)blockIdx.x * AQ;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmVt);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < KV_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 4);
+        mbar_init(o_full, 1);
+        mbar_init(o_free, 4);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, Q_BYTES);
+            tma_load_2d(&tmQ, q_full, sQ, head * AD, (int)(frame * p.L + q0));
+            for (int t = 0; t < p.num_tiles; ++t) {
+                const int s = t % KV_STAGES;
+                const uint32_t ph = (uint32_t)(t / KV_STAGES) & 1u;
+                mbar_wait(&kv_empty[s], ph ^ 1u);
+                mbar_expect_tx(&kv_full[s], K_BYTES + VT_BYTES);
+                uint8_t* kd = sKV + s * (K_BYTES + VT_BYTES);
+                const int key0 = (int)(frame * p.S + (int64_t)t * AK);
+                tma_load_2d(&tmK, &kv_full[s], kd, head * AD, key0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)  // V^T chunk c: rows head*32..+31, keys key0+32c..+31
+                    tma_load_2d(&tmVt, &kv_full[s], kd + K_BYTES + c * (AD * 32 * 4), key0 + c * 32, head * AD);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc(2, AQ, AK);   // 128 x 128
+            constexpr uint32_t idesc_o = umma_idesc(2, AQ, AD);   // 128 x 32
+            mbar_wait(q_full, 0);
+            const uint32_t q_addr = smem_u32(sQ);
+            const uint32_t p_addr = smem_u32(sP);
+            for (int t = 0; t < p.num_tiles; ++t) {
+                const int s = t % KV_STAGES;
+                const uint32_t ph = (uint32_t)(t / KV_STAGES) & 1u;
+                const uint32_t tp = (uint32_t)t & 1u;
+                mbar_wait(&kv_full[s], ph);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sKV + s * (K_BYTES + VT_BYTES));
+                const uint32_t v_addr = k_addr + K_BYTES;
+                // S = Q K^T   (S columns are free: P(t-1) was published, i.e. S(t-1) fully read)
+#pragma unroll
+                for (int k = 0; k < AD / 8; ++k)
+                    mma_tf32(tmem_S, umma_desc_k128(q_addr + k * 32), umma_desc_k128(k_addr + k * 32), idesc_s,
+                             k != 0 ? 1u : 0u);
+                tc_commit(s_full);
+                // O_t = P V
+                mbar_wait(p_full, tp);
+                if (t > 0) mbar_wait(o_free, tp ^ 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma_tf32(tmem_O, umma_desc_k128(p_addr + c * (AQ * 32 * 4) + k * 32),
+                                 umma_desc_k128(v_addr + c * (AD * 32 * 4) + k * 32), idesc_o, (c | k) != 0 ? 1u : 0u);
+                tc_commit(o_full);
+                tc_commit(&kv_empty[s]);
+            }
+        }
+    } else {
+        // ================================ softmax / output ================================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                 // query row inside the tile == TMEM lane
+        const bool row_ok = q0 + r < p.L;
+        float o[AD];
+#pragma unroll
+        for (int d = 0; d < AD; ++d) o[d] = 0.0f;
+        float mrun = -INFINITY, lrun = 0.0f;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        uint8_t* prow = sP + r * 128;                // row r of each [128 x 32] k-block (128-byte rows)
+        const int sw = r & 7;                        // SWIZZLE_128B: 16-byte chunk index ^= (row & 7)
+        for (int t = 0; t < p.num_tiles; ++t) {
+            const uint32_t tp = (uint32_t)t & 1u;
+            const int valid = (int)((p.S - (int64_t)t * AK) < AK ? (p.S - (int64_t)t * AK) : AK);
+            mbar_wait(s_full, tp);
+            tc_fence_after();
+            float sv[AK];
+            float tmax = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_S + lane_off + c * 32, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float x = (c * 32 + j < valid) ? __uint_as_float(raw[j]) * p.scale : -INFINITY;
+                    sv[c * 32 + j] = x;
+                    tmax = fmaxf(tmax, x);
+                }
+            }
+            const float mnew = fmaxf(mrun, tmax);
+            const float corr = expf(mrun - mnew);
+            float psum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint8_t* blk = prow + c * (AQ * 32 * 4);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 pv;
+                    pv.x = expf(sv[c * 32 + j] - mnew);
+                    pv.y = expf(sv[c * 32 + j + 1] - mnew);
+                    pv.z = expf(sv[c * 32 + j + 2] - mnew);
+                    pv.w = expf(sv[c * 32 + j + 3] - mnew);
+                    psum += (pv.x + pv.y) + (pv.z + pv.w);
+                    *reinterpret_cast<float4*>(blk + ((((j >> 2) ^ sw) & 7) << 4)) = pv;
+                }
+            }
+            lrun = lrun * corr + psum;
+            mrun = mnew;
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+            // fold O_t into the running output
+            mbar_wait(o_full, tp);
+            tc_fence_after();
+            uint32_t raw[32];
+            tmem_ld32(tmem_O + lane_off, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < AD; ++d) o[d] = fmaf(o[d], corr, __uint_as_float(raw[d]));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_free);
+        }
+        if (row_ok) {
+            const float inv = 1.0f / lrun;
+            float* op = p.out + ((int64_t)frame * p.L + q0 + r) * ((int64_t)p.heads * AD) + head * AD;
+#pragma unroll
+            for (int d = 0; d < AD; d += 4)
+                *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace tc
+
+bool attention_tc_supported(int64_t L, int64_t S, int heads, int D) {
+    uint64_t d[2] = {4, 4}, st[1] = {16};
+    (void)d;
+    (void)st;
+    return D == tc::AD && heads >= 1 && L >= 1 && S >= 1 && (S % 4 == 0);
+}
+
+// vt: V^T [heads*D, frames*S] row-major (keys contiguous): produced by the v_proj GEMM with swapped operands
+int attention_tc_launch(const float* q, const float* k, const float* vt, int64_t L, int64_t S, int frames, int heads,
+                        int D, float scale, float* out, cudaStream_t st) {
+    using namespace tc;
+    const int64_t C = (int64_t)heads * D;
+    uint64_t dq[2] = {(uint64_t)C, (uint64_t)(frames * L)}, sq[1] = {(uint64_t)C * 4};
+    uint32_t bq[2] = {AD, AQ};
+    uint64_t dk[2] = {(uint64_t)C, (uint64_t)(frames * S)}, sk[1] = {(uint64_t)C * 4};
+    uint32_t bk[2] = {AD, AK};
+    uint64_t dv[2] = {(uint64_t)(frames * S), (uint64_t)C}, sv[1] = {(uint64_t)(frames * S) * 4};
+    uint32_t bv[2] = {32, AD};
+    const CUtensorMap* tq = get_tmap_f32(q, 2, dq, sq, bq);
+    const CUtensorMap* tk = get_tmap_f32(k, 2, dk, sk, bk);
+    const CUtensorMap* tv = get_tmap_f32(vt, 2, dv, sv, bv);
+    if (!tq || !tk || !tv) return COFI_ECUDA;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attention smem=%d): %s", ATT_SMEM, cudaGetErrorString(e));
+            return COFI_ECUDA;
+        }
+        attr_done = true;
+    }
+    AttParams p{out, L, S, heads, scale, (int)ceil_div(S, AK)};
+    dim3 grid((unsigned)ceil_div(L, AQ), heads, frames);
+    attention_tc_kernel<<<grid, 192, ATT_SMEM, st>>>(*tq, *tk, *tv, p);
+    return check_launch("cofi_attention(tcgen05)");
+}
+
+}  // namespace cofi

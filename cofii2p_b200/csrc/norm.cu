@@ -34,12 +34,12 @@ norm_stats_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C, do
 
 // one block per (frame, group): reduce partials -> mean, rstd
 __global__ void __launch_bounds__(128)
-norm_finalize_kernel(const double* __restrict__ partials, int64_t R, int C, int G, float eps,
+norm_finalize_kernel(const double* __restrict__ partials, int nchunks, int64_t R, int C, int G, float eps,
                      float2* __restrict__ mean_rstd, float* __restrict__ mean_out, float* __restrict__ var_out) {
     const int frame = blockIdx.y, g = blockIdx.x;
     const int gs = C / G;
     double s = 0.0, ss = 0.0;
-    for (int t = threadIdx.x; t < kStatChunks * gs; t += blockDim.x) {
+    for (int t = threadIdx.x; t < nchunks * gs; t += blockDim.x) {
         const int chunk = t / gs, c = g * gs + (t - chunk * gs);
         const double* o = partials + (((int64_t)frame * kStatChunks + chunk) * C + c) * 2;
         s += o[0];
@@ -101,6 +101,87 @@ affine_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C
         if (scale) v = v * __ldg(scale + c) + __ldg(shift + c);
         if (residual) v += __ldg(residual + row * ldr + c);
         y[row * ldy + c] = apply_act(v, act);
+    }
+}
+
+// ---- vectorised variants (C % 4 == 0): thread = (4-channel chunk, row lane); no integer divisions in the loop ----
+// block = (TX, TY) with TX * TY = 256; grid = (row chunks <= kStatChunks, frames, channel-chunk groups)
+__global__ void __launch_bounds__(256)
+norm_stats_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C, double* __restrict__ partials) {
+    __shared__ double red[256][8 + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+    const int c4 = blockIdx.z * TX + tx;
+    const int frame = blockIdx.y, chunk = blockIdx.x;
+    const int64_t rows_per = (R + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = chunk * rows_per;
+    const int64_t r1 = (r0 + rows_per < R) ? r0 + rows_per : R;
+    double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    if (c4 * 4 < C) {
+        const float* p = x + ((int64_t)frame * R) * ldx + c4 * 4;
+        for (int64_t r = r0 + ty; r < r1; r += TY) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + r * ldx));
+            s[0] += v.x; ss[0] += (double)v.x * v.x;
+            s[1] += v.y; ss[1] += (double)v.y * v.y;
+            s[2] += v.z; ss[2] += (double)v.z * v.z;
+            s[3] += v.w; ss[3] += (double)v.w * v.w;
+        }
+    }
+    const int tid = ty * TX + tx;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        red[tid][i] = s[i];
+        red[tid][4 + i] = ss[i];
+    }
+    __syncthreads();
+    if (ty == 0 && c4 * 4 < C) {
+        for (int y = 1; y < TY; ++y)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s[i] += red[y * TX + tx][i];
+                ss[i] += red[y * TX + tx][4 + i];
+            }
+        double* o = partials + (((int64_t)frame * kStatChunks + chunk) * C + c4 * 4) * 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[2 * i] = s[i];
+            o[2 * i + 1] = ss[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+norm_apply_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C, int G,
+                      const float2* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ residual, int64_t ldr, int act,
+                      float* __restrict__ y, int64_t ldy) {
+    const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+    const int c4 = blockIdx.z * TX + tx;
+    if (c4 * 4 >= C) return;
+    const int frame = blockIdx.y;
+    const int gs = C / G;
+    float mean[4], a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c4 * 4 + i;
+        const float2 ms = __ldg(mean_rstd + (int64_t)frame * G + c / gs);
+        mean[i] = ms.x;
+        a[i] = gamma ? ms.y * __ldg(gamma + c) : ms.y;
+        b[i] = beta ? __ldg(beta + c) : 0.0f;
+    }
+    const int64_t rows_per = (R + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = blockIdx.x * rows_per;
+    const int64_t r1 = (r0 + rows_per < R) ? r0 + rows_per : R;
+    const int64_t base = (int64_t)frame * R;
+    for (int64_t r = r0 + ty; r < r1; r += TY) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (base + r) * ldx + c4 * 4));
+        float o[4] = {(v.x - mean[0]) * a[0] + b[0], (v.y - mean[1]) * a[1] + b[1], (v.z - mean[2]) * a[2] + b[2],
+                      (v.w - mean[3]) * a[3] + b[3]};
+        if (residual) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + (base + r) * ldr + c4 * 4));
+            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+        }
+        *reinterpret_cast<float4*>(y + (base + r) * ldy + c4 * 4) =
+            make_float4(apply_act(o[0], act), apply_act(o[1], act), apply_act(o[2], act), apply_act(o[3], act));
     }
 }
 
@@ -219,7 +300,20 @@ extern "C" int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int
     cudaStream_t st = (cudaStream_t)stream;
     double* part = reinterpret_cast<double*>(partials);
     float2* mr = reinterpret_cast<float2*>(part + (int64_t)frames * kStatChunks * C * 2);
-    {
+    const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && (!residual || ldr % 4 == 0) &&
+                     ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!residual || (uintptr_t)residual % 16 == 0);
+    const int C4 = C / 4;
+    int TX = 1;
+    while (TX < C4 && TX < 32) TX <<= 1;
+    const int TY = 256 / TX;
+    const unsigned zgroups = (unsigned)ceil_div(C4 > 0 ? C4 : 1, TX);
+    int stat_chunks = (int)(R / (4 * TY) < 1 ? 1 : (R / (4 * TY) > kStatChunks ? kStatChunks : R / (4 * TY)));
+    if (vec) {
+        dim3 grid((unsigned)stat_chunks, frames, zgroups), block(TX, TY);
+        norm_stats_vec_kernel<<<grid, block, 0, st>>>(x, ldx, R, C, part);
+        int rc = check_launch("cofi_norm_rows(stats)");
+        if (rc) return rc;
+    } else {
         const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32));
         dim3 grid((unsigned)ceil_div(C, threads), kStatChunks, frames);
         norm_stats_kernel<<<grid, threads, 0, st>>>(x, ldx, R, C, part);
@@ -228,11 +322,21 @@ extern "C" int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int
     }
     {
         dim3 grid(G, frames);
-        norm_finalize_kernel<<<grid, 128, 0, st>>>(part, R, C, G, eps, mr, mean_out, var_out);
+        norm_finalize_kernel<<<grid, 128, 0, st>>>(part, vec ? stat_chunks : kStatChunks, R, C, G, eps, mr, mean_out, var_out);
         int rc = check_launch("cofi_norm_rows(finalize)");
         if (rc) return rc;
     }
     const int64_t rows = R * frames;
+    if (vec) {
+        // enough row chunks to fill the machine: ~4 CTAs per SM overall
+        int64_t want = (148 * 4) / ((int64_t)frames * zgroups);
+        if (want < 1) want = 1;
+        int64_t maxc = ceil_div(R, TY);
+        if (want > maxc) want = maxc;
+        dim3 grid((unsigned)want, frames, zgroups), block(TX, TY);
+        norm_apply_vec_kernel<<<grid, block, 0, st>>>(x, ldx, R, C, G, mr, gamma, beta, residual, ldr, act, y, ldy);
+        return check_launch("cofi_norm_rows(apply)");
+    }
     norm_apply_kernel<<<ew_blocks(rows * C, 256), 256, 0, st>>>(x, ldx, R, C, G, mr, gamma, beta, residual, ldr, act,
                                                                 y, ldy, rows);
     return check_launch("cofi_norm_rows(apply)");

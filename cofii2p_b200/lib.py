@@ -36,6 +36,7 @@ SIGNATURES = {
     "cofi_upsample2x_cat_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "cofi_posenc_sine": (_i, [_vp, _l, _i, _i, _vp, _vp, _vp]),
     "cofi_attention": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _i, _vp]),
+    "cofi_attention_vt": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp]),
     "cofi_sim_argmin": (_i, [_vp, _l, _vp, _l, _l, _l, _i, _i, _vp, _vp, _i, _vp]),
     "cofi_select_matches": (_i, [_vp, _vp, _l, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "cofi_nn_argmin": (_i, [_vp, _l, _vp, _l, _vp, _vp]),

@@ -30,8 +30,13 @@ class LoFTREncoderLayer(nn.Module):
         # F.normalize(q) with default dim=1 == L2 over the sequence axis per (head, channel) (reference :53)
         q = ops.colnorm_rows(ops.gemm(x, self.q_proj.weight), frames)
         k = ops.gemm(source, self.k_proj.weight)
-        v = ops.gemm(source, self.v_proj.weight)
-        msg = self.attention(q, k, v, frames, self.nhead)
+        if ops.engine_id() == ops.ENGINE_TF32 and (source.shape[0] % 4 == 0):
+            # tcgen05 flash attention: V is produced directly as V^T (K-major operand) by swapping GEMM operands
+            vt = ops.gemm(self.v_proj.weight, source)
+            msg = ops.attention_vt(q, k, vt, frames, self.nhead, 1.0 / self.dim ** 0.5)
+        else:
+            v = ops.gemm(source, self.v_proj.weight)
+            msg = self.attention(q, k, v, frames, self.nhead)
         cat = torch.empty((x.shape[0], 2 * C), dtype=torch.float32, device=x.device)
         ops.gather_rows(x, None, frames=1, out=cat[:, :C])
         # message = norm1(merge(message)) lands in the right half of the concat buffer

@@ -357,6 +357,21 @@ def attention(q, k, v, frames: int, heads: int, scale: float, engine: Optional[i
     return out
 
 
+def attention_vt(q, k, vt, frames: int, heads: int, scale: float):
+    """tcgen05 flash attention; vt = V^T [heads*D, frames*S] (from gemm(W_v, source))."""
+    q, k, vt = _f32(q, "q").contiguous(), _f32(k, "k").contiguous(), _f32(vt, "vt").contiguous()
+    L, S = q.shape[0] // frames, k.shape[0] // frames
+    D = q.shape[1] // heads
+    out = torch.empty_like(q)
+    _meta(4.0 * frames * L * S * heads * D, 4.0 * (2 * q.numel() + 2 * k.numel()))
+    _call("cofi_attention_vt", _p(q), _p(k), _p(vt), L, S, frames, heads, D, float(scale), _p(out), _st())
+    return out
+
+
+def engine_id() -> int:
+    return _engine
+
+
 # ------------------------------------------------------------------------------------------ matching
 def sim_argmin(pt, px, frames: int = 1, engine: Optional[int] = None):
     pt, ldpt = _rows(pt, "pt")

@@ -172,6 +172,11 @@ int cofi_posenc_sine(const float* coords, int64_t rows, int n_dim, int d_model,
  * (model/transformer/linear_attention.py:69-77).  q [frames*L, heads*D], k,v [frames*S, heads*D]. D == 32. */
 int cofi_attention(const float* q, const float* k, const float* v, int64_t L, int64_t S, int frames, int heads,
                    int D, float scale, float* out, int engine, void* stream);
+/* Same contraction on the tcgen05 engine (TMA + TMEM flash attention, tf32 operands, fp32 softmax).  The value
+ * operand is passed K-major, vt = V^T [heads*D, frames*S]: the host obtains it for free from the v_proj GEMM with
+ * swapped operands (cofi_gemm(A = W_v, W = source)), so no transpose pass exists.  (frames*S) % 4 == 0. */
+int cofi_attention_vt(const float* q, const float* k, const float* vt, int64_t L, int64_t S, int frames, int heads,
+                      int D, float scale, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Matching (model/network.py:167-264, evaluation/eval_all.py:99-105)

@@ -97,3 +97,22 @@ def test_forward_golden_tc(cuda_model, engine, tol):
     if engine == "tf32x3":
         assert torch.equal(test[6].cpu(), torch.from_numpy(z["test/fine_center_xy"]))
         assert torch.equal(test[7].cpu(), torch.from_numpy(z["test/coarse_pc_points"]))
+
+
+@pytest.mark.parametrize("L,S,frames", [(1280, 1280, 1), (1280, 1280, 2), (300, 516, 2), (130, 64, 1), (128, 1024, 1)])
+def test_attention_tc(L, S, frames):
+    """tcgen05 flash attention (tf32 operands, fp32 softmax) vs torch fp64 attention; tolerance 5e-3 (tf32)."""
+    from cofii2p_b200 import ops
+    g = torch.Generator().manual_seed(L + S + frames)
+    q = torch.randn((frames * L, 128), generator=g)
+    k = torch.randn((frames * S, 128), generator=g)
+    v = torch.randn((frames * S, 128), generator=g)
+    refs = []
+    for f in range(frames):
+        qq = q[f * L:(f + 1) * L].view(1, L, 4, 32).double()
+        kk = k[f * S:(f + 1) * S].view(1, S, 4, 32).double()
+        vv = v[f * S:(f + 1) * S].view(1, S, 4, 32).double()
+        a = torch.softmax(torch.einsum("nlhd,nshd->nlsh", qq, kk) / 32 ** 0.5, dim=2)
+        refs.append(torch.einsum("nlsh,nshd->nlhd", a, vv).reshape(L, 128).float())
+    got = ops.attention_vt(q.cuda(), k.cuda(), v.t().contiguous().cuda(), frames, 4, 1.0 / 32 ** 0.5)
+    assert rel_err(got, torch.cat(refs)) < 5e-3, rel_err(got, torch.cat(refs))
