@@ -559,11 +559,4 @@ int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w,
     return dispatch<true>(ta, tb, p, bn, engine == COFI_GEMM_TF32X3, grid, st);
 }
 
-// similarity tensor-core engine lands in sim_tc.cu
-bool sim_argmin_tc_supported(int64_t, int64_t, int64_t, int64_t, int) { return false; }
-int sim_argmin_tc_launch(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int, int, int64_t*, float*,
-                         int, cudaStream_t) {
-    set_error("tensor-core similarity engine not built");
-    return COFI_EUNSUPPORTED;
-}
 }  // namespace cofi

@@ -22,8 +22,9 @@ def _pin(t: torch.Tensor) -> torch.Tensor:
 
 
 class InferenceEngine:
-    def __init__(self, model, batch: Dict, mode: str = "val", use_graph: bool = True):
-        """`batch`: output of frames.stack_frames (CPU or CUDA tensors) that fixes all shapes."""
+    def __init__(self, model, batch: Dict, mode: str = "val", use_graph: bool = True, stream=None):
+        """`batch`: output of frames.stack_frames (CPU or CUDA tensors) that fixes all shapes.
+        `stream`: compute stream shared by several engines (PipelinedEngine)."""
         assert mode == "val", "the graph covers the static-shape val/train-style forward; test mode adds an eager tail"
         self.model, self.mode, self.B = model, mode, batch["frames"]
         dev = next(model.parameters()).device
@@ -46,7 +47,7 @@ class InferenceEngine:
         self.launches_per_step = 0
         self._host_in = None
         self._host_out = None
-        self._stream = torch.cuda.Stream(device=dev)
+        self._stream = stream if stream is not None else torch.cuda.Stream(device=dev)
         # warm-up (fills weight-pack / BN-fold / positional-encoding caches), then capture
         with torch.no_grad():
             with torch.cuda.stream(self._stream):
@@ -106,10 +107,10 @@ class InferenceEngine:
             "inline": _pin(torch.stack([k.to(torch.int64) for k in batch["fine_pc_inline_index"]])),
         }
 
-    def upload(self, host: Dict) -> int:
+    def upload(self, host: Dict, stream=None) -> int:
         """Async H2D of one batch from pinned host buffers into the static inputs; returns the bytes copied."""
         nbytes = 0
-        with torch.cuda.stream(self._stream):
+        with torch.cuda.stream(stream if stream is not None else self._stream):
             for key in ("points", "neighbors", "subsampling", "upsampling"):
                 for dst, src in zip(self.inp[key], host[key]):
                     dst.copy_(src, non_blocking=True)
@@ -120,14 +121,14 @@ class InferenceEngine:
                 nbytes += src.numel() * src.element_size()
         return nbytes
 
-    def download(self) -> int:
+    def download(self, stream=None) -> int:
         """Async D2H of the step's results into pinned host buffers; returns the bytes copied."""
         flat = [self.out["img_norm"], self.out["pc_norm"], self.out["img_score"], self.out["pc_score"]] + \
             list(self.out["patch"]) + list(self.out["fine_pc"]) + [self.err]
         if self._host_out is None:
             self._host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in flat]
         nbytes = 0
-        with torch.cuda.stream(self._stream):
+        with torch.cuda.stream(stream if stream is not None else self._stream):
             for dst, src in zip(self._host_out, flat):
                 dst.copy_(src, non_blocking=True)
                 nbytes += src.numel() * src.element_size()
@@ -144,3 +145,49 @@ class InferenceEngine:
                 outs.append(pub + (self.out["patch"][b], self.out["fine_pc"][b], None, None))
         assert int(self.err.item()) == 0, "extract_patch: window outside the feature map"
         return outs
+
+
+class PipelinedEngine:
+    """Double-buffered end-to-end pipeline: while the graph of buffer set i computes, the H2D copy of batch i+1
+    lands in buffer set (i+1)%2 on a copy stream and the D2H of batch i-1 drains on a third stream (PCIe is full
+    duplex).  Steady-state step time = max(H2D, compute, D2H) instead of their sum."""
+
+    def __init__(self, model, batch: Dict, depth: int = 2):
+        dev = next(model.parameters()).device
+        self.compute = torch.cuda.Stream(device=dev)
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.engines = [InferenceEngine(model, batch, use_graph=True, stream=self.compute) for _ in range(depth)]
+        self.uploaded = [torch.cuda.Event() for _ in range(depth)]
+        self.computed = [torch.cuda.Event() for _ in range(depth)]
+        self.drained = [torch.cuda.Event() for _ in range(depth)]
+        for e in self.computed + self.drained:
+            e.record(self.compute)
+        self.i = 0
+        self.launches_per_step = self.engines[0].launches_per_step
+
+    def step(self, host: Dict):
+        """Enqueue one batch end to end (asynchronous); returns (h2d bytes, d2h bytes)."""
+        k = self.i % len(self.engines)
+        eng = self.engines[k]
+        self.h2d.wait_event(self.computed[k])      # buffer set k is free once its previous compute finished
+        nin = eng.upload(host, self.h2d)
+        self.uploaded[k].record(self.h2d)
+        self.compute.wait_event(self.uploaded[k])
+        self.compute.wait_event(self.drained[k])   # outputs of set k were copied out
+        eng.run()
+        self.computed[k].record(self.compute)
+        self.d2h.wait_event(self.computed[k])
+        nout = eng.download(self.d2h)
+        self.drained[k].record(self.d2h)
+        self.i += 1
+        return nin, nout
+
+    def synchronize(self):
+        self.h2d.synchronize()
+        self.compute.synchronize()
+        self.d2h.synchronize()
+
+    def last_results(self):
+        self.synchronize()
+        return self.engines[(self.i - 1) % len(self.engines)].results()

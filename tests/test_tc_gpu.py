@@ -116,3 +116,23 @@ def test_attention_tc(L, S, frames):
         refs.append(torch.einsum("nlsh,nshd->nlhd", a, vv).reshape(L, 128).float())
     got = ops.attention_vt(q.cuda(), k.cuda(), v.t().contiguous().cuda(), frames, 4, 1.0 / 32 ** 0.5)
     assert rel_err(got, torch.cat(refs)) < 5e-3, rel_err(got, torch.cat(refs))
+
+
+@pytest.mark.parametrize("npt,npx,c,frames", [(1280, 1280, 128, 2), (1000, 3000, 64, 1), (300, 130, 32, 1)])
+def test_sim_argmin_tc(npt, npx, c, frames):
+    """Fused similarity + arg-min on tcgen05 (tf32): same pixel as the exact fp32 engine except on near-ties, where
+    the chosen pixel's exact score must be within 2e-3 of the optimum."""
+    from cofii2p_b200 import ops
+    g = torch.Generator().manual_seed(npt + npx + c)
+    pt = F.normalize(torch.randn((frames * npt, c), generator=g), dim=1).cuda()
+    px = F.normalize(torch.randn((frames * npx, c), generator=g), dim=1).cuda()
+    bi, bv = ops.sim_argmin(pt, px, frames, engine=ops.ENGINE_FP32)
+    ti, tv = ops.sim_argmin(pt, px, frames, engine=ops.ENGINE_TF32)
+    assert int(ti.min()) >= 0 and int(ti.max()) < npx
+    same = (bi == ti).float().mean().item()
+    assert same > 0.98, same
+    for f in range(frames):
+        d = 1 - pt[f * npt:(f + 1) * npt].double() @ px[f * npx:(f + 1) * npx].double().t()
+        chosen = d.gather(1, ti[f * npt:(f + 1) * npt, None]).squeeze(1)
+        assert float((chosen - d.min(1).values).max()) < 2e-3
+        assert float((tv[f * npt:(f + 1) * npt].double() - chosen).abs().max()) < 2e-3
