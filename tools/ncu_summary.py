@@ -1,0 +1,82 @@
+"""Summarise ncu artefacts from gpurun_out/ into profiles/ (text that is committed; the .ncu-rep stay scratch).
+usage: python tools/ncu_summary.py launches <launches.csv> <out.md>
+       python tools/ncu_summary.py full <report.ncu-rep> <out.md>"""
+import collections, csv, re, subprocess, sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
+
+
+def launches(path, out):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        d = per.setdefault(row["ID"], {"name": re.sub(r"\(.*", "", row["Kernel Name"])})
+        v = float(row["Metric Value"].replace(",", ""))
+        if row["Metric Name"] == "gpu__time_duration.sum":
+            u = row["Metric Unit"]
+            d["us"] = v / 1e3 if u == "ns" else (v if u == "us" else v * 1e3)
+        else:
+            d[row["Metric Name"]] = v
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for d in per.values():
+        agg[d["name"]][0] += 1
+        agg[d["name"]][1] += d["us"]
+    tot = sum(v[1] for v in agg.values())
+    with open(out, "w") as f:
+        f.write(f"# ncu launch list ({path}): one eager batched step (8 frames), cold-cache serialised launches\n\n")
+        f.write(f"total {tot:.1f} us over {len(per)} launches\n\n| kernel | launches | us | share |\n|---|---|---|---|\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1]/tot:.3f} |\n")
+    print(open(out).read()[:1500])
+
+
+def full(path, out):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(out, "w") as f:
+        f.write(f"# ncu --set full summary of {path}\n\n")
+        for r in rows[2:]:
+            f.write(f"## {r[hdr.index('Kernel Name')][:110]}\n\n")
+            for k in KEYS:
+                hits = [i for i, h in enumerate(hdr) if h == k]
+                if hits:
+                    f.write(f"- {k}: {r[hits[0]]} {units[hits[0]]}\n")
+            f.write("\n")
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(src.splitlines()))
+    blocks, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "rows": []}
+            blocks.append(cur)
+        elif cur is not None:
+            cur["rows"].append(r)
+    with open(out, "a") as f:
+        for b in blocks[:1]:
+            h = b["rows"][0]
+            col = {x: i for i, x in enumerate(h)}
+            stalls = [x for x in h if x.startswith("stall_") and "Not" not in x]
+            data = []
+            for r in b["rows"][1:]:
+                try:
+                    data.append((int(r[col["# Samples"]]), r))
+                except Exception:
+                    pass
+            tot = sum(d[0] for d in data) or 1
+            f.write(f"## top stall sites (first kernel, {tot} samples)\n\n| samples | share | SASS | dominant stall |\n|---|---|---|---|\n")
+            for n, r in sorted(data, key=lambda d: -d[0])[:12]:
+                top = max(((int(r[col[s]] or 0), s) for s in stalls), default=(0, ""))
+                f.write(f"| {n} | {n/tot:.3f} | `{r[col['Source']][:70]}` | {top[1]} |\n")
+    print(open(out).read()[:2500])
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
