@@ -50,6 +50,9 @@ struct Epilogue {
     int64_t ldres;
     int accumulate;
     int act;
+    const float* ln_gamma;  // fused row LayerNorm over the N columns (tcgen05 engine, N <= 128): y = act(LN(x))+residual
+    const float* ln_beta;
+    float ln_eps;
 };
 
 constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
@@ -196,7 +199,7 @@ extern "C" int cofi_gemm(const float* A, int64_t lda, const float* W, int64_t ld
     COFI_REQUIRE(lda >= K && ldw >= K && ldc >= N, "cofi_gemm: leading dimension too small");
     COFI_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "cofi_gemm: A and W must be 16-byte aligned");
     if (M == 0) return COFI_OK;
-    Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, accumulate, act};
+    Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, accumulate, act, nullptr, nullptr, 0.0f};
     if (engine == COFI_GEMM_FP32) return gemm_simt_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, (cudaStream_t)stream);
     if (engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3) {
         if (!gemm_tc_supported(lda, ldw, ldc, M, N, K, A, W, C))
@@ -216,8 +219,30 @@ extern "C" int cofi_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, co
     COFI_REQUIRE(Cin % 4 == 0, "cofi_conv2d_nhwc: Cin=%d must be a multiple of 4 (pad the input)", Cin);
     COFI_REQUIRE((scale == nullptr) == (shift == nullptr), "cofi_conv2d_nhwc: scale and shift go together");
     COFI_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0, "cofi_conv2d_nhwc: 16-byte alignment");
-    Epilogue ep{nullptr, nullptr, scale, shift, residual, Cout, 0, act};
+    Epilogue ep{nullptr, nullptr, scale, shift, residual, Cout, 0, act, nullptr, nullptr, 0.0f};
     if ((engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3) && conv_tc_supported(B, H, W, Cin, Cout, KH, KW, stride, pad))
         return conv_tc_launch(x, B, H, W, Cin, w, Cout, KH, KW, pad, y, ep, engine, (cudaStream_t)stream);
     return conv_simt_launch(x, B, H, W, Cin, w, Cout, KH, KW, stride, pad, y, ep, (cudaStream_t)stream);
+}
+
+extern "C" int cofi_layer_norm_rows(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma,
+                                    const float* beta, float eps, int act, const float* residual, int64_t ldr,
+                                    float* y, int64_t ldy, void* stream);
+
+extern "C" int cofi_gemm_ln(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                            int N, int K, const float* bias, const float* gamma, const float* beta, float eps, int act,
+                            const float* residual, int64_t ldr, int engine, void* stream) {
+    COFI_REQUIRE(A && W && C && gamma && beta, "cofi_gemm_ln: null pointer");
+    COFI_REQUIRE(M >= 0 && N > 0 && K > 0, "cofi_gemm_ln: bad shape");
+    COFI_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K && ldc >= N, "cofi_gemm_ln: bad leading dimension");
+    COFI_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "cofi_gemm_ln: A and W must be 16-byte aligned");
+    if (M == 0) return COFI_OK;
+    if ((engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3) && N <= 128 && N % 32 == 0 &&
+        gemm_tc_supported(lda, ldw, ldc, M, N, K, A, W, C)) {
+        Epilogue ep{bias, nullptr, nullptr, nullptr, residual, ldr, 0, act, gamma, beta, eps};
+        return gemm_tc_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, engine, (cudaStream_t)stream);
+    }
+    int rc = cofi_gemm(A, lda, W, ldw, C, ldc, M, N, K, bias, nullptr, 0, COFI_ACT_NONE, engine, stream);
+    if (rc) return rc;
+    return cofi_layer_norm_rows(C, ldc, M, N, gamma, beta, eps, act, residual, ldr, C, ldc, stream);
 }

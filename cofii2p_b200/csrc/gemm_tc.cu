@@ -37,6 +37,9 @@ struct Epilogue {  // must match gemm_simt.cu
     int64_t ldres;
     int accumulate;
     int act;
+    const float* ln_gamma;  // fused row LayerNorm over the N columns (tcgen05 engine, N <= 128): y = act(LN(x))+residual
+    const float* ln_beta;
+    float ln_eps;
 };
 
 namespace tc {
@@ -152,7 +155,7 @@ struct Cfg {
     static constexpr int STAGE = A_BYTES + B_BYTES;
     static constexpr int NS = (BN == 128) ? 3 : 4;
     static constexpr int RING = STAGE * NS * (X3 ? 2 : 1);
-    static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */ + 2 * BN * 4 /* epilogue vectors */;
+    static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */ + 4 * BN * 4 /* epilogue vectors */;
     static constexpr int THREADS = X3 ? 320 : 192;
 };
 
@@ -171,6 +174,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::NS + 1);
     float* s_scale = reinterpret_cast<float*>(smem + C::RING + 256);  // [BN] per-column multiplier
     float* s_shift = s_scale + BN;                                   // [BN] per-column shift (+bias)
+    float* s_gamma = s_shift + BN;                                   // [BN] fused-LayerNorm weight
+    float* s_beta = s_gamma + BN;                                    // [BN] fused-LayerNorm bias
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
@@ -268,6 +273,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 s_scale[t] = sc;
                 s_shift[t] = sh;
+                s_gamma[t] = (p.ep.ln_gamma && n < p.N) ? __ldg(p.ep.ln_gamma + n) : 0.0f;
+                s_beta[t] = (p.ep.ln_gamma && n < p.N) ? __ldg(p.ep.ln_beta + n) : 0.0f;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
@@ -293,6 +300,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         float* stage = reinterpret_cast<float*>(smem) + q * (32 * 36);  // ring is idle once tmem_full fired
         const bool rvec_ok = has_res && ((ep.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
+        const bool has_ln = ep.ln_gamma != nullptr;  // host guarantees gridDim.y == 1 and N <= BN
+        float ln_mean = 0.0f, ln_rstd = 1.0f;
+        if (has_ln) {
+            float sum = 0.0f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < p.N) sum += fmaf(__uint_as_float(acc[j]), s_scale[c0 + j], s_shift[c0 + j]);
+            }
+            ln_mean = sum / (float)p.N;
+            float ssq = 0.0f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < p.N) {
+                        const float d = fmaf(__uint_as_float(acc[j]), s_scale[c0 + j], s_shift[c0 + j]) - ln_mean;
+                        ssq = fmaf(d, d, ssq);
+                    }
+            }
+            ln_rstd = rsqrtf(ssq / (float)p.N + ep.ln_eps);
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t acc[32];
@@ -316,6 +352,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
                     v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
                     v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+                }
+                if (has_ln) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (v[j] - ln_mean) * ln_rstd * s_gamma[c0 + j] + s_beta[c0 + j];
+                    if (ep.act == COFI_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    }
                 }
                 if (has_res) {
                     if (rvec_ok && full) {
@@ -349,7 +393,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (nb + j < p.N) v[j] += crow[nb + j];
                     }
                 }
-                if (ep.act == COFI_ACT_RELU) {
+                if (has_ln) {
+                    // activation was applied right after the norm, before the residual
+                } else if (ep.act == COFI_ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
                 } else if (ep.act == COFI_ACT_LRELU01) {

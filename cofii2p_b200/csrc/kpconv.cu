@@ -158,38 +158,52 @@ maxpool_rows_kernel(const float* __restrict__ x, int64_t ldx, int C, const int64
         if (id >= Ns) id = -1;
         idx[j] = (int)id;
     }
+    const bool vec = (C % 4) == 0;
     for (int c0 = 0; c0 < C; c0 += 128) {
         const int c = c0 + lane * 4;
+        const bool act = c < C;
         float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            for (int l = 0; l < 32; ++l) {
-                const int i = __shfl_sync(0xffffffffu, idx[j], l);
-                if (i == -2) continue;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i >= 0 && c < C) {
-                    if (c + 3 < C) {
-                        v = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)i * ldx + c));
-                    } else {
-                        const float* r = xb + (int64_t)i * ldx;
-                        v.x = r[c];
-                        if (c + 1 < C) v.y = r[c + 1];
-                        if (c + 2 < C) v.z = r[c + 2];
+#pragma unroll 2
+            for (int l = 0; l < 32; l += 4) {  // four independent gathers in flight per lane
+                int id[4];
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, idx[j], l + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (id[u] >= 0 && act) {
+                        const float* r = xb + (int64_t)id[u] * ldx;
+                        if (vec) {
+                            v[u] = __ldg(reinterpret_cast<const float4*>(r + c));
+                        } else {
+                            v[u].x = r[c];
+                            if (c + 1 < C) v[u].y = r[c + 1];
+                            if (c + 2 < C) v[u].z = r[c + 2];
+                            if (c + 3 < C) v[u].w = r[c + 3];
+                        }
                     }
                 }
-                mx.x = fmaxf(mx.x, v.x);
-                mx.y = fmaxf(mx.y, v.y);
-                mx.z = fmaxf(mx.z, v.z);
-                mx.w = fmaxf(mx.w, v.w);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (id[u] == -2) continue;  // beyond H: not a neighbour at all
+                    mx.x = fmaxf(mx.x, v[u].x);
+                    mx.y = fmaxf(mx.y, v[u].y);
+                    mx.z = fmaxf(mx.z, v[u].z);
+                    mx.w = fmaxf(mx.w, v[u].w);
+                }
             }
         }
         float* o = out + m * ldo;
-        if (c + 3 < C) {
+        if (act && vec) {
             *reinterpret_cast<float4*>(o + c) = mx;
-        } else if (c < C) {
+        } else if (act) {
             o[c] = mx.x;
             if (c + 1 < C) o[c + 1] = mx.y;
             if (c + 2 < C) o[c + 2] = mx.z;
+            if (c + 3 < C) o[c + 3] = mx.w;
         }
     }
 }

@@ -256,21 +256,28 @@ colsq_kernel(const float* __restrict__ x, int64_t ldx, int64_t L, int C, double*
     partials[((int64_t)frame * kStatChunks + chunk) * C + c] = ss;
 }
 
+// inv[frame, c] = 1 / max(sqrt(sum of the chunk partials), 1e-12)
+__global__ void __launch_bounds__(128)
+colnorm_finalize_kernel(const double* __restrict__ partials, int C, int total, float* __restrict__ inv) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // frame * C + c
+    if (t >= total) return;
+    const int frame = t / C, c = t - frame * C;
+    double ss = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < kStatChunks; ++k) ss += partials[((int64_t)frame * kStatChunks + k) * C + c];
+    inv[t] = fmaxf((float)sqrt(ss), 1e-12f);
+}
+
 __global__ void __launch_bounds__(256)
 colnorm_apply_kernel(const float* __restrict__ x, int64_t ldx, int64_t L, int C, int64_t total_rows,
-                     const double* __restrict__ partials, float* __restrict__ y, int64_t ldy) {
-    // each block handles a tile of rows for all channels; column norms recomputed per thread (C small)
+                     const float* __restrict__ denom, float* __restrict__ y, int64_t ldy) {
     const int64_t total = total_rows * C;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = t / C;
         const int c = (int)(t - row * C);
         const int64_t frame = row / L;
-        double ss = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < kStatChunks; ++k) ss += partials[((int64_t)frame * kStatChunks + k) * C + c];
-        const float denom = fmaxf((float)sqrt(ss), 1e-12f);
-        y[row * ldy + c] = __ldg(x + row * ldx + c) / denom;
+        y[row * ldy + c] = __ldg(x + row * ldx + c) / __ldg(denom + frame * C + c);
     }
 }
 
@@ -377,7 +384,7 @@ extern "C" int cofi_l2norm_rows(const float* x, int64_t ldx, int64_t rows, int C
 }
 
 extern "C" int64_t cofi_colnorm_workspace(int frames, int C) {
-    return (int64_t)frames * kStatChunks * C * sizeof(double);
+    return (int64_t)frames * kStatChunks * C * sizeof(double) + (int64_t)frames * C * sizeof(float) + 64;
 }
 
 extern "C" int cofi_colnorm_rows(const float* x, int64_t ldx, int64_t L, int C, int frames, void* colsq, float* y,
@@ -392,7 +399,11 @@ extern "C" int cofi_colnorm_rows(const float* x, int64_t ldx, int64_t L, int C, 
     colsq_kernel<<<grid, threads, 0, st>>>(x, ldx, L, C, part);
     int rc = check_launch("cofi_colnorm_rows(colsq)");
     if (rc) return rc;
+    float* denom = reinterpret_cast<float*>(part + (int64_t)frames * kStatChunks * C);
+    colnorm_finalize_kernel<<<(unsigned)ceil_div((int64_t)frames * C, 128), 128, 0, st>>>(part, C, frames * C, denom);
+    rc = check_launch("cofi_colnorm_rows(finalize)");
+    if (rc) return rc;
     const int64_t rows = L * frames;
-    colnorm_apply_kernel<<<ew_blocks(rows * C, 256), 256, 0, st>>>(x, ldx, L, C, rows, part, y, ldy);
+    colnorm_apply_kernel<<<ew_blocks(rows * C, 256), 256, 0, st>>>(x, ldx, L, C, rows, denom, y, ldy);
     return check_launch("cofi_colnorm_rows(apply)");
 }

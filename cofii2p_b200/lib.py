@@ -22,6 +22,7 @@ SIGNATURES = {
     "cofi_maxpool_rows": (_i, [_vp, _l, _i, _vp, _i, _l, _l, _i, _vp, _l, _vp]),
     "cofi_gather_rows": (_i, [_vp, _l, _i, _vp, _l, _l, _l, _i, _vp, _l, _vp]),
     "cofi_gemm": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "cofi_gemm_ln": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _vp, _f, _i, _vp, _l, _i, _vp]),
     "cofi_conv2d_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "cofi_norm_rows_workspace": (_l, [_i, _i]),
     "cofi_norm_rows": (_i, [_vp, _l, _l, _i, _i, _i, _vp, _vp, _f, _vp, _l, _i, _vp, _l, _vp, _vp, _vp, _vp]),

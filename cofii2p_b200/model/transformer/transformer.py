@@ -37,15 +37,14 @@ class LoFTREncoderLayer(nn.Module):
         else:
             v = ops.gemm(source, self.v_proj.weight)
             msg = self.attention(q, k, v, frames, self.nhead)
-        cat = torch.empty((x.shape[0], 2 * C), dtype=torch.float32, device=x.device)
-        ops.gather_rows(x, None, frames=1, out=cat[:, :C])
-        # message = norm1(merge(message)) lands in the right half of the concat buffer
-        m = ops.layer_norm_rows(ops.gemm(msg, self.merge.weight), self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        ops.gather_rows(m, None, frames=1, out=cat[:, C:])
-        h = ops.gemm(cat, self.mlp[0].weight, act=ops.ACT_RELU)
-        h = ops.gemm(h, self.mlp[2].weight)
-        # x + norm2(h)
-        return ops.layer_norm_rows(h, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=x)
+        # message = norm1(merge(message)): Linear + LayerNorm fused in the GEMM epilogue
+        m = ops.gemm_ln(msg, self.merge.weight, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        # mlp[0] on cat([x, message]) without materialising the concat: two K=C GEMMs accumulating into one output
+        w1 = self.mlp[0].weight
+        h = ops.gemm(x, w1[:, :C])
+        h = ops.gemm(m, w1[:, C:], out=h, accumulate=True, act=ops.ACT_RELU)
+        # x + norm2(mlp[2](h)): Linear + LayerNorm + residual in one kernel
+        return ops.gemm_ln(h, self.mlp[2].weight, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=x)
 
 
 class LocalFeatureTransformer(nn.Module):

@@ -210,6 +210,23 @@ def gemm(a, w, bias=None, rowdiv=None, act: int = ACT_NONE, out: Optional[torch.
     return out
 
 
+def gemm_ln(a, w, gamma, beta, eps: float = 1e-5, bias=None, act: int = ACT_NONE, residual=None,
+            engine: Optional[int] = None):
+    """act(LayerNorm(a @ w.T + bias)) + residual, one kernel on the tensor-core engines when N <= 128."""
+    a, lda = _rows(a, "a")
+    w, ldw = _rows(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ldr = 0
+    if residual is not None:
+        residual, ldr = _rows(residual, "residual")
+    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (2 if residual is not None else 1)))
+    _call("cofi_gemm_ln", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(gamma), _p(beta), float(eps), act,
+          _p(residual), ldr, _engine if engine is None else engine, _st())
+    return out
+
+
 def conv2d_nhwc(x, w_packed, kh: int, kw: int, stride: int, pad: int, scale=None, shift=None, residual=None,
                 act: int = ACT_NONE, engine: Optional[int] = None):
     """x [B,H,W,Cin] fp32 contiguous, w_packed [Cout, kh*kw*Cin]."""

@@ -98,6 +98,14 @@ int cofi_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, float* C
               int64_t M, int N, int K, const float* bias, const float* rowdiv, int accumulate, int act,
               int engine, void* stream);
 
+/* C[M,N] = act(LayerNorm_N(A W^T + bias) * gamma + beta) + residual : Linear -> LayerNorm(eps) -> act -> + residual as
+ * ONE kernel when a row fits a tile (N <= 128, N % 32 == 0, tensor-core engines): each epilogue thread owns a full
+ * output row in TMEM and normalises it in registers (model/transformer/transformer.py:57-58,61-64: merge+norm1 and
+ * mlp[2]+norm2+residual).  Other shapes/engines run cofi_gemm followed by cofi_layer_norm_rows. */
+int cofi_gemm_ln(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N, int K,
+                 const float* bias, const float* gamma, const float* beta, float eps, int act, const float* residual,
+                 int64_t ldr, int engine, void* stream);
+
 /* NHWC convolution as implicit GEMM (model/imagenet.py:26-34,142-143,377-394):
  *   y[b,ho,wo,co] = sum_{kh,kw,ci} x[b, ho*stride+kh-pad, wo*stride+kw-pad, ci] * w[co, kh, kw, ci]
  * w is [Cout, KH*KW*Cin] (host repacks the reference's [Cout,Cin,KH,KW]).  Cin % 4 == 0.

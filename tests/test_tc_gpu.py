@@ -136,3 +136,22 @@ def test_sim_argmin_tc(npt, npx, c, frames):
         chosen = d.gather(1, ti[f * npt:(f + 1) * npt, None]).squeeze(1)
         assert float((chosen - d.min(1).values).max()) < 2e-3
         assert float((tv[f * npt:(f + 1) * npt].double() - chosen).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("engine", ["fp32", "tf32", "tf32x3"])
+@pytest.mark.parametrize("m,n,k", [(1280, 128, 256), (1000, 64, 128), (333, 32, 64)])
+def test_gemm_ln_fused(engine, m, n, k):
+    """Linear -> LayerNorm -> ReLU -> + residual as one tcgen05 kernel (row lives in TMEM) vs torch."""
+    from cofii2p_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn((m, k), generator=g)
+    w = torch.randn((n, k), generator=g) / math.sqrt(k)
+    gamma, beta = torch.randn((n,), generator=g), torch.randn((n,), generator=g)
+    res = torch.randn((m, n), generator=g)
+    ref = F.relu(F.layer_norm(F.linear(a.double(), w.double()), (n,), gamma.double(), beta.double(), 1e-5)).float() + res
+    ops.set_engine(engine)
+    try:
+        got = ops.gemm_ln(a.cuda(), w.cuda(), gamma.cuda(), beta.cuda(), 1e-5, act=ops.ACT_RELU, residual=res.cuda())
+    finally:
+        ops.set_engine("fp32")
+    assert rel_err(got, ref) < (1e-2 if engine == "tf32" else 1e-4), rel_err(got, ref)
