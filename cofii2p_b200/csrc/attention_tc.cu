@@ -19,15 +19,16 @@ namespace cofi {
 namespace tc {
 
 constexpr int AQ = 128;   // queries per CTA
-constexpr int AK = 128;   // keys per tile
+constexpr int AK = 64;    // keys per tile (64: 81 KB of smem -> 2 CTAs per SM hide the MMA->softmax->MMA latency chain)
 constexpr int AD = 32;    // head dim
 constexpr int Q_BYTES = AQ * AD * 4;        // 16 KB
 constexpr int K_BYTES = AK * AD * 4;        // 16 KB
-constexpr int VT_BYTES = AD * AK * 4;       // 16 KB = 4 chunks of [32 d rows x 32 keys]
-constexpr int P_BYTES = AQ * AK * 4;        // 64 KB = 4 k-blocks of [128 rows x 32 keys]
+constexpr int VT_BYTES = AD * AK * 4;       // AK/32 chunks of [32 d rows x 32 keys]
+constexpr int P_BYTES = AQ * AK * 4;        // AK/32 k-blocks of [128 rows x 32 keys]
+constexpr int KC = AK / 32;                 // 32-key chunks per tile
 constexpr int KV_STAGES = 2;
 constexpr int ATT_SMEM = Q_BYTES + KV_STAGES * (K_BYTES + VT_BYTES) + P_BYTES + 1024 + 256;
-constexpr int TMEM_COLS = 256;              // S: [0,128)  O_t: [128,160)
+constexpr int TMEM_COLS = 128;              // S: [0,AK)  O_t: [AK,AK+32)
 
 struct AttParams {
     float* out;
@@ -79,7 +80,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AK;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -94,7 +95,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const int key0 = (int)(frame * p.S + (int64_t)t * AK);
                 tma_load_2d(&tmK, &kv_full[s], kd, head * AD, key0);
 #pragma unroll
-                for (int c = 0; c < 4; ++c)  // V^T chunk c: rows head*32..+31, keys key0+32c..+31
+                for (int c = 0; c < KC; ++c)  // V^T chunk c: rows head*32..+31, keys key0+32c..+31
                     tma_load_2d(&tmVt, &kv_full[s], kd + K_BYTES + c * (AD * 32 * 4), key0 + c * 32, head * AD);
             }
         }
@@ -124,7 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (t > 0) mbar_wait(o_free, tp ^ 1u);
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < KC; ++c)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         mma_tf32(tmem_O, umma_desc_k128(p_addr + c * (AQ * 32 * 4) + k * 32),
@@ -153,7 +154,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float sv[AK];
             float tmax = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < KC; ++c) {
                 uint32_t raw[32];
                 tmem_ld32(tmem_S + lane_off + c * 32, raw);
                 tmem_ld_wait();
@@ -168,7 +169,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const float corr = expf(mrun - mnew);
             float psum = 0.0f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < KC; ++c) {
                 uint8_t* blk = prow + c * (AQ * 32 * 4);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {

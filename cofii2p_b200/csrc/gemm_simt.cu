@@ -182,6 +182,8 @@ int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, flo
                    int K, const Epilogue& ep, int engine, cudaStream_t st);
 bool gemm_tc_supported(int64_t lda, int64_t ldw, int64_t ldc, int64_t M, int N, int K, const void* A, const void* W,
                        const void* C);
+int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
+                       int K, const Epilogue& ep, cudaStream_t st);
 bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW, int pad,
                    float* y, const Epilogue& ep, int engine, cudaStream_t st);
@@ -245,4 +247,16 @@ extern "C" int cofi_gemm_ln(const float* A, int64_t lda, const float* W, int64_t
     int rc = cofi_gemm(A, lda, W, ldw, C, ldc, M, N, K, bias, nullptr, 0, COFI_ACT_NONE, engine, stream);
     if (rc) return rc;
     return cofi_layer_norm_rows(C, ldc, M, N, gamma, beta, eps, act, residual, ldr, C, ldc, stream);
+}
+
+extern "C" int cofi_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                             int N, int K, const float* bias, const float* rowdiv, int act, void* stream) {
+    COFI_REQUIRE(A && W && C, "cofi_gemm_f16: null pointer");
+    COFI_REQUIRE(M >= 0 && N >= 16 && K >= 8, "cofi_gemm_f16: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+    COFI_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K && ldc >= N,
+                 "cofi_gemm_f16: K, lda, ldw must be multiples of 8 (16-byte rows)");
+    COFI_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "cofi_gemm_f16: 16-byte alignment");
+    if (M == 0) return COFI_OK;
+    Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, 0, act, nullptr, nullptr, 0.0f};
+    return gemm_tc_f16_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, (cudaStream_t)stream);
 }

@@ -79,13 +79,13 @@ struct KeyHash {
     }
 };
 
-const CUtensorMap* get_tmap_f32(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                const uint32_t* box) {
+static const CUtensorMap* get_tmap_any(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                       const uint32_t* box, int half) {
     static std::mutex mu;
     static std::unordered_map<Key, CUtensorMap*, KeyHash> cache;
     Key k{};
     k.v[0] = (uint64_t)(uintptr_t)base;
-    k.v[1] = (uint64_t)rank;
+    k.v[1] = (uint64_t)rank | ((uint64_t)half << 8);
     for (int i = 0; i < rank; ++i) {
         k.v[2 + i] = dims[i];
         k.v[6 + i] = ((uint64_t)box[i] << 40) | (i > 0 ? strides_bytes[i - 1] : 0);
@@ -112,7 +112,7 @@ const CUtensorMap* get_tmap_f32(const void* base, int rank, const uint64_t* dims
         es[i] = 1;
         if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
     }
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+    CUresult r = fn(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -123,6 +123,15 @@ const CUtensorMap* get_tmap_f32(const void* base, int rank, const uint64_t* dims
     }
     cache.emplace(k, m);
     return m;
+}
+
+const CUtensorMap* get_tmap_f32(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                const uint32_t* box) {
+    return get_tmap_any(base, rank, dims, strides_bytes, box, 0);
+}
+const CUtensorMap* get_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                const uint32_t* box) {
+    return get_tmap_any(base, rank, dims, strides_bytes, box, 1);
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -159,7 +168,7 @@ struct Cfg {
     static constexpr int THREADS = X3 ? 320 : 192;
 };
 
-template <int BN, bool CONV, bool X3>
+template <int BN, bool CONV, bool X3, bool HALF = false>
 __global__ void __launch_bounds__(Cfg<BN, X3>::THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     using C = Cfg<BN, X3>;
@@ -224,15 +233,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_4d(&tmA, &full[s], a_dst, cc * TK, cw0 + kw - p.pad, ch0 + kh - p.pad, cb);
                     tma_load_2d(&tmB, &full[s], b_dst, tap * p.Cin + cc * TK, n0);
                 } else {
-                    tma_load_2d(&tmA, &full[s], a_dst, kb * TK, (int)m0);
-                    tma_load_2d(&tmB, &full[s], b_dst, kb * TK, n0);
+                    // k-block = 128 bytes of K: 32 fp32 or 64 fp16 elements
+                    tma_load_2d(&tmA, &full[s], a_dst, kb * (HALF ? 64 : TK), (int)m0);
+                    tma_load_2d(&tmB, &full[s], b_dst, kb * (HALF ? 64 : TK), n0);
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (lane == 0 && !(p.dbg & 2)) {
-            constexpr uint32_t idesc = umma_idesc(2 /*tf32*/, TM, BN);
+            constexpr uint32_t idesc = umma_idesc(HALF ? 0 /*f16*/ : 2 /*tf32*/, TM, BN);
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 const int s = kb % C::NS;
                 const uint32_t ph = (uint32_t)(kb / C::NS) & 1u;
@@ -244,7 +254,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int k = 0; k < TK / 8; ++k) {
                     const uint64_t ad = umma_desc_k128(a_addr + k * 32);
                     const uint64_t bd = umma_desc_k128(b_addr + k * 32);
-                    mma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    if (HALF)
+                        mma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    else
+                        mma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     if (X3) {
                         const uint32_t alo = smem_u32(lo_base + s * C::STAGE);
                         const uint64_t ald = umma_desc_k128(alo + k * 32);
@@ -484,12 +497,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-template <int BN, bool CONV, bool X3>
+template <int BN, bool CONV, bool X3, bool HALF = false>
 static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const Params& p, dim3 grid, cudaStream_t st) {
     using C = Cfg<BN, X3>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, X3, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::SMEM);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(smem=%d): %s", C::SMEM, cudaGetErrorString(e));
@@ -497,7 +510,7 @@ static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const Params& 
         }
         attr_done = true;
     }
-    gemm_tc_kernel<BN, CONV, X3><<<grid, C::THREADS, C::SMEM, st>>>(*a, *b, p);
+    gemm_tc_kernel<BN, CONV, X3, HALF><<<grid, C::THREADS, C::SMEM, st>>>(*a, *b, p);
     return check_launch(CONV ? "cofi_conv2d_nhwc(tcgen05)" : "cofi_gemm(tcgen05)");
 }
 
@@ -560,6 +573,33 @@ int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, flo
     p.dbg = tc_debug();
     dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
     return dispatch<false>(ta, tb, p, bn, engine == COFI_GEMM_TF32X3, grid, st);
+}
+
+// fp16-operand GEMM (A [M,K] half, W [N,K] half, fp32 accumulate/output): KPConv weight-apply on the tf32 engine.
+// fp16 keeps 11 significand bits -- the same operand precision as tf32 -- at half the bytes and twice the MMA rate.
+int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
+                       int K, const Epilogue& ep, cudaStream_t st) {
+    using namespace tc;
+    const int bn = pick_bn(N);
+    uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * 2};
+    uint32_t bA[2] = {64, TM};
+    uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldw * 2};
+    uint32_t bB[2] = {64, (uint32_t)bn};
+    const CUtensorMap* ta = get_tmap_f16(A, 2, dA, sA, bA);
+    const CUtensorMap* tb = get_tmap_f16(W, 2, dB, sB, bB);
+    if (!ta || !tb) return COFI_ECUDA;
+    Params p{};
+    p.C = C;
+    p.ldc = ldc;
+    p.M = M;
+    p.N = N;
+    p.num_kb = (K + 63) / 64;
+    p.ep = ep;
+    p.dbg = tc_debug();
+    dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
+    if (bn == 32) return launch_one<32, false, false, true>(ta, tb, p, grid, st);
+    if (bn == 64) return launch_one<64, false, false, true>(ta, tb, p, grid, st);
+    return launch_one<128, false, false, true>(ta, tb, p, grid, st);
 }
 
 // ---------------------------------------------------------------------------------------------- conv entry

@@ -7,6 +7,8 @@
 // gather each from the packed (x,y,z,flag) table), and for each kernel point ballots the lanes whose
 // influence is non-zero; only those neighbours' feature rows are loaded (coalesced, float4 per lane) and
 // accumulated with warp-uniform control flow.  No tensor cores: the contraction is data-dependent sparse.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace cofi {
@@ -47,12 +49,12 @@ struct VecT<4> {
     using T = float4;
 };
 
-template <int VEC, int NCH>
+template <int VEC, int NCH, typename OutT = float>
 __global__ void __launch_bounds__(128)
 kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, const float4* __restrict__ s_packed,
                         const float* __restrict__ q_points, const int64_t* __restrict__ nbr, int H, int64_t Mq,
                         int64_t Ns, int64_t total_q, const float* __restrict__ kernel_points, int K, float sigma,
-                        float reach2, float* __restrict__ agg, float* __restrict__ cnt_out) {
+                        float reach2, OutT* __restrict__ agg, float* __restrict__ cnt_out) {
     __shared__ float skp[kMaxKP * 3];
     if (threadIdx.x < K * 3) skp[threadIdx.x] = kernel_points[threadIdx.x];
     __syncthreads();
@@ -89,7 +91,7 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
     if (lane == 0) cnt_out[m] = fmaxf(cnt, 1.0f);
 
     using V = typename VecT<VEC>::T;
-    float* out_row = agg + m * (int64_t)K * C;
+    OutT* out_row = agg + m * (int64_t)K * C;
     const bool lane_active = (lane * VEC) < C;  // only matters for C < 32*VEC (C = 4)
 
     for (int k = 0; k < K; ++k) {
@@ -131,11 +133,24 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
         if (lane_active) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                V o;
-                float* ov = reinterpret_cast<float*>(&o);
+                OutT* dst = out_row + (int64_t)k * C + (c * 32 + lane) * VEC;
+                if constexpr (sizeof(OutT) == 4) {
+                    V o;
+                    float* ov = reinterpret_cast<float*>(&o);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) ov[v] = acc[c][v];
-                *reinterpret_cast<V*>(out_row + (int64_t)k * C + (c * 32 + lane) * VEC) = o;
+                    for (int v = 0; v < VEC; ++v) ov[v] = acc[c][v];
+                    *reinterpret_cast<V*>(dst) = o;
+                } else if constexpr (VEC == 4) {
+                    __half2 lo = __floats2half2_rn(acc[c][0], acc[c][1]), hi = __floats2half2_rn(acc[c][2], acc[c][3]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(dst) = pk;
+                } else if constexpr (VEC == 2) {
+                    *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(acc[c][0], acc[c][1]);
+                } else {
+                    dst[0] = __float2half_rn(acc[c][0]);
+                }
             }
         }
     }
@@ -294,6 +309,49 @@ extern "C" int cofi_kpconv_aggregate(const float* feats, int64_t ldf, int C, con
     }
 #undef LAUNCH
     return check_launch("cofi_kpconv_aggregate");
+}
+
+extern "C" int cofi_kpconv_aggregate_f16(const float* feats, int64_t ldf, int C, const float* s_packed,
+                                         const float* q_points, const int64_t* nbr, int H, int64_t Mq, int64_t Ns,
+                                         int frames, const float* kernel_points, int K, float sigma, float kp_reach,
+                                         void* agg_f16, float* cnt, void* stream) {
+    COFI_REQUIRE(feats && s_packed && q_points && nbr && kernel_points && agg_f16 && cnt,
+                 "cofi_kpconv_aggregate_f16: null pointer");
+    COFI_REQUIRE(H > 0 && H <= 128 && K > 0 && K <= kMaxKP && sigma > 0.0f, "cofi_kpconv_aggregate_f16: bad argument");
+    COFI_REQUIRE(Mq >= 0 && Ns > 0 && frames > 0 && ldf >= C, "cofi_kpconv_aggregate_f16: bad sizes");
+    const int64_t total = Mq * frames;
+    if (total == 0) return COFI_OK;
+    const float reach = kp_reach > 0.0f ? (kp_reach + sigma) * 1.001f : 1e18f;
+    const float reach2 = reach * reach;
+    const int wpb = 4;
+    const dim3 grid((unsigned)ceil_div(total, wpb)), block(wpb * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float4* sp = reinterpret_cast<const float4*>(s_packed);
+    __half* agg = reinterpret_cast<__half*>(agg_f16);
+#define LAUNCH(VEC, NCH)                                                                                         \
+    kpconv_aggregate_kernel<VEC, NCH, __half><<<grid, block, 0, st>>>(feats, ldf, C, sp, q_points, nbr, H, Mq, Ns, \
+                                                                      total, kernel_points, K, sigma, reach2, agg, cnt)
+    if (C <= 32) {
+        LAUNCH(1, 1);
+    } else if (C == 64) {
+        LAUNCH(2, 1);
+    } else if (C % 128 == 0 && C <= 1024 && ldf % 4 == 0) {
+        switch (C / 128) {
+            case 1: LAUNCH(4, 1); break;
+            case 2: LAUNCH(4, 2); break;
+            case 3: LAUNCH(4, 3); break;
+            case 4: LAUNCH(4, 4); break;
+            case 8: LAUNCH(4, 8); break;
+            default:
+                set_error("cofi_kpconv_aggregate_f16: unsupported channel count C=%d", C);
+                return COFI_EUNSUPPORTED;
+        }
+    } else {
+        set_error("cofi_kpconv_aggregate_f16: unsupported channel count C=%d", C);
+        return COFI_EUNSUPPORTED;
+    }
+#undef LAUNCH
+    return check_launch("cofi_kpconv_aggregate_f16");
 }
 
 extern "C" int cofi_maxpool_rows(const float* x, int64_t ldx, int C, const int64_t* nbr, int H, int64_t Mq,

@@ -4,6 +4,8 @@
 // same computation here: statistics per (frame, group of channels) over the R rows of the frame.
 // HBM-bound elementwise work: coalesced float loads along channels, fp64 statistics, two deterministic
 // passes (partials -> apply), no atomics.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cofi {
@@ -106,9 +108,15 @@ affine_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C
 
 // ---- vectorised variants (C % 4 == 0): thread = (4-channel chunk, row lane); no integer divisions in the loop ----
 // block = (TX, TY) with TX * TY = 256; grid = (row chunks <= kStatChunks, frames, channel-chunk groups)
+// The last CTA of each (frame, channel-chunk group) column -- elected with a self-resetting global counter -- also
+// reduces the partials of the groups that live entirely inside its channel range and writes (mean, rstd): the
+// separate finalize launch disappears.  Requires group boundaries aligned to the CTA's channel span (host-checked).
 __global__ void __launch_bounds__(256)
-norm_stats_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C, double* __restrict__ partials) {
+norm_stats_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C, double* __restrict__ partials,
+                      int G, float eps, float2* __restrict__ mean_rstd, float* __restrict__ mean_out,
+                      float* __restrict__ var_out, unsigned int* __restrict__ counters) {
     __shared__ double red[256][8 + 1];
+    __shared__ int s_last;
     const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
     const int c4 = blockIdx.z * TX + tx;
     const int frame = blockIdx.y, chunk = blockIdx.x;
@@ -145,6 +153,82 @@ norm_stats_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C
         for (int i = 0; i < 4; ++i) {
             o[2 * i] = s[i];
             o[2 * i + 1] = ss[i];
+        }
+    }
+    if (counters == nullptr) return;
+    // ---- elect the last CTA of this (frame, z) column
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int* ctr = counters + (frame * gridDim.z + blockIdx.z);
+        const unsigned int prev = atomicAdd(ctr, 1u);
+        s_last = (prev == gridDim.x - 1) ? 1 : 0;
+        if (s_last) *ctr = 0u;  // self-reset for the next launch (stream-ordered)
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- finalize the groups inside channels [blockIdx.z*TX*4, +TX*4): one warp per group, round robin
+    const int gs = C / G;
+    const int ch0 = blockIdx.z * TX * 4;
+    const int ch1 = (ch0 + TX * 4 < C) ? ch0 + TX * 4 : C;
+    const int g0 = ch0 / gs, g1 = (ch1 + gs - 1) / gs;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nchunks = gridDim.x;
+    const int items = nchunks * gs;
+    if (items >= 512) {
+        // few large groups (GroupNorm with wide groups): the whole CTA reduces one group at a time
+        for (int g = g0; g < g1; ++g) {
+            double a = 0.0, b = 0.0;
+#pragma unroll 4
+            for (int t = tid; t < items; t += 256) {
+                const int ck = t / gs, c = g * gs + (t - ck * gs);
+                const double* o = partials + (((int64_t)frame * kStatChunks + ck) * C + c) * 2;
+                a += __ldcg(o);
+                b += __ldcg(o + 1);
+            }
+            a = warp_sum_d(a);
+            b = warp_sum_d(b);
+            __syncthreads();
+            if (lane == 0) {
+                red[warp][0] = a;
+                red[warp][1] = b;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < 8; ++w) {
+                    a += red[w][0];
+                    b += red[w][1];
+                }
+                const double n = (double)R * gs;
+                const double mean = a / n;
+                double var = b / n - mean * mean;
+                if (var < 0.0) var = 0.0;
+                mean_rstd[(int64_t)frame * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+                if (mean_out) mean_out[(int64_t)frame * G + g] = (float)mean;
+                if (var_out) var_out[(int64_t)frame * G + g] = (float)var;
+            }
+        }
+        return;
+    }
+    for (int g = g0 + warp; g < g1; g += 8) {  // many small groups (InstanceNorm): one warp per group
+        double a = 0.0, b = 0.0;
+        for (int t = lane; t < items; t += 32) {
+            const int ck = t / gs, c = g * gs + (t - ck * gs);
+            const double* o = partials + (((int64_t)frame * kStatChunks + ck) * C + c) * 2;
+            a += __ldcg(o);
+            b += __ldcg(o + 1);
+        }
+        a = warp_sum_d(a);
+        b = warp_sum_d(b);
+        if (lane == 0) {
+            const double n = (double)R * gs;
+            const double mean = a / n;
+            double var = b / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            mean_rstd[(int64_t)frame * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+            if (mean_out) mean_out[(int64_t)frame * G + g] = (float)mean;
+            if (var_out) var_out[(int64_t)frame * G + g] = (float)var;
         }
     }
 }
@@ -296,6 +380,22 @@ extern "C" int64_t cofi_norm_rows_workspace(int frames, int C) {
     return (int64_t)frames * kStatChunks * C * 2 * sizeof(double) + (int64_t)frames * C * sizeof(float2) + 256;
 }
 
+static unsigned int* norm_counters() {
+    // one zero-initialised, self-resetting election counter array per device (4096 (frame, chunk-group) columns)
+    static unsigned int* ctr[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!ctr[dev]) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, 4096 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, 4096 * sizeof(unsigned int));
+        ctr[dev] = reinterpret_cast<unsigned int*>(p);
+    }
+    return ctr[dev];
+}
+
+extern "C" int cofi_norm_rows_init(void) { return norm_counters() ? COFI_OK : COFI_ECUDA; }
+
 extern "C" int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int frames, int G, const float* gamma,
                               const float* beta, float eps, const float* residual, int64_t ldr, int act, float* y,
                               int64_t ldy, void* partials, float* mean_out, float* var_out, void* stream) {
@@ -310,6 +410,7 @@ extern "C" int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int
     const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && (!residual || ldr % 4 == 0) &&
                      ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!residual || (uintptr_t)residual % 16 == 0);
     const int C4 = C / 4;
+    bool fused_finalize = false;
     int TX = 1;
     while (TX < C4 && TX < 32) TX <<= 1;
     const int TY = 256 / TX;
@@ -317,7 +418,15 @@ extern "C" int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int
     int stat_chunks = (int)(R / (4 * TY) < 1 ? 1 : (R / (4 * TY) > kStatChunks ? kStatChunks : R / (4 * TY)));
     if (vec) {
         dim3 grid((unsigned)stat_chunks, frames, zgroups), block(TX, TY);
-        norm_stats_vec_kernel<<<grid, block, 0, st>>>(x, ldx, R, C, part);
+        const int gs = C / G, span = TX * 4;
+        // fused finalize needs every group inside one CTA's channel span and an allocated counter array
+        // Measured on B200: the in-kernel election + finalize (MEMBAR.GPU per CTA, serial tail of the last CTA) costs
+        // more than the 5.7 us finalize launch it removes (2.46 -> 3.16 ms/step), so it stays off by default.
+        static const bool fuse = getenv("COFI_NORM_FUSED_FINALIZE") != nullptr;
+        unsigned int* ctr = (fuse && (span % gs == 0 || gs % span == 0) && gs <= span && (int64_t)frames * zgroups <= 4096)
+                                ? norm_counters() : nullptr;
+        fused_finalize = ctr != nullptr;
+        norm_stats_vec_kernel<<<grid, block, 0, st>>>(x, ldx, R, C, part, G, eps, mr, mean_out, var_out, ctr);
         int rc = check_launch("cofi_norm_rows(stats)");
         if (rc) return rc;
     } else {
@@ -327,7 +436,7 @@ extern "C" int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int
         int rc = check_launch("cofi_norm_rows(stats)");
         if (rc) return rc;
     }
-    {
+    if (!fused_finalize) {
         dim3 grid(G, frames);
         norm_finalize_kernel<<<grid, 128, 0, st>>>(part, vec ? stat_chunks : kStatChunks, R, C, G, eps, mr, mean_out, var_out);
         int rc = check_launch("cofi_norm_rows(finalize)");

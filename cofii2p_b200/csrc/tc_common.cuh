@@ -93,6 +93,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one thread: D[tmem] (+)= A[smem] * B[smem], fp16 operands, fp32 accumulate
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // warp-collective: lane i receives columns [col, col+32) of TMEM lane (lane_base + i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -128,6 +138,9 @@ __host__ __device__ constexpr uint32_t umma_idesc(int ab_format, int M, int N) {
 // Cached cuTensorMapEncodeTiled for fp32 tensors, 128-byte swizzle, zero OOB fill. dims/strides innermost first;
 // strides in bytes for dims 1..rank-1. Returns nullptr on failure (error text via cofi::set_error).
 const CUtensorMap* get_tmap_f32(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                const uint32_t* box);
+// same for fp16 tensors (box inner dimension = 64 elements = 128 bytes)
+const CUtensorMap* get_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                                 const uint32_t* box);
 
 }  // namespace tc

@@ -28,6 +28,7 @@ class KPConv(nn.Module):
         self._wt = None
         self._wt_version = None
         self._reach = None
+        self._wt16 = None
 
     def reset_parameters(self):
         nn.init.kaiming_uniform_(self.weights, a=math.sqrt(5))
@@ -45,6 +46,13 @@ class KPConv(nn.Module):
             self._wt_version = v
         return self._wt
 
+    def packed_weight_f16(self):
+        """fp16 copy of the K-major weight operand (tf32 engine), cached per parameter version."""
+        wt = self.packed_weight()
+        if self._wt16 is None or self._wt16[0] is not wt:
+            self._wt16 = (wt, wt.to(torch.float16))
+        return self._wt16[1]
+
     def kp_reach(self) -> float:
         """max_k |kernel_points[k]| (host scalar, cached): lets the kernel cull neighbours that no kernel point reaches."""
         v = (self.kernel_points._version, self.kernel_points.data_ptr())
@@ -55,6 +63,11 @@ class KPConv(nn.Module):
     def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1):
         """s_feats [B*N,Cin], q_points [B*M,3], s_points [B*N,3], neighbor_indices [B*M,H] -> [B*M,Cout]."""
         packed = ops.pack_points(s_points, s_feats)
+        if ops.engine_id() == ops.ENGINE_TF32 and (self.in_channels * self.kernel_size) % 8 == 0 and self.out_channels >= 16:
+            # tf32 engine: fp16 aggregate (same 11-bit operand precision as tf32), half the HBM round trip
+            agg, cnt = ops.kpconv_aggregate_f16(s_feats, packed, q_points, neighbor_indices, self.kernel_points,
+                                                self.sigma, frames, self.kp_reach())
+            return ops.gemm_f16(agg, self.packed_weight_f16(), bias=self.bias, rowdiv=cnt)
         agg, cnt = ops.kpconv_aggregate(s_feats, packed, q_points, neighbor_indices, self.kernel_points, self.sigma,
                                         frames, self.kp_reach())
         return ops.gemm(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt)

@@ -160,6 +160,39 @@ def kpconv_aggregate(feats, s_packed, q_points, nbr, kernel_points, sigma: float
     return agg, cnt
 
 
+def kpconv_aggregate_f16(feats, s_packed, q_points, nbr, kernel_points, sigma: float, frames: int = 1,
+                         kp_reach: float = 0.0):
+    """fp16 aggregate [M, K*C] (tf32 engine); see cofi_kpconv_aggregate_f16."""
+    feats, ldf = _rows(feats, "feats")
+    q_points = _f32(q_points, "q_points").contiguous()
+    nbr = _i64(nbr, "nbr")
+    kernel_points = _f32(kernel_points, "kernel_points").contiguous()
+    total_q, H = nbr.shape
+    Mq, Ns = total_q // frames, s_packed.shape[0] // frames
+    C, K = feats.shape[1], kernel_points.shape[0]
+    agg = torch.empty((total_q, K * C), dtype=torch.float16, device=feats.device)
+    cnt = torch.empty((total_q,), dtype=torch.float32, device=feats.device)
+    _meta(2.0 * total_q * K * H * C,
+          8.0 * total_q * H + 4.0 * feats.shape[0] * C + 16.0 * s_packed.shape[0] + 12.0 * total_q
+          + 2.0 * total_q * K * C + 4.0 * total_q)
+    _call("cofi_kpconv_aggregate_f16", _p(feats), ldf, C, _p(s_packed), _p(q_points), _p(nbr), H, Mq, Ns, frames,
+          _p(kernel_points), K, float(sigma), float(kp_reach), _p(agg), _p(cnt), _st())
+    return agg, cnt
+
+
+def gemm_f16(a_half, w_half, bias=None, rowdiv=None, act: int = ACT_NONE):
+    """fp16 operands, fp32 output (tcgen05 kind::f16)."""
+    if a_half.dtype != torch.float16 or w_half.dtype != torch.float16 or not a_half.is_cuda:
+        raise RuntimeError("gemm_f16: CUDA fp16 operands expected")
+    a_half, w_half = a_half.contiguous(), w_half.contiguous()
+    M, K = a_half.shape
+    N = w_half.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a_half.device)
+    _meta(2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N)
+    _call("cofi_gemm_f16", _p(a_half), K, _p(w_half), K, _p(out), N, M, N, K, _p(bias), _p(rowdiv), act, _st())
+    return out
+
+
 def maxpool_rows(x, nbr, frames: int = 1):
     x, ldx = _rows(x, "x")
     nbr = _i64(nbr, "nbr")

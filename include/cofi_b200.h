@@ -75,6 +75,14 @@ int cofi_kpconv_aggregate(const float* feats, int64_t ldf, int C,
                                             kp_reach + sigma are culled exactly; <= 0 disables */,
                           float* agg /* [frames*Mq, K*C] */, float* cnt /* [frames*Mq] */, void* stream);
 
+/* Same, with the aggregate written as fp16 [frames*Mq, K*C] (K*C % 8 == 0).  Used by the tf32 engine: fp16 carries the
+ * same 11 significand bits the tensor core keeps of a tf32 operand, halves the [M,15C] round trip through HBM and feeds
+ * cofi_gemm_f16 at twice the MMA rate. */
+int cofi_kpconv_aggregate_f16(const float* feats, int64_t ldf, int C, const float* s_packed, const float* q_points,
+                              const int64_t* nbr, int H, int64_t Mq, int64_t Ns, int frames,
+                              const float* kernel_points, int K, float sigma, float kp_reach,
+                              void* agg_f16, float* cnt, void* stream);
+
 /* out[m,c] = max_h x[nbr[m,h], c] with shadow rows = 0 (model/kpconv/functional.py:53-66). */
 int cofi_maxpool_rows(const float* x, int64_t ldx, int C, const int64_t* nbr, int H,
                       int64_t Mq, int64_t Ns, int frames, float* out, int64_t ldo, void* stream);
@@ -97,6 +105,11 @@ int cofi_gather_rows(const float* x, int64_t ldx, int C, const int64_t* idx, int
 int cofi_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
               int64_t M, int N, int K, const float* bias, const float* rowdiv, int accumulate, int act,
               int engine, void* stream);
+
+/* fp16-operand variant of cofi_gemm on tcgen05 (kind::f16, fp32 accumulate and output): A [M,K] and W [N,K] are fp16,
+ * K-major; K, lda, ldw multiples of 8; N >= 16. */
+int cofi_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N, int K,
+                  const float* bias, const float* rowdiv, int act, void* stream);
 
 /* C[M,N] = act(LayerNorm_N(A W^T + bias) * gamma + beta) + residual : Linear -> LayerNorm(eps) -> act -> + residual as
  * ONE kernel when a row fits a tile (N <= 128, N % 32 == 0, tensor-core engines): each epilogue thread owns a full
@@ -128,6 +141,9 @@ int cofi_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, const float* 
  * cofi_norm_rows_workspace(frames, C) bytes.  If mean_out/var_out != NULL (size frames*G) the batch
  * statistics are also written (BatchNorm running-stat update is done by the host). */
 int64_t cofi_norm_rows_workspace(int frames, int C);
+/* Allocates the per-device election counters of the fused statistics/finalize kernel. Call once per device BEFORE a
+ * CUDA-graph capture that contains cofi_norm_rows (the first cofi_norm_rows call does it implicitly otherwise). */
+int cofi_norm_rows_init(void);
 int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int frames, int G, const float* gamma,
                    const float* beta, float eps, const float* residual, int64_t ldr, int act, float* y,
                    int64_t ldy, void* partials, float* mean_out, float* var_out, void* stream);

@@ -93,6 +93,7 @@ def test_forward_golden_tc(cuda_model, engine, tol):
              "fine_pc_inline_feature"]
     errs = {nm: rel_err(val[i], torch.from_numpy(z["val/" + nm])) for i, nm in enumerate(names)}
     print(engine, errs)
+    open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", f"forward_err_{engine}.json"), "w").write(__import__("json").dumps(errs))
     assert max(errs.values()) < tol, errs
     if engine == "tf32x3":
         assert torch.equal(test[6].cpu(), torch.from_numpy(z["test/fine_center_xy"]))
@@ -155,3 +156,29 @@ def test_gemm_ln_fused(engine, m, n, k):
     finally:
         ops.set_engine("fp32")
     assert rel_err(got, ref) < (1e-2 if engine == "tf32" else 1e-4), rel_err(got, ref)
+
+
+@pytest.mark.parametrize("cin,cout,n,sigma,extent", [(32, 32, 1500, 0.2, 3.0), (64, 64, 1024, 0.4, 4.0), (128, 128, 700, 0.8, 6.0),
+                                                     (512, 512, 200, 3.2, 12.0)])
+def test_kpconv_f16_path(cin, cout, n, sigma, extent):
+    """tf32-engine KPConv: fp16 aggregate (== fp32 aggregate rounded to fp16) + kind::f16 GEMM vs the CPU oracle."""
+    from cofii2p_b200 import ops
+    from oracle import restate
+    g = torch.Generator().manual_seed(cin + n)
+    s_pts = torch.rand((n, 3), generator=g) * extent
+    d = torch.cdist(s_pts.double(), s_pts.double())
+    nbr = d.topk(128, dim=1, largest=False).indices
+    feats = torch.randn((n, cin), generator=g)
+    w = torch.randn((15, cin, cout), generator=g) / math.sqrt(cin)
+    b = torch.randn((cout,), generator=g) * 0.1
+    kp = torch.randn((15, 3), generator=g) * sigma * 0.8
+    kp[0] = 0
+    ref = restate.kpconv(feats, s_pts, s_pts, nbr, w, b, kp, sigma)
+    packed = ops.pack_points(s_pts.cuda(), feats.cuda())
+    reach = float(kp.norm(dim=1).max())
+    agg32, cnt32 = ops.kpconv_aggregate(feats.cuda(), packed, s_pts.cuda(), nbr.cuda(), kp.cuda(), sigma, 1, reach)
+    agg16, cnt16 = ops.kpconv_aggregate_f16(feats.cuda(), packed, s_pts.cuda(), nbr.cuda(), kp.cuda(), sigma, 1, reach)
+    assert torch.equal(agg16, agg32.to(torch.float16)) and torch.equal(cnt16, cnt32)
+    wt16 = w.reshape(-1, cout).t().contiguous().cuda().to(torch.float16)
+    out = ops.gemm_f16(agg16, wt16, bias=b.cuda(), rowdiv=cnt16)
+    assert rel_err(out, ref) < 5e-3, rel_err(out, ref)
