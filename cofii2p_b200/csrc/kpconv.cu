@@ -49,6 +49,15 @@ struct VecT<4> {
     using T = float4;
 };
 
+// One warp per query point.
+//   1. each lane loads 4 of the <=128 neighbours (one 16-byte gather of (x,y,z,flag) each), forms the relative position
+//      and culls exactly: |rel| > max|kp| + sigma can not be influenced by any kernel point;
+//   2. surviving ("near") neighbours are compacted in ascending-h order into a per-warp shared-memory list;
+//   3. the n_near x K (neighbour, kernel point) pairs are enumerated kernel-point-major and dealt 32 at a time to the
+//      lanes, so the sqrt/div influence evaluations are spread over the warp instead of 60 per lane; a ballot keeps the
+//      non-zero influences, which are consumed in order (same accumulation order as a dense h loop): broadcast
+//      (row, weight), every lane loads its float4 slice of that feature row and accumulates; when the kernel point
+//      changes the finished [C] row (or zeros) is stored.
 template <int VEC, int NCH, typename OutT = float>
 __global__ void __launch_bounds__(128)
 kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, const float4* __restrict__ s_packed,
@@ -56,37 +65,41 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
                         int64_t Ns, int64_t total_q, const float* __restrict__ kernel_points, int K, float sigma,
                         float reach2, OutT* __restrict__ agg, float* __restrict__ cnt_out) {
     __shared__ float skp[kMaxKP * 3];
+    __shared__ float4 snear[4][128];  // per warp: (rx, ry, rz, __int_as_float(row index))
     if (threadIdx.x < K * 3) skp[threadIdx.x] = kernel_points[threadIdx.x];
     __syncthreads();
 
-    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     const int lane = threadIdx.x & 31;
     if (m >= total_q) return;
     const int64_t frame = m / Mq;
     const float* fbase = feats + frame * Ns * ldf;
     const float4* sp = s_packed + frame * Ns;
     const float qx = __ldg(q_points + m * 3 + 0), qy = __ldg(q_points + m * 3 + 1), qz = __ldg(q_points + m * 3 + 2);
+    float4* near = snear[wib];
 
-    int idx[4];
-    float rx[4], ry[4], rz[4];
     float cnt = 0.0f;
+    int n_near = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int h = j * 32 + lane;
-        int64_t id = (h < H) ? __ldg(nbr + m * H + h) : Ns;
-        idx[j] = -1;
-        rx[j] = ry[j] = rz[j] = 0.0f;
+        const int64_t id = (h < H) ? __ldg(nbr + m * H + h) : Ns;
+        bool is_near = false;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
         if (id >= 0 && id < Ns) {
             const float4 p = __ldg(sp + id);
-            rx[j] = p.x - qx;  // neighbours - q_points, reference kpconv.py:93
-            ry[j] = p.y - qy;
-            rz[j] = p.z - qz;
+            rx = p.x - qx;  // neighbours - q_points, reference kpconv.py:93
+            ry = p.y - qy;
+            rz = p.z - qz;
             cnt += p.w;
-            // exact cull: a neighbour farther from the query than max|kp| + sigma has zero influence for every
-            // kernel point (triangle inequality; the margin absorbs fp32 rounding), so it never enters the k loop
-            if (rx[j] * rx[j] + ry[j] * ry[j] + rz[j] * rz[j] <= reach2) idx[j] = (int)id;
+            is_near = rx * rx + ry * ry + rz * rz <= reach2;
         }  // else shadow neighbour: point at 1e6, zero feature -> zero influence
+        const unsigned bal = __ballot_sync(0xffffffffu, is_near);
+        if (is_near) near[n_near + __popc(bal & ((1u << lane) - 1u))] = make_float4(rx, ry, rz, __int_as_float((int)id));
+        n_near += __popc(bal);
     }
+    __syncwarp();
     cnt = warp_sum(cnt);
     if (lane == 0) cnt_out[m] = fmaxf(cnt, 1.0f);
 
@@ -94,42 +107,13 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
     OutT* out_row = agg + m * (int64_t)K * C;
     const bool lane_active = (lane * VEC) < C;  // only matters for C < 32*VEC (C = 4)
 
-    for (int k = 0; k < K; ++k) {
-        const float kx = skp[k * 3 + 0], ky = skp[k * 3 + 1], kz = skp[k * 3 + 2];
-        float acc[NCH][VEC];
+    float acc[NCH][VEC];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
+    for (int c = 0; c < NCH; ++c)
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[c][v] = 0.0f;
+        for (int v = 0; v < VEC; ++v) acc[c][v] = 0.0f;
 
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float w = 0.0f;
-            if (idx[j] >= 0) {
-                // differences = neighbours - kernel_points; sq = sum(d^2); w = clamp(1 - sqrt(sq)/sigma, 0)
-                // (reference kpconv.py:97-99), evaluated without FMA contraction
-                const float dx = rx[j] - kx, dy = ry[j] - ky, dz = rz[j] - kz;
-                const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                w = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsqrt_rn(sq), sigma)), 0.0f);
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, w > 0.0f);
-            while (mask) {
-                const int l = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int i = __shfl_sync(0xffffffffu, idx[j], l);
-                const float ww = __shfl_sync(0xffffffffu, w, l);
-                const float* row = fbase + (int64_t)i * ldf;
-                if (lane_active) {
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        const V f = __ldg(reinterpret_cast<const V*>(row + (c * 32 + lane) * VEC));
-                        const float* fv = reinterpret_cast<const float*>(&f);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(ww, fv[v], acc[c][v]);
-                    }
-                }
-            }
-        }
+    auto store_row = [&](int k) {  // writes acc as row k and clears it
         if (lane_active) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -153,7 +137,49 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
                 }
             }
         }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[c][v] = 0.0f;
+    };
+
+    int cur_k = 0;  // kernel point whose row is being accumulated
+    const int total_pairs = n_near * K;
+    for (int base = 0; base < total_pairs; base += 32) {
+        const int pidx = base + lane;
+        float w = 0.0f;
+        int pk = 0, prow = 0;
+        if (pidx < total_pairs) {
+            pk = pidx / n_near;
+            const float4 nb = near[pidx - pk * n_near];
+            prow = __float_as_int(nb.w);
+            // differences = neighbours - kernel_points; sq = sum(d^2); w = clamp(1 - sqrt(sq)/sigma, 0)
+            // (reference kpconv.py:97-99), evaluated without FMA contraction
+            const float dx = nb.x - skp[pk * 3 + 0], dy = nb.y - skp[pk * 3 + 1], dz = nb.z - skp[pk * 3 + 2];
+            const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            w = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsqrt_rn(sq), sigma)), 0.0f);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, w > 0.0f);
+        while (mask) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int ek = __shfl_sync(0xffffffffu, pk, l);
+            const int er = __shfl_sync(0xffffffffu, prow, l);
+            const float ew = __shfl_sync(0xffffffffu, w, l);
+            while (cur_k < ek) store_row(cur_k++);  // finished rows (zeros when nothing influenced them)
+            if (lane_active) {
+                const float* row = fbase + (int64_t)er * ldf;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const V f = __ldg(reinterpret_cast<const V*>(row + (c * 32 + lane) * VEC));
+                    const float* fv = reinterpret_cast<const float*>(&f);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(ew, fv[v], acc[c][v]);
+                }
+            }
+        }
     }
+    while (cur_k < K) store_row(cur_k++);
 }
 
 // ------------------------------------------------------------------------------------------ maxpool_rows

@@ -126,7 +126,28 @@ norm_stats_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C
     double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
     if (c4 * 4 < C) {
         const float* p = x + ((int64_t)frame * R) * ldx + c4 * 4;
-        for (int64_t r = r0 + ty; r < r1; r += TY) {
+        // four independent row loads in flight per thread; a 4-row batch is summed in fp32 (exact enough: 4 terms),
+        // batches accumulate in fp64
+        int64_t r = r0 + ty;
+        for (; r + 3 * TY < r1; r += 4 * TY) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(p + (r + u * TY) * ldx));
+            float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                fs[0] += v[u].x; fq[0] = fmaf(v[u].x, v[u].x, fq[0]);
+                fs[1] += v[u].y; fq[1] = fmaf(v[u].y, v[u].y, fq[1]);
+                fs[2] += v[u].z; fq[2] = fmaf(v[u].z, v[u].z, fq[2]);
+                fs[3] += v[u].w; fq[3] = fmaf(v[u].w, v[u].w, fq[3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s[i] += (double)fs[i];
+                ss[i] += (double)fq[i];
+            }
+        }
+        for (; r < r1; r += TY) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(p + r * ldx));
             s[0] += v.x; ss[0] += (double)v.x * v.x;
             s[1] += v.y; ss[1] += (double)v.y * v.y;
@@ -256,16 +277,31 @@ norm_apply_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t R, int C
     const int64_t r0 = blockIdx.x * rows_per;
     const int64_t r1 = (r0 + rows_per < R) ? r0 + rows_per : R;
     const int64_t base = (int64_t)frame * R;
-    for (int64_t r = r0 + ty; r < r1; r += TY) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (base + r) * ldx + c4 * 4));
+    auto one = [&](const float4& v, const float4& rr, int64_t row) {
         float o[4] = {(v.x - mean[0]) * a[0] + b[0], (v.y - mean[1]) * a[1] + b[1], (v.z - mean[2]) * a[2] + b[2],
                       (v.w - mean[3]) * a[3] + b[3]};
-        if (residual) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + (base + r) * ldr + c4 * 4));
-            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
-        }
-        *reinterpret_cast<float4*>(y + (base + r) * ldy + c4 * 4) =
+        o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+        *reinterpret_cast<float4*>(y + row * ldy + c4 * 4) =
             make_float4(apply_act(o[0], act), apply_act(o[1], act), apply_act(o[2], act), apply_act(o[3], act));
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t r = r0 + ty;
+    for (; r + 3 * TY < r1; r += 4 * TY) {  // four independent rows in flight per thread
+        float4 v[4], rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t row = base + r + u * TY;
+            v[u] = __ldg(reinterpret_cast<const float4*>(x + row * ldx + c4 * 4));
+            rr[u] = residual ? __ldg(reinterpret_cast<const float4*>(residual + row * ldr + c4 * 4)) : zero4;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) one(v[u], rr[u], base + r + u * TY);
+    }
+    for (; r < r1; r += TY) {
+        const int64_t row = base + r;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * ldx + c4 * 4));
+        const float4 rr = residual ? __ldg(reinterpret_cast<const float4*>(residual + row * ldr + c4 * 4)) : zero4;
+        one(v, rr, row);
     }
 }
 
@@ -445,7 +481,7 @@ extern "C" int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int
     const int64_t rows = R * frames;
     if (vec) {
         // enough row chunks to fill the machine: ~4 CTAs per SM overall
-        int64_t want = (148 * 4) / ((int64_t)frames * zgroups);
+        int64_t want = (148 * 8) / ((int64_t)frames * zgroups);
         if (want < 1) want = 1;
         int64_t maxc = ceil_div(R, TY);
         if (want > maxc) want = maxc;
