@@ -249,6 +249,62 @@ maxpool_rows_kernel(const float* __restrict__ x, int64_t ldx, int C, const int64
     }
 }
 
+// fp16-input variant (tf32 engine): rounding is monotonic, so max over fp16-rounded rows == fp16-rounded max; the
+// gather moves half the bytes (the kernel is L2-gather-bound: 128 rows per output row).  8 channels (16 B) per lane.
+__global__ void __launch_bounds__(128)
+maxpool_rows_f16_kernel(const __half* __restrict__ x, int64_t ldx, int C, const int64_t* __restrict__ nbr, int H,
+                        int64_t Mq, int64_t Ns, int64_t total_q, float* __restrict__ out, int64_t ldo) {
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= total_q) return;
+    const int64_t frame = m / Mq;
+    const __half* xb = x + frame * Ns * ldx;
+    int idx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int h = j * 32 + lane;
+        int64_t id = (h < H) ? __ldg(nbr + m * H + h) : -2;
+        if (id >= Ns) id = -1;
+        idx[j] = (int)id;
+    }
+    for (int c0 = 0; c0 < C; c0 += 256) {
+        const int c = c0 + lane * 8;
+        const bool act = c < C;
+        __half2 mx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx[i] = __float2half2_rn(-65504.0f);
+        const __half2 zero2 = __float2half2_rn(0.0f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll 2
+            for (int l = 0; l < 32; l += 4) {
+                int id[4];
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, idx[j], l + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);  // shadow row = zeros
+                    if (id[u] >= 0 && act) v[u] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)id[u] * ldx + c));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (id[u] == -2) continue;
+                    const __half2* hv = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) mx[i] = __hmax2(mx[i], id[u] >= 0 ? hv[i] : zero2);
+                }
+            }
+        }
+        if (act) {
+            float* o = out + m * ldo + c;
+            const float2 a = __half22float2(mx[0]), b = __half22float2(mx[1]), cc = __half22float2(mx[2]), d = __half22float2(mx[3]);
+            *reinterpret_cast<float4*>(o) = make_float4(a.x, a.y, b.x, b.y);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(cc.x, cc.y, d.x, d.y);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- gather_rows
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ x, int64_t ldx, int C, const int64_t* __restrict__ idx,
@@ -391,6 +447,20 @@ extern "C" int cofi_maxpool_rows(const float* x, int64_t ldx, int C, const int64
     maxpool_rows_kernel<<<(unsigned)ceil_div(total, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
         x, ldx, C, nbr, H, Mq, Ns, total, out, ldo);
     return check_launch("cofi_maxpool_rows");
+}
+
+extern "C" int cofi_maxpool_rows_f16(const void* x_f16, int64_t ldx, int C, const int64_t* nbr, int H, int64_t Mq,
+                                     int64_t Ns, int frames, float* out, int64_t ldo, void* stream) {
+    COFI_REQUIRE(x_f16 && nbr && out, "cofi_maxpool_rows_f16: null pointer");
+    COFI_REQUIRE(H > 0 && H <= 128 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldo % 4 == 0 && ldx >= C && ldo >= C,
+                 "cofi_maxpool_rows_f16: C and ldx must be multiples of 8, ldo of 4");
+    COFI_REQUIRE(((uintptr_t)x_f16 % 16) == 0 && ((uintptr_t)out % 16) == 0, "cofi_maxpool_rows_f16: 16-byte alignment");
+    const int64_t total = Mq * frames;
+    if (total == 0) return COFI_OK;
+    const int wpb = 4;
+    maxpool_rows_f16_kernel<<<(unsigned)ceil_div(total, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(x_f16), ldx, C, nbr, H, Mq, Ns, total, out, ldo);
+    return check_launch("cofi_maxpool_rows_f16");
 }
 
 extern "C" int cofi_gather_rows(const float* x, int64_t ldx, int C, const int64_t* idx, int64_t idx_stride,

@@ -21,6 +21,7 @@ SIGNATURES = {
     "cofi_kpconv_aggregate": (_i, [_vp, _l, _i, _vp, _vp, _vp, _i, _l, _l, _i, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "cofi_kpconv_aggregate_f16": (_i, [_vp, _l, _i, _vp, _vp, _vp, _i, _l, _l, _i, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "cofi_maxpool_rows": (_i, [_vp, _l, _i, _vp, _i, _l, _l, _i, _vp, _l, _vp]),
+    "cofi_maxpool_rows_f16": (_i, [_vp, _l, _i, _vp, _i, _l, _l, _i, _vp, _l, _vp]),
     "cofi_gather_rows": (_i, [_vp, _l, _i, _vp, _l, _l, _l, _i, _vp, _l, _vp]),
     "cofi_gemm": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "cofi_gemm_f16": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _vp]),
@@ -42,6 +43,8 @@ SIGNATURES = {
     "cofi_attention": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _i, _vp]),
     "cofi_attention_vt": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp]),
     "cofi_sim_argmin": (_i, [_vp, _l, _vp, _l, _l, _l, _i, _i, _vp, _vp, _i, _vp]),
+    "cofi_sim_argmin_f16": (_i, [_vp, _l, _vp, _l, _l, _l, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "cofi_cast_f16": (_i, [_vp, _l, _l, _i, _vp, _l, _vp]),
     "cofi_select_matches": (_i, [_vp, _vp, _l, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "cofi_nn_argmin": (_i, [_vp, _l, _vp, _l, _vp, _vp]),
     "cofi_extract_patch": (_i, [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp, _vp]),

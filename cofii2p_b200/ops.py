@@ -203,6 +203,21 @@ def maxpool_rows(x, nbr, frames: int = 1):
     return out
 
 
+def maxpool_rows_f16(x_half, nbr, frames: int = 1):
+    """max over neighbours on an fp16 copy of the features (tf32 engine); fp32 result."""
+    if x_half.dtype != torch.float16 or not x_half.is_cuda:
+        raise RuntimeError("maxpool_rows_f16: CUDA fp16 features expected")
+    x_half = x_half.contiguous()
+    nbr = _i64(nbr, "nbr")
+    total_q, H = nbr.shape
+    C = x_half.shape[1]
+    out = torch.empty((total_q, C), dtype=torch.float32, device=x_half.device)
+    _meta(1.0 * total_q * H * C, 8.0 * total_q * H + 2.0 * x_half.numel() + 4.0 * total_q * C)
+    _call("cofi_maxpool_rows_f16", _p(x_half), C, C, _p(nbr), H, total_q // frames, x_half.shape[0] // frames, frames,
+          _p(out), C, _st())
+    return out
+
+
 def gather_rows(x, idx: Optional[torch.Tensor], idx_stride: int = 1, frames: int = 1, out: Optional[torch.Tensor] = None,
                 rows_out: Optional[int] = None):
     """out[i,:C] = x[idx[i*idx_stride]] per frame (idx None -> identity copy). `out` may be a column slice of a
@@ -432,6 +447,34 @@ def sim_argmin(pt, px, frames: int = 1, engine: Optional[int] = None):
     _meta(2.0 * frames * Npt * Npx * pt.shape[1], 4.0 * (pt.numel() + px.numel()) + 12.0 * pt.shape[0])
     _call("cofi_sim_argmin", _p(pt), ldpt, _p(px), ldpx, Npt, Npx, pt.shape[1], frames, _p(idx), _p(val),
                               ENGINE_FP32 if engine is None else engine, _st())
+    return idx, val
+
+
+def cast_f16(x):
+    x, ldx = _rows(x, "x")
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _call("cofi_cast_f16", _p(x), ldx, x.shape[0], x.shape[1], _p(y), x.shape[1], _st())
+    return y
+
+
+def sim_argmin_f16(pt_h, px_h, frames: int = 1):
+    """fp16 feature rows (cast_f16 of the L2-normalised features) -> (argmin index, min distance)."""
+    if pt_h.dtype != torch.float16 or px_h.dtype != torch.float16 or not pt_h.is_cuda:
+        raise RuntimeError("sim_argmin_f16: CUDA fp16 operands expected")
+    pt_h, px_h = pt_h.contiguous(), px_h.contiguous()
+    Npt, Npx = pt_h.shape[0] // frames, px_h.shape[0] // frames
+    C = pt_h.shape[1]
+    idx = torch.empty((pt_h.shape[0],), dtype=torch.int64, device=pt_h.device)
+    val = torch.empty((pt_h.shape[0],), dtype=torch.float32, device=pt_h.device)
+    ctas = ((Npt + 255) // 256) * frames
+    nsplit = max(1, min((Npx + 127) // 128, (2 * 148 + ctas - 1) // ctas)) if ctas < 148 else 1
+    ws_i = ws_v = None
+    if nsplit > 1:
+        ws_i = torch.empty((nsplit, pt_h.shape[0]), dtype=torch.int64, device=pt_h.device)
+        ws_v = torch.empty((nsplit, pt_h.shape[0]), dtype=torch.float32, device=pt_h.device)
+    _meta(2.0 * frames * Npt * Npx * C, 2.0 * (pt_h.numel() + px_h.numel()) + 12.0 * pt_h.shape[0])
+    _call("cofi_sim_argmin_f16", _p(pt_h), C, _p(px_h), C, Npt, Npx, C, frames, _p(idx), _p(val), nsplit, _p(ws_i), _p(ws_v),
+          _st())
     return idx, val
 
 

@@ -87,6 +87,11 @@ int cofi_kpconv_aggregate_f16(const float* feats, int64_t ldf, int C, const floa
 int cofi_maxpool_rows(const float* x, int64_t ldx, int C, const int64_t* nbr, int H,
                       int64_t Mq, int64_t Ns, int frames, float* out, int64_t ldo, void* stream);
 
+/* Same on an fp16 copy of x (cofi_cast_f16): exact max of the fp16-rounded rows (rounding is monotonic), half the
+ * gather bytes; fp32 output. tf32 engine only. C % 8 == 0. */
+int cofi_maxpool_rows_f16(const void* x_f16, int64_t ldx, int C, const int64_t* nbr, int H, int64_t Mq, int64_t Ns,
+                          int frames, float* out, int64_t ldo, void* stream);
+
 /* out[i, 0:C] = x[idx[i*idx_stride], 0:C] (shadow -> 0), or x[i] when idx == NULL.
  * nearest_upsample reads only column 0 of its [N,128] table (model/kpconv/functional.py:18-20):
  * idx_stride = 128.  `out` may point into a wider concat buffer (ldo) -> torch.cat of
@@ -211,6 +216,17 @@ int cofi_attention_vt(const float* q, const float* k, const float* vt, int64_t L
  * best_val[p] = min.  (model/network.py:174-179).  pt [frames*Npt, C], px [frames*Npx, C]. */
 int cofi_sim_argmin(const float* pt, int64_t ldpt, const float* px, int64_t ldpx, int64_t Npt, int64_t Npx, int C,
                     int frames, int64_t* best_idx, float* best_val, int engine, void* stream);
+
+/* fp16-operand throughput engine of the same fused similarity + arg-min (tcgen05 kind::f16, 256-point CTAs, TMEM fully
+ * used, matrix never written).  pt/px are fp16 [rows, C] (C = 64 or 128), e.g. produced by cofi_cast_f16 from the
+ * L2-normalised fp32 features. */
+int cofi_sim_argmin_f16(const void* pt, int64_t ldpt, const void* px, int64_t ldpx, int64_t Npt, int64_t Npx, int C,
+                        int frames, int64_t* best_idx, float* best_val,
+                        int nsplit /* >1: the pixel range is split over nsplit CTAs per point tile (fills the machine when
+                                      frames*Npt/256 < #SMs); partial results go to ws_* [nsplit, frames*Npt] and are merged */,
+                        int64_t* ws_idx, float* ws_val, void* stream);
+/* y[rows, C] (fp16) = x[rows, C] (fp32), round to nearest. C, ldx, ldy even. */
+int cofi_cast_f16(const float* x, int64_t ldx, int64_t rows, int C, void* y, int64_t ldy, void* stream);
 
 /* Test-mode selection loop of model/network.py:146-151 + :169,:184-186 in one kernel, per frame:
  * find the first threshold t in thresholds[0..nthr) with at least `min_count` points satisfying
