@@ -67,6 +67,7 @@ class CoFiI2P(nn.Module):
                                              nn.Conv2d(64, 1, 1, bias=False), nn.Sigmoid())
         self._img_pos = {}
         self._thr = {}
+        self._side_streams = {}
 
     # ------------------------------------------------------------------------------------------ pieces
     def _pc_feature(self, x):
@@ -101,29 +102,45 @@ class CoFiI2P(nn.Module):
           img_norm [B*HW,128], pc_norm [B*N4,128], img_score [B*HW,1], pc_score [B*N4,1],
           up2 NHWC [B,H/2,W/2,64] (L2-normalised), pc_decode_3 [B*N1,64] (L2-normalised)."""
         B = frames
-        pcs = self.pc_encoder(pc_data_dict, frames, taps)
-        s2, s4, s8 = self.img_encoder.forward_nhwc(img)
         hw = self.pe_H * self.pe_W
-        pc_decode_3 = ops.l2norm_rows(pcs[0])                                            # network.py:82
-        pc_pos = self.pc_pos_encoding(pc_data_dict["points"][-1])                         # :107
-        f_pc = ops.l2norm_rows(self._pc_feature(pcs[3]), add=pc_pos)                      # :84,:114
+        main = torch.cuda.current_stream()
+        # ---- image stream on a forked CUDA stream: ResNet + decoder are independent of the point stream (only the
+        # transformer joins them), so inside the captured graph the two branches run concurrently and the image
+        # branch's tensor-core convs fill the SMs left idle by the gather/HBM-bound point kernels.
+        side = self._side_streams.get(img.device)
+        if side is None:
+            side = self._side_streams[img.device] = torch.cuda.Stream(device=img.device)
         img_pos = self._image_pos(img.device)
         if B > 1:
             key = (str(img.device), B)
             if key not in self._img_pos:
                 self._img_pos[key] = img_pos.repeat(B, 1)
             img_pos = self._img_pos[key]
-        s8n = ops.l2norm_rows(s8.reshape(B * hw, 128))                                    # :90 (feeds decoder too)
-        f_img = ops.l2norm_rows(s8.reshape(B * hw, 128), add=img_pos)                     # :113
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            s2, s4, s8 = self.img_encoder.forward_nhwc(img)
+            s8n = ops.l2norm_rows(s8.reshape(B * hw, 128))                                # :90 (feeds decoder too)
+            f_img = ops.l2norm_rows(s8.reshape(B * hw, 128), add=img_pos)                 # :113
+            tokens_ready = torch.cuda.Event()
+            tokens_ready.record(side)
+            up4 = self.img_upsample_1.forward_nhwc(s8n.view(B, self.pe_H, self.pe_W, 128), s4)   # :129
+            up2 = self.img_upsample_2.forward_nhwc(up4, s2)                               # :130
+            Bh, Hh, Wh, Ch = up2.shape
+            up2n = ops.l2norm_rows(up2.reshape(-1, Ch)).view(Bh, Hh, Wh, Ch)
+        # ---- point stream on the main stream
+        pcs = self.pc_encoder(pc_data_dict, frames, taps)
+        pc_decode_3 = ops.l2norm_rows(pcs[0])                                            # network.py:82
+        pc_pos = self.pc_pos_encoding(pc_data_dict["points"][-1])                         # :107
+        f_pc = ops.l2norm_rows(self._pc_feature(pcs[3]), add=pc_pos)                      # :84,:114
+        main.wait_event(tokens_ready)
+        f_img_side = f_img  # keep the side-stream allocation alive until the join (no cross-stream block reuse)
         f_img, f_pc = self.transformer(f_img, f_pc, frames)                               # :115
         pc_score = self._score_head(self.pc_score_layer, f_pc, frames)                    # :123
         img_score = self._score_head(self.img_score_layer, f_img, frames)                 # :124
         pc_norm = ops.l2norm_rows(f_pc)                                                   # :125
         img_norm = ops.l2norm_rows(f_img)                                                 # :126
-        up4 = self.img_upsample_1.forward_nhwc(s8n.view(B, self.pe_H, self.pe_W, 128), s4)   # :129
-        up2 = self.img_upsample_2.forward_nhwc(up4, s2)                                   # :130
-        Bh, Hh, Wh, Ch = up2.shape
-        up2n = ops.l2norm_rows(up2.reshape(-1, Ch)).view(Bh, Hh, Wh, Ch)
+        main.wait_stream(side)  # join: decoder output (and every side-stream temporary) is complete from here on
+        del f_img_side
         if taps is not None:
             taps.update(img_s2=s2, img_s4=s4, img_s8=s8, tr_img=f_img, tr_pc=f_pc, img_up4=up4, img_up2=up2n,
                         pc_decode_3=pc_decode_3)
