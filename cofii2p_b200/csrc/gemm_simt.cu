@@ -179,11 +179,11 @@ int conv_simt_launch(const float* x, int B, int H, int W, int Cin, const float* 
 
 // tensor-core engines (gemm_tc.cu)
 int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
-                   int K, const Epilogue& ep, int engine, cudaStream_t st);
+                   int K, const Epilogue& ep, int engine, cudaStream_t st, float* stat_out = nullptr);
 bool gemm_tc_supported(int64_t lda, int64_t ldw, int64_t ldc, int64_t M, int N, int K, const void* A, const void* W,
                        const void* C);
 int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
-                       int K, const Epilogue& ep, cudaStream_t st);
+                       int K, const Epilogue& ep, cudaStream_t st, float* stat_out = nullptr);
 bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW, int pad,
                    float* y, const Epilogue& ep, int engine, cudaStream_t st);
@@ -259,4 +259,29 @@ extern "C" int cofi_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
     if (M == 0) return COFI_OK;
     Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, 0, act, nullptr, nullptr, 0.0f};
     return gemm_tc_f16_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, (cudaStream_t)stream);
+}
+
+// GEMM whose epilogue also emits per-128-row-tile column statistics (sum, sum of squares) of the stored output, so the
+// GroupNorm that follows (cofi_norm_rows_pre) skips its statistics pass.  tensor-core engines only; M % 128 == 0.
+extern "C" int cofi_gemm_colstats(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+                                  int64_t M, int N, int K, const float* bias, const float* rowdiv, int engine,
+                                  float* stats /* [M/128, N, 2] */, void* stream) {
+    COFI_REQUIRE(A && W && C && stats, "cofi_gemm_colstats: null pointer");
+    COFI_REQUIRE(M > 0 && M % 128 == 0 && N >= 16 && K > 0, "cofi_gemm_colstats: M must be a positive multiple of 128, N >= 16");
+    COFI_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K && ldc >= N, "cofi_gemm_colstats: bad leading dimension");
+    COFI_REQUIRE(engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3, "cofi_gemm_colstats: tensor-core engines only");
+    COFI_REQUIRE(gemm_tc_supported(lda, ldw, ldc, M, N, K, A, W, C), "cofi_gemm_colstats: shape/alignment unsupported");
+    Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, 0, COFI_ACT_NONE, nullptr, nullptr, 0.0f};
+    return gemm_tc_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, engine, (cudaStream_t)stream, stats);
+}
+
+extern "C" int cofi_gemm_f16_colstats(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc,
+                                      int64_t M, int N, int K, const float* bias, const float* rowdiv, float* stats,
+                                      void* stream) {
+    COFI_REQUIRE(A && W && C && stats, "cofi_gemm_f16_colstats: null pointer");
+    COFI_REQUIRE(M > 0 && M % 128 == 0 && N >= 16 && K >= 8, "cofi_gemm_f16_colstats: M must be a positive multiple of 128");
+    COFI_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K && ldc >= N, "cofi_gemm_f16_colstats: bad leading dimension");
+    COFI_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "cofi_gemm_f16_colstats: 16-byte alignment");
+    Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, 0, COFI_ACT_NONE, nullptr, nullptr, 0.0f};
+    return gemm_tc_f16_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, (cudaStream_t)stream, stats);
 }

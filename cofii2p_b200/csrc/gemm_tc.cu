@@ -149,6 +149,7 @@ struct Params {
     Epilogue ep;
     // convolution geometry (CONV only)
     int Ho, Wo, Cin, cpt /* 32-channel chunks per tap */, KW, pad, tiles_w, tiles_per_img;
+    float* stat_out;  // optional [row tiles][N][2] per-tile column (sum, sum of squares) of the stored output
     int dbg;  // COFI_TC_DEBUG bits (perf triage only): 1 = skip global stores, 2 = skip TMA+MMA
 };
 
@@ -164,7 +165,7 @@ struct Cfg {
     static constexpr int STAGE = A_BYTES + B_BYTES;
     static constexpr int NS = (BN == 128) ? 3 : 4;
     static constexpr int RING = STAGE * NS * (X3 ? 2 : 1);
-    static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */ + 4 * BN * 4 /* epilogue vectors */;
+    static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */ + 12 * BN * 4 /* epilogue vectors + column statistics */;
     static constexpr int THREADS = X3 ? 320 : 192;
 };
 
@@ -185,6 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s_shift = s_scale + BN;                                   // [BN] per-column shift (+bias)
     float* s_gamma = s_shift + BN;                                   // [BN] fused-LayerNorm weight
     float* s_beta = s_gamma + BN;                                    // [BN] fused-LayerNorm bias
+    float* s_col = s_beta + BN;                                      // [4 quarters][BN][2] column statistics
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
@@ -425,6 +427,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     *reinterpret_cast<float4*>(st + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
             __syncwarp();
+            if (p.stat_out) {
+                // per-tile column statistics for the GroupNorm that follows (host guarantees M % 128 == 0, act none):
+                // lane = column, 32 conflict-free shared loads over this warp's 32 staged rows
+                float cs = 0.0f, cq = 0.0f;
+                if (nb + lane < p.N) {
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const float x = stage[rr * 36 + lane];
+                        cs += x;
+                        cq = fmaf(x, x, cq);
+                    }
+                }
+                s_col[(q * BN + c0 + lane) * 2 + 0] = cs;
+                s_col[(q * BN + c0 + lane) * 2 + 1] = cq;
+            }
             // transposed write-out: 8 lanes cover the 32 columns (128 B) of one row, 4 rows per instruction, so every
             // store instruction writes four full 128-byte lines (the per-thread-row layout would scatter 16-byte pieces)
             if (nb < p.N && !(p.dbg & 5)) {
@@ -457,6 +474,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next chunk
+        }
+        if (p.stat_out) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int t = threadIdx.x - 64;
+            if (t < BN && n0 + t < p.N) {
+                float cs = 0.0f, cq = 0.0f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    cs += s_col[(qq * BN + t) * 2 + 0];
+                    cq += s_col[(qq * BN + t) * 2 + 1];
+                }
+                float* o = p.stat_out + ((int64_t)blockIdx.x * p.N + n0 + t) * 2;
+                o[0] = cs;
+                o[1] = cq;
+            }
         }
         tc_fence_before();
     } else if (X3) {
@@ -553,7 +585,7 @@ bool gemm_tc_supported(int64_t lda, int64_t ldw, int64_t ldc, int64_t M, int N, 
 }
 
 int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
-                   int K, const Epilogue& ep, int engine, cudaStream_t st) {
+                   int K, const Epilogue& ep, int engine, cudaStream_t st, float* stat_out) {
     using namespace tc;
     const int bn = pick_bn(N);
     uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * 4};
@@ -570,6 +602,7 @@ int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, flo
     p.N = N;
     p.num_kb = (K + TK - 1) / TK;
     p.ep = ep;
+    p.stat_out = stat_out;
     p.dbg = tc_debug();
     dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
     return dispatch<false>(ta, tb, p, bn, engine == COFI_GEMM_TF32X3, grid, st);
@@ -578,7 +611,7 @@ int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, flo
 // fp16-operand GEMM (A [M,K] half, W [N,K] half, fp32 accumulate/output): KPConv weight-apply on the tf32 engine.
 // fp16 keeps 11 significand bits -- the same operand precision as tf32 -- at half the bytes and twice the MMA rate.
 int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
-                       int K, const Epilogue& ep, cudaStream_t st) {
+                       int K, const Epilogue& ep, cudaStream_t st, float* stat_out) {
     using namespace tc;
     const int bn = pick_bn(N);
     uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * 2};
@@ -595,6 +628,7 @@ int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, f
     p.N = N;
     p.num_kb = (K + 63) / 64;
     p.ep = ep;
+    p.stat_out = stat_out;
     p.dbg = tc_debug();
     dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
     if (bn == 32) return launch_one<32, false, false, true>(ta, tb, p, grid, st);

@@ -106,6 +106,39 @@ affine_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C
     }
 }
 
+// finalize from the fp32 per-tile column statistics a GEMM epilogue produced: tiles [frames][tiles_per_frame][C][2]
+__global__ void __launch_bounds__(128)
+norm_finalize_tiles_kernel(const float* __restrict__ tiles, int tiles_per_frame, int64_t R, int C, int G, float eps,
+                           float2* __restrict__ mean_rstd) {
+    const int frame = blockIdx.y, g = blockIdx.x;
+    const int gs = C / G;
+    double s = 0.0, ss = 0.0;
+    for (int t = threadIdx.x; t < tiles_per_frame * gs; t += blockDim.x) {
+        const int tile = t / gs, c = g * gs + (t - tile * gs);
+        const float2 v = __ldg(reinterpret_cast<const float2*>(tiles) + ((int64_t)frame * tiles_per_frame + tile) * C + c);
+        s += (double)v.x;
+        ss += (double)v.y;
+    }
+    __shared__ double sh[2][4];
+    s = warp_sum_d(s);
+    ss = warp_sum_d(ss);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        sh[0][w] = s;
+        sh[1][w] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+        ss = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+        const double n = (double)R * gs;
+        const double mean = s / n;
+        double var = ss / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mean_rstd[(int64_t)frame * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+}
+
 // ---- vectorised variants (C % 4 == 0): thread = (4-channel chunk, row lane); no integer divisions in the loop ----
 // block = (TX, TY) with TX * TY = 256; grid = (row chunks <= kStatChunks, frames, channel-chunk groups)
 // The last CTA of each (frame, channel-chunk group) column -- elected with a self-resetting global counter -- also
@@ -551,4 +584,36 @@ extern "C" int cofi_colnorm_rows(const float* x, int64_t ldx, int64_t L, int C, 
     const int64_t rows = L * frames;
     colnorm_apply_kernel<<<ew_blocks(rows * C, 256), 256, 0, st>>>(x, ldx, L, C, rows, denom, y, ldy);
     return check_launch("cofi_colnorm_rows(apply)");
+}
+
+// GroupNorm whose statistics were produced by the preceding GEMM's epilogue (cofi_gemm_colstats): finalize + apply only.
+extern "C" int cofi_norm_rows_pre(const float* x, int64_t ldx, int64_t R, int C, int frames, int G, const float* gamma,
+                                  const float* beta, float eps, const float* residual, int64_t ldr, int act, float* y,
+                                  int64_t ldy, const float* tile_stats, void* workspace, void* stream) {
+    COFI_REQUIRE(x && y && tile_stats && workspace, "cofi_norm_rows_pre: null pointer");
+    COFI_REQUIRE(R > 0 && R % 128 == 0 && C > 0 && C % 4 == 0 && frames > 0 && G > 0 && C % G == 0,
+                 "cofi_norm_rows_pre: R must be a multiple of 128, C of 4");
+    COFI_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && (!residual || ldr % 4 == 0), "cofi_norm_rows_pre: leading dimensions % 4");
+    COFI_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)workspace % 8) == 0 &&
+                     (!residual || (uintptr_t)residual % 16 == 0), "cofi_norm_rows_pre: alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* mr = reinterpret_cast<float2*>(workspace);  // frames*G float2
+    {
+        dim3 grid(G, frames);
+        norm_finalize_tiles_kernel<<<grid, 128, 0, st>>>(tile_stats, (int)(R / 128), R, C, G, eps, mr);
+        int rc = check_launch("cofi_norm_rows_pre(finalize)");
+        if (rc) return rc;
+    }
+    const int C4 = C / 4;
+    int TX = 1;
+    while (TX < C4 && TX < 32) TX <<= 1;
+    const int TY = 256 / TX;
+    const unsigned zgroups = (unsigned)ceil_div(C4, TX);
+    int64_t want = (148 * 8) / ((int64_t)frames * zgroups);
+    if (want < 1) want = 1;
+    const int64_t maxc = ceil_div(R, TY);
+    if (want > maxc) want = maxc;
+    dim3 grid((unsigned)want, frames, zgroups), block(TX, TY);
+    norm_apply_vec_kernel<<<grid, block, 0, st>>>(x, ldx, R, C, G, mr, gamma, beta, residual, ldr, act, y, ldy);
+    return check_launch("cofi_norm_rows_pre(apply)");
 }

@@ -25,11 +25,14 @@ SIGNATURES = {
     "cofi_gather_rows": (_i, [_vp, _l, _i, _vp, _l, _l, _l, _i, _vp, _l, _vp]),
     "cofi_gemm": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "cofi_gemm_f16": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _vp]),
+    "cofi_gemm_colstats": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "cofi_gemm_f16_colstats": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _vp, _vp]),
     "cofi_gemm_ln": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _vp, _f, _i, _vp, _l, _i, _vp]),
     "cofi_conv2d_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "cofi_norm_rows_workspace": (_l, [_i, _i]),
     "cofi_norm_rows_init": (_i, []),
     "cofi_norm_rows": (_i, [_vp, _l, _l, _i, _i, _i, _vp, _vp, _f, _vp, _l, _i, _vp, _l, _vp, _vp, _vp, _vp]),
+    "cofi_norm_rows_pre": (_i, [_vp, _l, _l, _i, _i, _i, _vp, _vp, _f, _vp, _l, _i, _vp, _l, _vp, _vp, _vp]),
     "cofi_affine_rows": (_i, [_vp, _l, _l, _i, _vp, _vp, _vp, _l, _i, _vp, _l, _vp]),
     "cofi_layer_norm_rows": (_i, [_vp, _l, _l, _i, _vp, _vp, _f, _i, _vp, _l, _vp, _l, _vp]),
     "cofi_l2norm_rows": (_i, [_vp, _l, _l, _i, _vp, _l, _vp, _l, _vp]),

@@ -60,14 +60,20 @@ class KPConv(nn.Module):
             self._reach = (v, float(self.kernel_points.detach().norm(dim=1).max().item()))
         return self._reach[1]
 
-    def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1):
+    def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1, want_stats: bool = False):
         """s_feats [B*N,Cin], q_points [B*M,3], s_points [B*N,3], neighbor_indices [B*M,H] -> [B*M,Cout]."""
         packed = ops.pack_points(s_points, s_feats)
         if ops.engine_id() == ops.ENGINE_TF32 and (self.in_channels * self.kernel_size) % 8 == 0 and self.out_channels >= 16:
             # tf32 engine: fp16 aggregate (same 11-bit operand precision as tf32), half the HBM round trip
             agg, cnt = ops.kpconv_aggregate_f16(s_feats, packed, q_points, neighbor_indices, self.kernel_points,
                                                 self.sigma, frames, self.kp_reach())
-            return ops.gemm_f16(agg, self.packed_weight_f16(), bias=self.bias, rowdiv=cnt)
+            if want_stats and ops.colstats_ok(q_points.shape[0], frames, self.out_channels):
+                return ops.gemm_f16_colstats(agg, self.packed_weight_f16(), bias=self.bias, rowdiv=cnt)
+            out = ops.gemm_f16(agg, self.packed_weight_f16(), bias=self.bias, rowdiv=cnt)
+            return (out, None) if want_stats else out
         agg, cnt = ops.kpconv_aggregate(s_feats, packed, q_points, neighbor_indices, self.kernel_points, self.sigma,
                                         frames, self.kp_reach())
-        return ops.gemm(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt)
+        if want_stats and ops.colstats_ok(q_points.shape[0], frames, self.out_channels):
+            return ops.gemm_colstats(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt)
+        out = ops.gemm(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt)
+        return (out, None) if want_stats else out

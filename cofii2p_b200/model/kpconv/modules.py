@@ -20,7 +20,10 @@ class GroupNorm(nn.Module):
         self.num_groups, self.num_channels = num_groups, num_channels
         self.norm = nn.GroupNorm(num_groups, num_channels)
 
-    def forward(self, x, frames: int = 1, act: int = ops.ACT_NONE, residual=None):
+    def forward(self, x, frames: int = 1, act: int = ops.ACT_NONE, residual=None, tile_stats=None):
+        if tile_stats is not None:  # statistics came out of the producing GEMM's epilogue
+            return ops.norm_rows_pre(x, tile_stats, frames, self.num_groups, self.norm.weight, self.norm.bias, self.norm.eps,
+                                     residual=residual, act=act)
         return ops.norm_rows(x, frames, self.num_groups, self.norm.weight, self.norm.bias, self.norm.eps,
                              residual=residual, act=act)
 
@@ -41,10 +44,13 @@ class UnaryBlock(nn.Module):
         self.leaky_relu = nn.LeakyReLU(0.1) if has_relu else None
 
     def forward(self, x, frames: int = 1, residual=None, final_act: int = None):
-        y = ops.gemm(x, self.mlp.weight, bias=self.mlp.bias)
         act = ops.ACT_LRELU if self.leaky_relu is not None else ops.ACT_NONE
         if final_act is not None:
             act = final_act
+        if ops.colstats_ok(x.shape[0], frames, self.out_channels):
+            y, st = ops.gemm_colstats(x, self.mlp.weight, bias=self.mlp.bias)
+            return self.norm(y, frames, act=act, residual=residual, tile_stats=st)
+        y = ops.gemm(x, self.mlp.weight, bias=self.mlp.bias)
         return self.norm(y, frames, act=act, residual=residual)
 
 
@@ -68,8 +74,8 @@ class ConvBlock(nn.Module):
         self.leaky_relu = nn.LeakyReLU(negative_slope=negative_slope)
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1):
-        x = self.KPConv(s_feats, q_points, s_points, neighbor_indices, frames)
-        return self.norm(x, frames, act=ops.ACT_LRELU)
+        x, st = self.KPConv(s_feats, q_points, s_points, neighbor_indices, frames, want_stats=True)
+        return self.norm(x, frames, act=ops.ACT_LRELU, tile_stats=st)
 
 
 class ResidualBlock(nn.Module):
@@ -89,8 +95,8 @@ class ResidualBlock(nn.Module):
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1):
         x = self.unary1(s_feats, frames) if isinstance(self.unary1, UnaryBlock) else s_feats
-        x = self.KPConv(x, q_points, s_points, neighbor_indices, frames)
-        x = self.norm_conv(x, frames, act=ops.ACT_LRELU)
+        x, st = self.KPConv(x, q_points, s_points, neighbor_indices, frames, want_stats=True)
+        x = self.norm_conv(x, frames, act=ops.ACT_LRELU, tile_stats=st)
         shortcut = maxpool(s_feats, neighbor_indices, frames) if self.strided else s_feats
         if isinstance(self.unary_shortcut, UnaryBlock):
             shortcut = self.unary_shortcut(shortcut, frames)

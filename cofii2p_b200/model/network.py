@@ -68,6 +68,7 @@ class CoFiI2P(nn.Module):
         self._img_pos = {}
         self._thr = {}
         self._side_streams = {}
+        self.fork_image_stream = True  # run the image branch on a forked CUDA stream (bench's per-kernel profile pass turns it off)
 
     # ------------------------------------------------------------------------------------------ pieces
     def _pc_feature(self, x):
@@ -107,7 +108,7 @@ class CoFiI2P(nn.Module):
         # ---- image stream on a forked CUDA stream: ResNet + decoder are independent of the point stream (only the
         # transformer joins them), so inside the captured graph the two branches run concurrently and the image
         # branch's tensor-core convs fill the SMs left idle by the gather/HBM-bound point kernels.
-        side = self._side_streams.get(img.device)
+        side = self._side_streams.get(img.device) if self.fork_image_stream else main
         if side is None:
             side = self._side_streams[img.device] = torch.cuda.Stream(device=img.device)
         img_pos = self._image_pos(img.device)

@@ -258,6 +258,49 @@ def gemm(a, w, bias=None, rowdiv=None, act: int = ACT_NONE, out: Optional[torch.
     return out
 
 
+def gemm_colstats(a, w, bias=None, rowdiv=None):
+    """tensor-core GEMM that also returns the per-128-row-tile column statistics of its output (for norm_rows_pre)."""
+    a, lda = _rows(a, "a")
+    w, ldw = _rows(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    stats = torch.empty((M // 128, N, 2), dtype=torch.float32, device=a.device)
+    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
+    _call("cofi_gemm_colstats", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(rowdiv), _engine, _p(stats), _st())
+    return out, stats
+
+
+def gemm_f16_colstats(a_half, w_half, bias=None, rowdiv=None):
+    a_half, w_half = a_half.contiguous(), w_half.contiguous()
+    M, K = a_half.shape
+    N = w_half.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a_half.device)
+    stats = torch.empty((M // 128, N, 2), dtype=torch.float32, device=a_half.device)
+    _meta(2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N)
+    _call("cofi_gemm_f16_colstats", _p(a_half), K, _p(w_half), K, _p(out), N, M, N, K, _p(bias), _p(rowdiv), _p(stats), _st())
+    return out, stats
+
+
+def colstats_ok(rows: int, frames: int, n: int) -> bool:
+    """GEMM-epilogue statistics apply on the tf32 engine when every frame is a whole number of 128-row tiles."""
+    return _engine == ENGINE_TF32 and rows % frames == 0 and (rows // frames) % 128 == 0 and n >= 16 and n % 4 == 0
+
+
+def norm_rows_pre(x, stats, frames: int, groups: int, gamma, beta, eps: float = 1e-5, residual=None, act: int = ACT_NONE):
+    x, ldx = _rows(x, "x")
+    rows, C = x.shape
+    y = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+    ws = torch.empty((frames * groups * 2,), dtype=torch.float32, device=x.device)
+    ldr = 0
+    if residual is not None:
+        residual, ldr = _rows(residual, "residual")
+    _meta(4.0 * rows * C, 4.0 * rows * C * (2 + (residual is not None)))
+    _call("cofi_norm_rows_pre", _p(x), ldx, rows // frames, C, frames, groups, _p(gamma), _p(beta), float(eps), _p(residual), ldr,
+          act, _p(y), C, _p(stats), _p(ws), _st())
+    return y
+
+
 def gemm_ln(a, w, gamma, beta, eps: float = 1e-5, bias=None, act: int = ACT_NONE, residual=None,
             engine: Optional[int] = None):
     """act(LayerNorm(a @ w.T + bias)) + residual, one kernel on the tensor-core engines when N <= 128."""

@@ -116,6 +116,15 @@ int cofi_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, float* C
 int cofi_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N, int K,
                   const float* bias, const float* rowdiv, int act, void* stream);
 
+/* cofi_gemm / cofi_gemm_f16 whose epilogue ALSO writes, per 128-row tile, the column sums and sums of squares of the
+ * stored output: stats[M/128, N, 2] (fp32).  The GroupNorm that follows every point-branch Linear / KPConv
+ * (model/kpconv/modules.py:89-94,155-159,222-240) then needs no statistics pass: cofi_norm_rows_pre reduces the tiles
+ * (fp64) and applies.  Tensor-core engines, M % 128 == 0, no activation. */
+int cofi_gemm_colstats(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
+                       int K, const float* bias, const float* rowdiv, int engine, float* stats, void* stream);
+int cofi_gemm_f16_colstats(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
+                           int K, const float* bias, const float* rowdiv, float* stats, void* stream);
+
 /* C[M,N] = act(LayerNorm_N(A W^T + bias) * gamma + beta) + residual : Linear -> LayerNorm(eps) -> act -> + residual as
  * ONE kernel when a row fits a tile (N <= 128, N % 32 == 0, tensor-core engines): each epilogue thread owns a full
  * output row in TMEM and normalises it in registers (model/transformer/transformer.py:57-58,61-64: merge+norm1 and
@@ -152,6 +161,12 @@ int cofi_norm_rows_init(void);
 int cofi_norm_rows(const float* x, int64_t ldx, int64_t R, int C, int frames, int G, const float* gamma,
                    const float* beta, float eps, const float* residual, int64_t ldr, int act, float* y,
                    int64_t ldy, void* partials, float* mean_out, float* var_out, void* stream);
+
+/* cofi_norm_rows with the statistics taken from cofi_gemm_colstats tiles (R % 128 == 0): finalize + apply only.
+ * workspace: frames*G*8 bytes. */
+int cofi_norm_rows_pre(const float* x, int64_t ldx, int64_t R, int C, int frames, int G, const float* gamma,
+                       const float* beta, float eps, const float* residual, int64_t ldr, int act, float* y, int64_t ldy,
+                       const float* tile_stats, void* workspace, void* stream);
 
 /* y = act(x*scale[c] + shift[c] + residual): eval-mode BatchNorm as a per-channel affine. */
 int cofi_affine_rows(const float* x, int64_t ldx, int64_t rows, int C, const float* scale, const float* shift,

@@ -218,3 +218,34 @@ def test_maxpool_f16_is_rounded_exact_max():
     xs = torch.cat((x.to(torch.float16).float(), torch.zeros(1, 512)), 0)
     ref = xs[nbr.reshape(-1)].view(450, 128, 512).max(1)[0]
     assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("rows,frames,k,n,groups", [(2560, 2, 64, 128, 32), (1280, 1, 480, 32, 32), (1024, 8, 128, 256, 32)])
+def test_gemm_colstats_feeds_groupnorm(rows, frames, k, n, groups):
+    """GEMM-epilogue column statistics + norm_rows_pre == GEMM + two-pass norm_rows (same engine), and both match torch."""
+    from cofii2p_b200 import ops
+    g = torch.Generator().manual_seed(rows + k + n)
+    a = torch.randn((rows * frames, k), generator=g)
+    w = torch.randn((n, k), generator=g) / math.sqrt(k)
+    b = torch.randn((n,), generator=g)
+    gamma, beta = torch.randn((n,), generator=g), torch.randn((n,), generator=g)
+    res = torch.randn((rows * frames, n), generator=g)
+    ops.set_engine("tf32")
+    try:
+        assert ops.colstats_ok(rows * frames, frames, n)
+        y, st = ops.gemm_colstats(a.cuda(), w.cuda(), bias=b.cuda())
+        got = ops.norm_rows_pre(y, st, frames, groups, gamma.cuda(), beta.cuda(), 1e-5, residual=res.cuda(), act=ops.ACT_LRELU)
+        y2 = ops.gemm(a.cuda(), w.cuda(), bias=b.cuda())
+        ref2 = ops.norm_rows(y2, frames, groups, gamma.cuda(), beta.cuda(), 1e-5, residual=res.cuda(), act=ops.ACT_LRELU)
+        assert torch.equal(y, y2)
+        # column sums agree with the stored output
+        assert rel_err(st[..., 0].sum(0), y.double().sum(0).float()) < 1e-4
+        assert rel_err(got, ref2) < 1e-5
+    finally:
+        ops.set_engine("fp32")
+    lin = torch.nn.functional.linear(a.double(), w.double(), b.double())
+    refs = []
+    for f in range(frames):
+        yy = F.group_norm(lin[f * rows:(f + 1) * rows].t().unsqueeze(0), groups, gamma.double(), beta.double(), 1e-5).squeeze(0).t()
+        refs.append(F.leaky_relu(yy.float() + res[f * rows:(f + 1) * rows], 0.1))
+    assert rel_err(got, torch.cat(refs)) < 1e-2
