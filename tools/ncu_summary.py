@@ -78,5 +78,43 @@ def full(path, out):
     print(open(out).read()[:2500])
 
 
+def family(name):
+    """kernel name -> the op family bench.py reports"""
+    m = re.search(r"gemm_tc_kernel<\(?(?:int\))?\s*(\d+),\s*\(?(?:bool\))?\s*(\d)", name)
+    if m:
+        return "cofi_conv2d_nhwc" if m.group(2) == "1" else "cofi_gemm*"
+    if "gemm_simt_kernel" in name:
+        return "cofi_conv2d_nhwc" if "ConvA" in name else "cofi_gemm*"
+    for key, fam in (("kpconv_aggregate", "cofi_kpconv_aggregate*"), ("attention_tc", "cofi_attention_vt"),
+                     ("attention_simt", "cofi_attention"), ("maxpool_rows_f16", "cofi_maxpool_rows_f16"),
+                     ("maxpool_rows", "cofi_maxpool_rows"), ("norm_", "cofi_norm_rows*"), ("sim_argmin", "cofi_sim_argmin")):
+        if key in name:
+            return fam
+    return re.sub(r"_kernel.*", "", name.split("::")[-1])
+
+
+def traffic(path, out):
+    """per-family average DRAM bytes per launch -> profiles/traffic.json (read by bench.py)"""
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        d = per.setdefault(row["ID"], {"name": re.sub(r"\(.*", "", row["Kernel Name"])})
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        if row["Metric Name"].startswith("dram__bytes"):
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            d["bytes"] = d.get("bytes", 0.0) + v * mult
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for d in per.values():
+        f = family(d["name"])
+        agg[f][0] += 1
+        agg[f][1] += d.get("bytes", 0.0)
+    res = {k: v[1] / v[0] for k, v in agg.items()}
+    json.dump(res, open(out, "w"), indent=1, sort_keys=True)
+    for k, v in sorted(res.items(), key=lambda kv: -kv[1] * agg[kv[0]][0]):
+        print(f"{k:32s} launches={agg[k][0]:4d} avg_dram_MB_per_launch={v/1e6:9.2f} total_GB={v*agg[k][0]/1e9:7.2f}")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
