@@ -128,7 +128,7 @@ extern "C" int cofi_attention_vt(const float* q, const float* k, const float* vt
                      ((uintptr_t)out % 16) == 0,
                  "cofi_attention_vt: 16-byte alignment required");
     if (!attention_tc_supported(L, S, heads, D)) {
-        set_error("cofi_attention_vt: unsupported shape (D=%d must be 32, frames*S*4 bytes must be 16-byte aligned)", D);
+        set_error("cofi_attention_vt: unsupported shape (D=%d must be 32 or 64, frames*S*4 bytes must be 16-byte aligned)", D);
         return COFI_EUNSUPPORTED;
     }
     return attention_tc_launch(q, k, vt, L, S, frames, heads, D, scale, out, (cudaStream_t)stream);

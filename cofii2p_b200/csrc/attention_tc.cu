@@ -20,15 +20,18 @@ namespace tc {
 
 constexpr int AQ = 128;   // queries per CTA
 constexpr int AK = 64;    // keys per tile (64: 81 KB of smem -> 2 CTAs per SM hide the MMA->softmax->MMA latency chain)
-constexpr int AD = 32;    // head dim
-constexpr int Q_BYTES = AQ * AD * 4;        // 16 KB
-constexpr int K_BYTES = AK * AD * 4;        // 16 KB
-constexpr int VT_BYTES = AD * AK * 4;       // AK/32 chunks of [32 d rows x 32 keys]
 constexpr int P_BYTES = AQ * AK * 4;        // AK/32 k-blocks of [128 rows x 32 keys]
 constexpr int KC = AK / 32;                 // 32-key chunks per tile
 constexpr int KV_STAGES = 2;
-constexpr int ATT_SMEM = Q_BYTES + KV_STAGES * (K_BYTES + VT_BYTES) + P_BYTES + 1024 + 256;
-constexpr int TMEM_COLS = 128;              // S: [0,AK)  O_t: [AK,AK+32)
+constexpr int TMEM_COLS = 128;              // S: [0,AK)  O_t: [AK,AK+AD), AD <= 64
+template <int AD>
+struct ACfg {                               // AD = head dimension (32: the reference's 128/4; 64: BASELINE config 4's 256/4)
+    static constexpr int DB = AD / 32;                 // 32-float k-blocks of the head dimension
+    static constexpr int Q_BYTES = AQ * AD * 4;        // DB k-blocks of [128 rows x 32]
+    static constexpr int K_BYTES = AK * AD * 4;        // DB k-blocks of [AK keys x 32]
+    static constexpr int VT_BYTES = AD * AK * 4;       // KC chunks of [AD d-rows x 32 keys]
+    static constexpr int SMEM = Q_BYTES + KV_STAGES * (K_BYTES + VT_BYTES) + P_BYTES + 1024 + 256;
+};
 
 struct AttParams {
     float* out;
@@ -38,11 +41,13 @@ struct AttParams {
     int num_tiles;
 };
 
+template <int AD>
 __global__ void __launch_bounds__(192)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, const AttParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int Q_BYTES = ACfg<AD>::Q_BYTES, K_BYTES = ACfg<AD>::K_BYTES, VT_BYTES = ACfg<AD>::VT_BYTES, DB = ACfg<AD>::DB;
     uint8_t* sQ = smem;
     uint8_t* sKV = smem + Q_BYTES;                                   // [stage][K | Vt]
     uint8_t* sP = sKV + KV_STAGES * (K_BYTES + VT_BYTES);
@@ -85,7 +90,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(q_full, Q_BYTES);
-            tma_load_2d(&tmQ, q_full, sQ, head * AD, (int)(frame * p.L + q0));
+            for (int kb = 0; kb < DB; ++kb)
+                tma_load_2d(&tmQ, q_full, sQ + kb * (AQ * 128), head * AD + kb * 32, (int)(frame * p.L + q0));
             for (int t = 0; t < p.num_tiles; ++t) {
                 const int s = t % KV_STAGES;
                 const uint32_t ph = (uint32_t)(t / KV_STAGES) & 1u;
@@ -93,16 +99,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mbar_expect_tx(&kv_full[s], K_BYTES + VT_BYTES);
                 uint8_t* kd = sKV + s * (K_BYTES + VT_BYTES);
                 const int key0 = (int)(frame * p.S + (int64_t)t * AK);
-                tma_load_2d(&tmK, &kv_full[s], kd, head * AD, key0);
+                for (int kb = 0; kb < DB; ++kb)
+                    tma_load_2d(&tmK, &kv_full[s], kd + kb * (AK * 128), head * AD + kb * 32, key0);
 #pragma unroll
-                for (int c = 0; c < KC; ++c)  // V^T chunk c: rows head*32..+31, keys key0+32c..+31
+                for (int c = 0; c < KC; ++c)  // V^T chunk c: rows head*AD..+AD-1, keys key0+32c..+31
                     tma_load_2d(&tmVt, &kv_full[s], kd + K_BYTES + c * (AD * 32 * 4), key0 + c * 32, head * AD);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = umma_idesc(2, AQ, AK);   // 128 x 128
-            constexpr uint32_t idesc_o = umma_idesc(2, AQ, AD);   // 128 x 32
+            constexpr uint32_t idesc_o = umma_idesc(2, AQ, AD);   // 128 x AD
             mbar_wait(q_full, 0);
             const uint32_t q_addr = smem_u32(sQ);
             const uint32_t p_addr = smem_u32(sP);
@@ -116,9 +123,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t v_addr = k_addr + K_BYTES;
                 // S = Q K^T   (S columns are free: P(t-1) was published, i.e. S(t-1) fully read)
 #pragma unroll
-                for (int k = 0; k < AD / 8; ++k)
-                    mma_tf32(tmem_S, umma_desc_k128(q_addr + k * 32), umma_desc_k128(k_addr + k * 32), idesc_s,
-                             k != 0 ? 1u : 0u);
+                for (int kb = 0; kb < DB; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma_tf32(tmem_S, umma_desc_k128(q_addr + kb * (AQ * 128) + k * 32),
+                                 umma_desc_k128(k_addr + kb * (AK * 128) + k * 32), idesc_s, (kb | k) != 0 ? 1u : 0u);
                 tc_commit(s_full);
                 // O_t = P V
                 mbar_wait(p_full, tp);
@@ -191,11 +200,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // fold O_t into the running output
             mbar_wait(o_full, tp);
             tc_fence_after();
-            uint32_t raw[32];
-            tmem_ld32(tmem_O + lane_off, raw);
-            tmem_ld_wait();
 #pragma unroll
-            for (int d = 0; d < AD; ++d) o[d] = fmaf(o[d], corr, __uint_as_float(raw[d]));
+            for (int db = 0; db < DB; ++db) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_O + lane_off + db * 32, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int d = 0; d < 32; ++d) o[db * 32 + d] = fmaf(o[db * 32 + d], corr, __uint_as_float(raw[d]));
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(o_free);
@@ -221,7 +233,7 @@ bool attention_tc_supported(int64_t L, int64_t S, int heads, int D) {
     uint64_t d[2] = {4, 4}, st[1] = {16};
     (void)d;
     (void)st;
-    return D == tc::AD && heads >= 1 && L >= 1 && S >= 1 && (S % 4 == 0);
+    return (D == 32 || D == 64) && heads >= 1 && L >= 1 && S >= 1 && (S % 4 == 0);
 }
 
 // vt: V^T [heads*D, frames*S] row-major (keys contiguous): produced by the v_proj GEMM with swapped operands
@@ -230,27 +242,35 @@ int attention_tc_launch(const float* q, const float* k, const float* vt, int64_t
     using namespace tc;
     const int64_t C = (int64_t)heads * D;
     uint64_t dq[2] = {(uint64_t)C, (uint64_t)(frames * L)}, sq[1] = {(uint64_t)C * 4};
-    uint32_t bq[2] = {AD, AQ};
+    uint32_t bq[2] = {32, AQ};
     uint64_t dk[2] = {(uint64_t)C, (uint64_t)(frames * S)}, sk[1] = {(uint64_t)C * 4};
-    uint32_t bk[2] = {AD, AK};
+    uint32_t bk[2] = {32, AK};
     uint64_t dv[2] = {(uint64_t)(frames * S), (uint64_t)C}, sv[1] = {(uint64_t)(frames * S) * 4};
-    uint32_t bv[2] = {32, AD};
+    uint32_t bv[2] = {32, (uint32_t)D};
     const CUtensorMap* tq = get_tmap_f32(q, 2, dq, sq, bq);
     const CUtensorMap* tk = get_tmap_f32(k, 2, dk, sk, bk);
     const CUtensorMap* tv = get_tmap_f32(vt, 2, dv, sv, bv);
     if (!tq || !tk || !tv) return COFI_ECUDA;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-        if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(attention smem=%d): %s", ATT_SMEM, cudaGetErrorString(e));
-            return COFI_ECUDA;
-        }
-        attr_done = true;
-    }
     AttParams p{out, L, S, heads, scale, (int)ceil_div(S, AK)};
     dim3 grid((unsigned)ceil_div(L, AQ), heads, frames);
-    attention_tc_kernel<<<grid, 192, ATT_SMEM, st>>>(*tq, *tk, *tv, p);
+    static bool attr_done[2] = {false, false};
+    auto set_attr = [&](auto kern, int smem, int slot) -> int {
+        if (attr_done[slot]) return COFI_OK;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(attention smem=%d): %s", smem, cudaGetErrorString(e));
+            return COFI_ECUDA;
+        }
+        attr_done[slot] = true;
+        return COFI_OK;
+    };
+    if (D == 32) {
+        if (int rc = set_attr(attention_tc_kernel<32>, ACfg<32>::SMEM, 0)) return rc;
+        attention_tc_kernel<32><<<grid, 192, ACfg<32>::SMEM, st>>>(*tq, *tk, *tv, p);
+    } else {
+        if (int rc = set_attr(attention_tc_kernel<64>, ACfg<64>::SMEM, 1)) return rc;
+        attention_tc_kernel<64><<<grid, 192, ACfg<64>::SMEM, st>>>(*tq, *tk, *tv, p);
+    }
     return check_launch("cofi_attention(tcgen05)");
 }
 

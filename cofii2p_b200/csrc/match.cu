@@ -129,7 +129,8 @@ sim_argmin_simt_kernel(const float* __restrict__ pt, int64_t ldpt, const float* 
 // --------------------------------------------------------------------------------------- select_matches
 __global__ void __launch_bounds__(1024)
 select_matches_kernel(const float* __restrict__ score, const int64_t* __restrict__ best_idx, int64_t Npt, int gridH,
-                      int gridW, const float* __restrict__ thresholds, int nthr, int min_count, float xy_scale,
+                      int gridW, int xmax, int ymax, const float* __restrict__ thresholds, int nthr, int min_count,
+                      float xy_scale,
                       int32_t* __restrict__ out_count, int64_t* __restrict__ out_index, float* __restrict__ out_xy) {
     const int frame = blockIdx.x;
     const float* sc = score + (int64_t)frame * Npt;
@@ -141,7 +142,7 @@ select_matches_kernel(const float* __restrict__ score, const int64_t* __restrict
         int local = 0;
         for (int64_t p = threadIdx.x; p < Npt; p += blockDim.x) {
             const int x = (int)(bi[p] % gridW), y = (int)(bi[p] / gridW);
-            const bool m = (x >= 2) && (x <= gridW - 2) && (y <= gridH - 2) && (y >= 2);
+            const bool m = (x >= 2) && (x <= xmax) && (y <= ymax) && (y >= 2);
             local += (sc[p] >= thr && m) ? 1 : 0;
         }
         if (threadIdx.x == 0) s_sum = 0;
@@ -163,7 +164,7 @@ select_matches_kernel(const float* __restrict__ score, const int64_t* __restrict
         float* ox = out_xy + (int64_t)frame * 2 * Npt;
         for (int64_t p = 0; p < Npt; ++p) {
             const int x = (int)(bi[p] % gridW), y = (int)(bi[p] / gridW);
-            const bool m = (x >= 2) && (x <= gridW - 2) && (y <= gridH - 2) && (y >= 2);
+            const bool m = (x >= 2) && (x <= xmax) && (y <= ymax) && (y >= 2);
             if (sc[p] >= thr && m) {
                 oi[n] = p;
                 ox[n] = (float)x * xy_scale;
@@ -328,12 +329,12 @@ extern "C" int cofi_sim_argmin(const float* pt, int64_t ldpt, const float* px, i
 }
 
 extern "C" int cofi_select_matches(const float* score, const int64_t* best_idx, int64_t Npt, int frames, int gridH,
-                                   int gridW, const float* thresholds, int nthr, int min_count, float xy_scale,
-                                   int32_t* out_count, int64_t* out_index, float* out_xy, void* stream) {
+                                   int gridW, int xmax, int ymax, const float* thresholds, int nthr, int min_count,
+                                   float xy_scale, int32_t* out_count, int64_t* out_index, float* out_xy, void* stream) {
     COFI_REQUIRE(score && best_idx && thresholds && out_count && out_index && out_xy, "cofi_select_matches: null pointer");
     COFI_REQUIRE(Npt > 0 && frames > 0 && nthr > 0 && gridH > 4 && gridW > 4, "cofi_select_matches: bad shape");
-    select_matches_kernel<<<frames, 1024, 0, (cudaStream_t)stream>>>(score, best_idx, Npt, gridH, gridW, thresholds,
-                                                                    nthr, min_count, xy_scale, out_count, out_index,
+    select_matches_kernel<<<frames, 1024, 0, (cudaStream_t)stream>>>(score, best_idx, Npt, gridH, gridW, xmax, ymax,
+                                                                    thresholds, nthr, min_count, xy_scale, out_count, out_index,
                                                                     out_xy);
     return check_launch("cofi_select_matches");
 }

@@ -522,14 +522,15 @@ def sim_argmin_f16(pt_h, px_h, frames: int = 1):
 
 
 def select_matches(score, best_idx, frames: int, grid_h: int, grid_w: int, thresholds: torch.Tensor, min_count: int = 4,
-                   xy_scale: float = 1.0):
+                   xy_scale: float = 1.0, xmax: int = 62, ymax: int = 18):
+    """xmax / ymax default to the reference's literals (model/network.py:184)."""
     score = _f32(score, "score").contiguous().view(-1)
     best_idx = _i64(best_idx, "best_idx")
     Npt = score.numel() // frames
     cnt = torch.empty((frames, 2), dtype=torch.int32, device=score.device)
     oidx = torch.empty((frames, Npt), dtype=torch.int64, device=score.device)
     oxy = torch.empty((frames, 2, Npt), dtype=torch.float32, device=score.device)
-    _call("cofi_select_matches", _p(score), _p(best_idx), Npt, frames, grid_h, grid_w, _p(thresholds),
+    _call("cofi_select_matches", _p(score), _p(best_idx), Npt, frames, grid_h, grid_w, int(xmax), int(ymax), _p(thresholds),
                                   thresholds.numel(), min_count, float(xy_scale), _p(cnt), _p(oidx), _p(oxy), _st())
     return cnt, oidx, oxy
 

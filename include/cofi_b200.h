@@ -245,10 +245,12 @@ int cofi_cast_f16(const float* x, int64_t ldx, int64_t rows, int C, void* y, int
 
 /* Test-mode selection loop of model/network.py:146-151 + :169,:184-186 in one kernel, per frame:
  * find the first threshold t in thresholds[0..nthr) with at least `min_count` points satisfying
- * score >= t AND the border mask on their matched pixel (2<=x<=W-2, 2<=y<=H-2 for the 20x64 grid);
+ * score >= t AND the border mask on their matched pixel (2<=x<=xmax, 2<=y<=ymax);
  * emit those point indices in ascending order.  out_count[frame*2+0] = n, out_count[frame*2+1] = index of the
  * threshold used; out_index[frame*Npt ..]; out_xy[frame*2*Npt ..] laid out as [2][Npt] (x=col, y=row, fp32). */
 int cofi_select_matches(const float* score, const int64_t* best_idx, int64_t Npt, int frames, int gridH, int gridW,
+                        int xmax, int ymax /* border mask 2 <= x <= xmax, 2 <= y <= ymax; the reference hard-codes 62 / 18
+                                              (network.py:184) for every grid */,
                         const float* thresholds, int nthr, int min_count, float xy_scale /* out_xy = pixel * xy_scale;
                         network.py:156 multiplies by 4 */, int32_t* out_count, int64_t* out_index, float* out_xy, void* stream);
 

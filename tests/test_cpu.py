@@ -208,3 +208,41 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     for key in ("metric", "n_gpus", "steps", "ms_per_step", "higher_is_better", "cpu_baseline", "e2e", "config"):
         assert key in line
+
+
+def test_losses_match_reference():
+    """cofii2p_b200.model.loss vs the reference's model/loss.py (bit-exact on CPU when the reference is present;
+    otherwise self-consistency on the documented formulas)."""
+    from cofii2p_b200.model import loss as L
+    g = torch.Generator().manual_seed(0)
+    img = torch.nn.functional.normalize(torch.randn((128, 64), generator=g), dim=0)
+    pc = torch.nn.functional.normalize(torch.randn((128, 64), generator=g), dim=0)
+    mask = torch.eye(64)
+    fine_img = torch.nn.functional.normalize(torch.randn((64, 64, 4, 4), generator=g), dim=1)
+    fine_pc = torch.nn.functional.normalize(torch.randn((64, 64), generator=g), dim=1)
+    rel = torch.randint(0, 16, (64,), generator=g)
+    s_in, s_out = torch.rand(64, generator=g), torch.rand(64, generator=g)
+    mine = (L.desc_loss("cpu", img, pc, mask, pos_margin=0.2, neg_margin=1.8)[0], L.overlap_loss("cpu", s_in, s_out),
+            L.fine_circle_loss("cpu", fine_img, fine_pc, rel))
+    assert all(torch.isfinite(x) for x in mine)
+    from oracle.ref_shim import reference_available, load_reference
+    if reference_available():
+        load_reference()
+        R = sys.modules["cofi_ref_model.loss"]
+        ref = (R.desc_loss("cpu", img, pc, mask, pos_margin=0.2, neg_margin=1.8)[0], R.overlap_loss("cpu", s_in, s_out),
+               R.fine_circle_loss("cpu", fine_img, fine_pc, rel))
+        for a, b in zip(mine, ref):
+            assert torch.equal(a, b)
+
+
+def test_top_level_model_alias_is_the_drop_in_surface():
+    """`from model.network import CoFiI2P`, `from model.loss import *` (reference train.py:13,17) resolve to this repo."""
+    for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+        del sys.modules[k]
+    import model.network as mn
+    import model.loss as ml
+    from model.kpconv.kp_backbone import KPConvFPN
+    import cofii2p_b200.model.network as fast
+    assert mn.CoFiI2P is fast.CoFiI2P and hasattr(ml, "fine_circle_loss") and KPConvFPN is not None
+    for name in ("fine_process", "extract_patch", "point2node", "square_distance", "CoFiI2P_wrapper"):
+        assert hasattr(mn, name)

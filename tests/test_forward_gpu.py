@@ -149,3 +149,69 @@ def test_pipelined_engine_matches_forward(cuda_model):
             single = _run(cuda_model, f, "val")
             for a, b in zip(o, single):
                 assert (a is None and b is None) or rel_err(a, b) < 1e-6
+
+
+def test_train_mode_batchnorm_matches_oracle(seeded_sd):
+    """model.train(): the decoder's BatchNorm uses batch statistics and updates running stats (reference imagenet.py:381-394)."""
+    from cofii2p_b200.model.network import CoFiI2P
+    from cofii2p_b200.options import Options_KITTI
+    from cofii2p_b200.frames import frame_to
+    from cofii2p_b200 import ops
+    from oracle import restate
+    ops.set_engine("fp32")
+    m = CoFiI2P(Options_KITTI())
+    m.load_state_dict(seeded_sd, strict=True)
+    m = m.cuda().train()
+    frame = get_frame(0, 4096)
+    sd = {k: v.clone() for k, v in seeded_sd.items()}
+    with torch.no_grad():
+        ref = restate.forward(sd, frame["pc_data_dict"], frame["img"], frame["fine_center_kpt_coors"], frame["fine_xy"],
+                              frame["fine_pc_inline_index"], "train", bn_training=True)
+        f = frame_to(frame, "cuda")
+        got = m(f["pc_data_dict"], f["img"], f["fine_center_kpt_coors"], f["fine_xy"], f["fine_pc_inline_index"], "train")
+    for a, b in zip(got, ref):
+        assert (a is None and b is None) or rel_err(a, b) < TOL
+    new = m.state_dict()
+    for k in ("img_upsample_1.conv.0.bn1.running_mean", "img_upsample_2.conv.1.bn2.running_var",
+              "img_upsample_2.conv.0.conv_skip.1.running_mean"):
+        assert rel_err(new[k], sd[k]) < 1e-4, k          # F.batch_norm(training=True) updated sd in place
+        assert not torch.equal(new[k].cpu(), seeded_sd[k])
+    assert int(new["img_upsample_1.conv.0.bn1.num_batches_tracked"]) == 1
+
+
+def test_other_image_size_nuscenes(seeded_sd):
+    """Options_Nuscenes geometry (160 x 320 image, reference data/options.py:73-74): generic (non-TMA-tiled) conv shapes,
+    20 x 40 coarse grid, reference-literal border mask."""
+    from cofii2p_b200.model.network import CoFiI2P
+    from cofii2p_b200.options import Options_KITTI
+    from cofii2p_b200.frames import frame_to
+    from cofii2p_b200 import ops
+    from oracle import restate
+    opt = Options_KITTI()
+    opt.img_W = 320
+    m = CoFiI2P(opt)
+    m.load_state_dict(seeded_sd, strict=True)
+    m = m.cuda().eval()
+    frame = get_frame(2, 4096)
+    frame = dict(frame)
+    frame["img"] = frame["img"][:, :, :, :320].contiguous()
+    k = frame["fine_center_kpt_coors"].clone()
+    k[0] = k[0].clamp(max=150)
+    frame["fine_center_kpt_coors"] = k
+    for engine, tol in (("fp32", TOL), ("tf32", 5e-2)):
+        ops.set_engine(engine)
+        try:
+            for mode in ("val", "test"):
+                with torch.no_grad():
+                    ref = restate.forward(seeded_sd, frame["pc_data_dict"], frame["img"], frame["fine_center_kpt_coors"],
+                                          frame["fine_xy"], frame["fine_pc_inline_index"], mode, img_hw=(160, 320))
+                    f = frame_to(frame, "cuda")
+                    got = m(f["pc_data_dict"], f["img"], f["fine_center_kpt_coors"], f["fine_xy"],
+                            f["fine_pc_inline_index"], mode)
+                for a, b in zip(got[:4], ref[:4]):
+                    assert rel_err(a, b) < tol, (engine, mode, rel_err(a, b))
+                if engine == "fp32":
+                    for a, b in zip(got[4:], ref[4:]):
+                        assert (a is None and b is None) or (tuple(a.shape) == tuple(b.shape) and rel_err(a, b) < tol)
+        finally:
+            ops.set_engine("fp32")

@@ -249,3 +249,22 @@ def test_gemm_colstats_feeds_groupnorm(rows, frames, k, n, groups):
         yy = F.group_norm(lin[f * rows:(f + 1) * rows].t().unsqueeze(0), groups, gamma.double(), beta.double(), 1e-5).squeeze(0).t()
         refs.append(F.leaky_relu(yy.float() + res[f * rows:(f + 1) * rows], 0.1))
     assert rel_err(got, torch.cat(refs)) < 1e-2
+
+
+@pytest.mark.parametrize("L,S,frames", [(1280, 1024, 1), (300, 260, 2)])
+def test_attention_tc_head_dim_64(L, S, frames):
+    """BASELINE config 4 shape: 1280 super-pixels x 1024 super-points, d_model 256 = 4 heads x 64."""
+    from cofii2p_b200 import ops
+    g = torch.Generator().manual_seed(L + S)
+    q = torch.randn((frames * L, 256), generator=g)
+    k = torch.randn((frames * S, 256), generator=g)
+    v = torch.randn((frames * S, 256), generator=g)
+    refs = []
+    for f in range(frames):
+        qq = q[f * L:(f + 1) * L].view(1, L, 4, 64).double()
+        kk = k[f * S:(f + 1) * S].view(1, S, 4, 64).double()
+        vv = v[f * S:(f + 1) * S].view(1, S, 4, 64).double()
+        a = torch.softmax(torch.einsum("nlhd,nshd->nlsh", qq, kk) / 64 ** 0.5, dim=2)
+        refs.append(torch.einsum("nlsh,nshd->nlhd", a, vv).reshape(L, 256).float())
+    got = ops.attention_vt(q.cuda(), k.cuda(), v.t().contiguous().cuda(), frames, 4, 1.0 / 64 ** 0.5)
+    assert rel_err(got, torch.cat(refs)) < 5e-3, rel_err(got, torch.cat(refs))
