@@ -215,3 +215,22 @@ def test_other_image_size_nuscenes(seeded_sd):
                         assert (a is None and b is None) or (tuple(a.shape) == tuple(b.shape) and rel_err(a, b) < tol)
         finally:
             ops.set_engine("fp32")
+
+
+def test_graph_cached_forward_matches_eager(cuda_model):
+    """enable_cuda_graph(): the per-frame forward replays a cached graph of the static-shape core; results identical."""
+    from cofii2p_b200 import ops
+    ops.set_engine("fp32")
+    frames = [get_frame(s, 4096) for s in (0, 1)]
+    eager = [[_run(cuda_model, f, mode) for mode in ("val", "test")] for f in frames]
+    cuda_model.enable_cuda_graph(True)
+    try:
+        for rep in range(2):
+            for f, e in zip(frames, eager):
+                for mode, ref in zip(("val", "test"), e):
+                    got = _run(cuda_model, f, mode)
+                    for a, b in zip(got, ref):
+                        assert (a is None and b is None) or torch.equal(a, b)
+        assert len(cuda_model._graphs) == 1
+    finally:
+        cuda_model.enable_cuda_graph(False)
