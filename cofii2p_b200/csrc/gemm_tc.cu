@@ -568,7 +568,14 @@ static int tc_debug() {
     return v;
 }
 
-static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
+// Output-tile width: the widest of 128/64/32 that still yields at least one CTA per SM -- small problems (the
+// transformer's 10240 x 128 projections are 80 row tiles) are latency-bound and want more, narrower CTAs.
+static int pick_bn(int N, int64_t row_tiles = 1 << 30, bool full_row = false) {
+    int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    if (full_row) return bn;
+    while (bn > 32 && row_tiles * ((N + bn - 1) / bn) < 148) bn >>= 1;
+    return bn;
+}
 
 }  // namespace tc
 
@@ -587,7 +594,7 @@ bool gemm_tc_supported(int64_t lda, int64_t ldw, int64_t ldc, int64_t M, int N, 
 int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
                    int K, const Epilogue& ep, int engine, cudaStream_t st, float* stat_out) {
     using namespace tc;
-    const int bn = pick_bn(N);
+    const int bn = pick_bn(N, ceil_div(M, TM), ep.ln_gamma != nullptr);
     uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * 4};
     uint32_t bA[2] = {TK, TM};
     uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldw * 4};
@@ -613,7 +620,7 @@ int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, flo
 int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
                        int K, const Epilogue& ep, cudaStream_t st, float* stat_out) {
     using namespace tc;
-    const int bn = pick_bn(N);
+    const int bn = pick_bn(N, ceil_div(M, TM));
     uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * 2};
     uint32_t bA[2] = {64, TM};
     uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldw * 2};
@@ -650,7 +657,7 @@ int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w,
                    float* y, const Epilogue& ep, int engine, cudaStream_t st) {
     using namespace tc;
     const int Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
-    const int bn = pick_bn(Cout);
+    const int bn = pick_bn(Cout, (int64_t)B * (Wo / CONV_TW) * (Ho / CONV_TH));
     const int Ktot = KH * KW * Cin;
     uint64_t dA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t sA[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
