@@ -7,28 +7,25 @@ from .modules import ConvBlock, ResidualBlock, UnaryBlock, LastUnaryBlock
 from .functional import nearest_upsample
 
 
+# (block name, in/out channels as multiples of init_dim, radius/sigma multiplier, strided); strided blocks keep the
+# finer stage's radius (reference kp_backbone.py:11-73).  encoder1_1 is the only plain ConvBlock.
+_ENCODER = (("encoder1_2", 1, 2, 1, False),
+            ("encoder2_1", 2, 2, 1, True), ("encoder2_2", 2, 4, 2, False), ("encoder2_3", 4, 4, 2, False),
+            ("encoder3_1", 4, 4, 2, True), ("encoder3_2", 4, 8, 4, False), ("encoder3_3", 8, 8, 4, False),
+            ("encoder4_1", 8, 8, 4, True), ("encoder4_2", 8, 16, 8, False), ("encoder4_3", 16, 16, 8, False),
+            ("encoder5_1", 16, 16, 8, True), ("encoder5_2", 16, 32, 16, False), ("encoder5_3", 32, 32, 16, False))
+
+
 class KPConvFPN(nn.Module):
     def __init__(self, input_dim, output_dim, init_dim, kernel_size, init_radius, init_sigma, norm, group_norm):
         super().__init__()
-        d, k, r, s = init_dim, kernel_size, init_radius, init_sigma
-        a = (norm, group_norm)
-        self.encoder1_1 = ConvBlock(input_dim, d, k, r, s, *a)
-        self.encoder1_2 = ResidualBlock(d, d * 2, k, r, s, *a)
-        self.encoder2_1 = ResidualBlock(d * 2, d * 2, k, r, s, *a, strided=True)
-        self.encoder2_2 = ResidualBlock(d * 2, d * 4, k, r * 2, s * 2, *a)
-        self.encoder2_3 = ResidualBlock(d * 4, d * 4, k, r * 2, s * 2, *a)
-        self.encoder3_1 = ResidualBlock(d * 4, d * 4, k, r * 2, s * 2, *a, strided=True)
-        self.encoder3_2 = ResidualBlock(d * 4, d * 8, k, r * 4, s * 4, *a)
-        self.encoder3_3 = ResidualBlock(d * 8, d * 8, k, r * 4, s * 4, *a)
-        self.encoder4_1 = ResidualBlock(d * 8, d * 8, k, r * 4, s * 4, *a, strided=True)
-        self.encoder4_2 = ResidualBlock(d * 8, d * 16, k, r * 8, s * 8, *a)
-        self.encoder4_3 = ResidualBlock(d * 16, d * 16, k, r * 8, s * 8, *a)
-        self.encoder5_1 = ResidualBlock(d * 16, d * 16, k, r * 8, s * 8, *a, strided=True)
-        self.encoder5_2 = ResidualBlock(d * 16, d * 32, k, r * 16, s * 16, *a)
-        self.encoder5_3 = ResidualBlock(d * 32, d * 32, k, r * 16, s * 16, *a)
-        self.decoder4 = UnaryBlock(d * 48, d * 16, *a)
-        self.decoder3 = UnaryBlock(d * 24, d * 8, *a)
-        self.decoder2 = LastUnaryBlock(d * 12, output_dim)
+        self.encoder1_1 = ConvBlock(input_dim, init_dim, kernel_size, init_radius, init_sigma, norm, group_norm)
+        for name, cin, cout, scale, strided in _ENCODER:  # registration order == the reference's state_dict order
+            setattr(self, name, ResidualBlock(init_dim * cin, init_dim * cout, kernel_size, init_radius * scale,
+                                              init_sigma * scale, norm, group_norm, strided=strided))
+        self.decoder4 = UnaryBlock(init_dim * (32 + 16), init_dim * 16, norm, group_norm)
+        self.decoder3 = UnaryBlock(init_dim * (16 + 8), init_dim * 8, norm, group_norm)
+        self.decoder2 = LastUnaryBlock(init_dim * (8 + 4), output_dim)
 
     def _up_cat(self, coarse, up_table, skip, frames):
         """torch.cat([nearest_upsample(coarse, up), skip], 1) written straight into one buffer."""

@@ -14,15 +14,13 @@ class LoFTREncoderLayer(nn.Module):
         super().__init__()
         assert attention == "full", "the reference instantiates ATTENTION='full' (model/network.py:35)"
         self.dim, self.nhead = d_model // nhead, nhead
-        self.q_proj = nn.Linear(d_model, d_model, bias=False)
-        self.k_proj = nn.Linear(d_model, d_model, bias=False)
-        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        for name in ("q_proj", "k_proj", "v_proj"):  # bias-free projections (state_dict order q, k, v, merge, mlp, norms)
+            setattr(self, name, nn.Linear(d_model, d_model, bias=False))
         self.attention = FullAttention()
         self.merge = nn.Linear(d_model, d_model, bias=False)
-        self.mlp = nn.Sequential(nn.Linear(d_model * 2, d_model * 2, bias=False), nn.ReLU(True),
-                                 nn.Linear(d_model * 2, d_model, bias=False))
-        self.norm1 = nn.LayerNorm(d_model)
-        self.norm2 = nn.LayerNorm(d_model)
+        hidden = 2 * d_model
+        self.mlp = nn.Sequential(nn.Linear(hidden, hidden, bias=False), nn.ReLU(True), nn.Linear(hidden, d_model, bias=False))
+        self.norm1, self.norm2 = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
 
     def forward(self, x, source, frames: int = 1):
         """x [B*L,C], source [B*S,C] -> [B*L,C]."""
