@@ -617,3 +617,21 @@ extern "C" int cofi_norm_rows_pre(const float* x, int64_t ldx, int64_t R, int C,
     norm_apply_vec_kernel<<<grid, block, 0, st>>>(x, ldx, R, C, G, mr, gamma, beta, residual, ldr, act, y, ldy);
     return check_launch("cofi_norm_rows_pre(apply)");
 }
+
+// statistics only: (mean, rstd) per (frame, group) as float2 -- consumed by cofi_norm_rows_bwd
+extern "C" int cofi_norm_rows_stats(const float* x, int64_t ldx, int64_t R, int C, int frames, int G, float eps,
+                                    void* partials, float* mean_rstd, void* stream) {
+    COFI_REQUIRE(x && partials && mean_rstd && R > 0 && C > 0 && frames > 0 && G > 0 && C % G == 0,
+                 "cofi_norm_rows_stats: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* part = reinterpret_cast<double*>(partials);
+    const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32));
+    dim3 grid((unsigned)ceil_div(C, threads), kStatChunks, frames);
+    norm_stats_kernel<<<grid, threads, 0, st>>>(x, ldx, R, C, part);
+    int rc = check_launch("cofi_norm_rows_stats(stats)");
+    if (rc) return rc;
+    dim3 g2(G, frames);
+    norm_finalize_kernel<<<g2, 128, 0, st>>>(part, kStatChunks, R, C, G, eps, reinterpret_cast<float2*>(mean_rstd), nullptr,
+                                            nullptr);
+    return check_launch("cofi_norm_rows_stats(finalize)");
+}

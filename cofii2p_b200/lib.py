@@ -52,6 +52,32 @@ SIGNATURES = {
     "cofi_nn_argmin": (_i, [_vp, _l, _vp, _l, _vp, _vp]),
     "cofi_extract_patch": (_i, [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp, _vp]),
     "cofi_fine_match": (_i, [_vp, _vp, _l, _i, _vp, _vp]),
+    # ---- training (backward.cu)
+    "cofi_act_bwd": (_i, [_vp, _vp, _l, _i, _vp, _vp]),
+    "cofi_rowscale": (_i, [_vp, _l, _i, _vp, _vp, _vp]),
+    "cofi_colsum_workspace": (_l, [_i]),
+    "cofi_colsum": (_i, [_vp, _l, _l, _i, _vp, _i, _vp, _vp]),
+    "cofi_norm_rows_stats": (_i, [_vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "cofi_norm_rows_bwd_workspace": (_l, [_i, _i]),
+    "cofi_norm_rows_bwd": (_i, [_vp, _vp, _vp, _l, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "cofi_layer_norm_bwd": (_i, [_vp, _vp, _l, _i, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp]),
+    "cofi_l2norm_bwd": (_i, [_vp, _vp, _l, _i, _vp, _vp]),
+    "cofi_colnorm_bwd_workspace": (_l, [_i, _i]),
+    "cofi_colnorm_bwd": (_i, [_vp, _vp, _l, _i, _i, _vp, _vp, _vp]),
+    "cofi_scatter_add_rows": (_i, [_vp, _l, _i, _vp, _l, _l, _l, _i, _vp, _vp]),
+    "cofi_maxpool_rows_bwd": (_i, [_vp, _i, _vp, _i, _l, _l, _i, _vp, _vp, _vp]),
+    "cofi_kpconv_aggregate_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _l, _l, _i, _vp, _i, _f, _f, _vp, _vp]),
+    "cofi_upsample2x_cat_bwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "cofi_maxpool2d_3x3s2_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "cofi_dilate2_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "cofi_extract_patch_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp]),
+    "cofi_gemm_tn_workspace": (_l, [_l, _i, _i]),
+    "cofi_gemm_tn": (_i, [_vp, _l, _vp, _l, _vp, _l, _i, _i, _i, _vp, _vp]),
+    "cofi_conv2d_wgrad_workspace": (_l, [_i, _i, _i, _i, _i, _i, _i]),
+    "cofi_conv2d_wgrad_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "cofi_attention_fwd_lse": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "cofi_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "cofi_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
 }
 
 _lib = None

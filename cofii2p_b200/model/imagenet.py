@@ -8,6 +8,7 @@ only: the reference executes them but never uses their outputs (reference model/
 import torch
 import torch.nn as nn
 
+from .. import autograd as ad
 from .. import ops
 
 
@@ -42,6 +43,9 @@ def packed_conv_weight(conv: nn.Conv2d, cin_pad: int = None):
 
 def run_conv(conv: nn.Conv2d, x_nhwc, scale=None, shift=None, residual=None, act=ops.ACT_NONE, cin_pad=None):
     kh, kw = conv.kernel_size
+    if ad.active(conv):  # training: differentiable conv (no folded-BN epilogue on this path)
+        assert scale is None and residual is None and act == ops.ACT_NONE
+        return ad.conv2d(x_nhwc, conv.weight, conv.stride[0], conv.padding[0])
     return ops.conv2d_nhwc(x_nhwc, packed_conv_weight(conv, cin_pad), kh, kw, conv.stride[0], conv.padding[0],
                            scale=scale, shift=shift, residual=residual, act=act)
 
@@ -50,6 +54,8 @@ def instance_norm_nhwc(x, act=ops.ACT_NONE, residual=None, eps=1e-5):
     """affine-free InstanceNorm2d = per-(image, channel) statistics over H*W rows."""
     B, H, W, C = x.shape
     res = None if residual is None else residual.reshape(B * H * W, C)
+    if torch.is_grad_enabled() and x.requires_grad:
+        return ad.norm_rows(x.reshape(B * H * W, C), B, C, None, None, eps, res, act).view(B, H, W, C)
     return ops.norm_rows(x.reshape(B * H * W, C), B, C, None, None, eps, residual=res, act=act).view(B, H, W, C)
 
 
@@ -115,7 +121,7 @@ class ResNet(nn.Module):
         x = ops.nchw_to_nhwc(img_nchw, cpad=4)
         x = instance_norm_nhwc(run_conv(self.conv1, x, cin_pad=4), act=ops.ACT_RELU)
         s2 = x
-        x = ops.maxpool2d_3x3s2_nhwc(x)
+        x = ad.maxpool2d(x) if (torch.is_grad_enabled() and x.requires_grad) else ops.maxpool2d_3x3s2_nhwc(x)
         for blk in self.layer1:
             x = blk.forward_nhwc(x)
         s4 = x
@@ -165,8 +171,14 @@ def _bn_train(bn: nn.BatchNorm2d, y_nhwc, act, residual=None):
     """train-mode BatchNorm: batch statistics over B*H*W rows (+ running-stat update like nn.BatchNorm2d)."""
     B, H, W, C = y_nhwc.shape
     res = None if residual is None else residual.reshape(B * H * W, C)
-    out, mean, var = ops.norm_rows(y_nhwc.reshape(B * H * W, C), 1, C, bn.weight, bn.bias, bn.eps, residual=res,
-                                   act=act, want_stats=True)
+    flat = y_nhwc.reshape(B * H * W, C)
+    if ad.active(bn):
+        out = ad.norm_rows(flat, 1, C, bn.weight, bn.bias, bn.eps, res, act)
+        with torch.no_grad():
+            mr = ops.norm_rows_stats(flat.detach(), 1, C, bn.eps)
+            mean, var = mr[:, 0], 1.0 / (mr[:, 1] * mr[:, 1]) - bn.eps
+    else:
+        out, mean, var = ops.norm_rows(flat, 1, C, bn.weight, bn.bias, bn.eps, residual=res, act=act, want_stats=True)
     with torch.no_grad():
         n = B * H * W
         m = bn.momentum
@@ -212,7 +224,7 @@ class ImageUpSample(nn.Module):
         self.conv = nn.Sequential(ResidualConv(in_channel, output_channel), ResidualConv(output_channel, output_channel))
 
     def forward_nhwc(self, x1, x2):
-        x = ops.upsample2x_cat_nhwc(x1, x2)
+        x = ad.upsample2x_cat(x1, x2) if ad.active(self) else ops.upsample2x_cat_nhwc(x1, x2)
         x = self.conv[0].forward_nhwc(x)
         return self.conv[1].forward_nhwc(x)
 

@@ -2,6 +2,7 @@
 import torch
 import torch.nn as nn
 
+from ... import autograd as ad
 from ... import ops
 from .modules import ConvBlock, ResidualBlock, UnaryBlock, LastUnaryBlock
 from .functional import nearest_upsample
@@ -29,6 +30,8 @@ class KPConvFPN(nn.Module):
 
     def _up_cat(self, coarse, up_table, skip, frames):
         """torch.cat([nearest_upsample(coarse, up), skip], 1) written straight into one buffer."""
+        if ad.active(self):
+            return torch.cat([nearest_upsample(coarse, up_table, frames), skip], 1)
         n, c1, c2 = skip.shape[0], coarse.shape[1], skip.shape[1]
         buf = torch.empty((n, c1 + c2), dtype=torch.float32, device=skip.device)
         nearest_upsample(coarse, up_table, frames, out=buf[:, :c1])

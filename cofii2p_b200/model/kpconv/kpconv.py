@@ -4,6 +4,7 @@ import math
 import torch
 import torch.nn as nn
 
+from ... import autograd as ad
 from ... import ops
 from .kernel_points import load_kernels
 
@@ -62,6 +63,10 @@ class KPConv(nn.Module):
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1, want_stats: bool = False):
         """s_feats [B*N,Cin], q_points [B*M,3], s_points [B*N,3], neighbor_indices [B*M,H] -> [B*M,Cout]."""
+        if ad.active(self):  # training: differentiable kernels (fp32 aggregate, engine-selected GEMMs)
+            out = ad.kpconv(s_feats, self.weights, self.bias, q_points, s_points, neighbor_indices, self.kernel_points,
+                            self.sigma, frames, self.kp_reach())
+            return (out, None) if want_stats else out
         packed = ops.pack_points(s_points, s_feats)
         if ops.engine_id() == ops.ENGINE_TF32 and (self.in_channels * self.kernel_size) % 8 == 0 and self.out_channels >= 16:
             # tf32 engine: fp16 aggregate (same 11-bit operand precision as tf32), half the HBM round trip

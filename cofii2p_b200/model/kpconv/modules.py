@@ -3,6 +3,7 @@ parameter containers only (identical state_dict keys); the arithmetic runs in li
 import torch
 import torch.nn as nn
 
+from ... import autograd as ad
 from ... import ops
 from .functional import maxpool, nearest_upsample
 from .kpconv import KPConv
@@ -21,6 +22,8 @@ class GroupNorm(nn.Module):
         self.norm = nn.GroupNorm(num_groups, num_channels)
 
     def forward(self, x, frames: int = 1, act: int = ops.ACT_NONE, residual=None, tile_stats=None):
+        if ad.active(self):
+            return ad.norm_rows(x, frames, self.num_groups, self.norm.weight, self.norm.bias, self.norm.eps, residual, act)
         if tile_stats is not None:  # statistics came out of the producing GEMM's epilogue
             return ops.norm_rows_pre(x, tile_stats, frames, self.num_groups, self.norm.weight, self.norm.bias, self.norm.eps,
                                      residual=residual, act=act)
@@ -47,6 +50,8 @@ class UnaryBlock(nn.Module):
         act = ops.ACT_LRELU if self.leaky_relu is not None else ops.ACT_NONE
         if final_act is not None:
             act = final_act
+        if ad.active(self):
+            return self.norm(ad.linear(x, self.mlp.weight, self.mlp.bias), frames, act=act, residual=residual)
         if ops.colstats_ok(x.shape[0], frames, self.out_channels):
             y, st = ops.gemm_colstats(x, self.mlp.weight, bias=self.mlp.bias)
             return self.norm(y, frames, act=act, residual=residual, tile_stats=st)
@@ -61,6 +66,8 @@ class LastUnaryBlock(nn.Module):
         self.mlp = nn.Linear(in_channels, out_channels, bias=bias)
 
     def forward(self, x, frames: int = 1):
+        if ad.active(self):
+            return ad.linear(x, self.mlp.weight, self.mlp.bias)
         return ops.gemm(x, self.mlp.weight, bias=self.mlp.bias)
 
 

@@ -16,6 +16,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
+from .. import autograd as ad
 from .. import ops
 from .imagenet import ImageEncoder, ImageUpSample, ResidualConv  # noqa: F401  (ResidualConv: reference import surface)
 from .kpconv.kp_backbone import KPConvFPN
@@ -76,6 +77,10 @@ class CoFiI2P(nn.Module):
     def _pc_feature(self, x):
         """Linear-LN-ReLU-Linear-LN-ReLU-Linear (reference network.py:29)."""
         l = self.pc_feature_layer
+        if ad.active(self):
+            x = ad.layer_norm(ad.linear(x, l[0].weight), l[1].weight, l[1].bias, l[1].eps, act=ops.ACT_RELU)
+            x = ad.layer_norm(ad.linear(x, l[3].weight), l[4].weight, l[4].bias, l[4].eps, act=ops.ACT_RELU)
+            return ad.linear(x, l[6].weight)
         x = ops.layer_norm_rows(ops.gemm(x, l[0].weight), l[1].weight, l[1].bias, l[1].eps, act=ops.ACT_RELU)
         x = ops.layer_norm_rows(ops.gemm(x, l[3].weight), l[4].weight, l[4].bias, l[4].eps, act=ops.ACT_RELU)
         return ops.gemm(x, l[6].weight)
@@ -87,6 +92,10 @@ class CoFiI2P(nn.Module):
         w0 = seq[0].weight.reshape(seq[0].weight.shape[0], -1)
         w3 = seq[3].weight.reshape(seq[3].weight.shape[0], -1)
         w6 = seq[6].weight.reshape(seq[6].weight.shape[0], -1)
+        if torch.is_grad_enabled() and tokens.requires_grad:
+            x = ad.norm_rows(ad.linear(tokens, w0), frames, w0.shape[0], None, None, seq[1].eps, None, ops.ACT_RELU)
+            x = ad.norm_rows(ad.linear(x, w3), frames, w3.shape[0], None, None, seq[4].eps, None, ops.ACT_RELU)
+            return ad.linear(x, w6, None, ops.ACT_SIGMOID)
         x = ops.norm_rows(ops.gemm(tokens, w0), frames, w0.shape[0], eps=seq[1].eps, act=ops.ACT_RELU)
         x = ops.norm_rows(ops.gemm(x, w3), frames, w3.shape[0], eps=seq[4].eps, act=ops.ACT_RELU)
         return ops.gemm(x, w6, act=ops.ACT_SIGMOID)
@@ -106,11 +115,13 @@ class CoFiI2P(nn.Module):
           up2 NHWC [B,H/2,W/2,64] (L2-normalised), pc_decode_3 [B*N1,64] (L2-normalised)."""
         B = frames
         hw = self.pe_H * self.pe_W
+        train = ad.active(self)
+        l2 = (lambda t, add=None: ad.l2norm(t, add)) if train else (lambda t, add=None: ops.l2norm_rows(t, add=add))
         main = torch.cuda.current_stream()
         # ---- image stream on a forked CUDA stream: ResNet + decoder are independent of the point stream (only the
         # transformer joins them), so inside the captured graph the two branches run concurrently and the image
         # branch's tensor-core convs fill the SMs left idle by the gather/HBM-bound point kernels.
-        side = self._side_streams.get(img.device) if self.fork_image_stream else main
+        side = self._side_streams.get(img.device) if (self.fork_image_stream and not train) else main
         if side is None:
             side = self._side_streams[img.device] = torch.cuda.Stream(device=img.device)
         img_pos = self._image_pos(img.device)
@@ -122,26 +133,26 @@ class CoFiI2P(nn.Module):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             s2, s4, s8 = self.img_encoder.forward_nhwc(img)
-            s8n = ops.l2norm_rows(s8.reshape(B * hw, 128))                                # :90 (feeds decoder too)
-            f_img = ops.l2norm_rows(s8.reshape(B * hw, 128), add=img_pos)                 # :113
+            s8n = l2(s8.reshape(B * hw, 128))                                             # :90 (feeds decoder too)
+            f_img = l2(s8.reshape(B * hw, 128), img_pos)                                  # :113
             tokens_ready = torch.cuda.Event()
             tokens_ready.record(side)
             up4 = self.img_upsample_1.forward_nhwc(s8n.view(B, self.pe_H, self.pe_W, 128), s4)   # :129
             up2 = self.img_upsample_2.forward_nhwc(up4, s2)                               # :130
             Bh, Hh, Wh, Ch = up2.shape
-            up2n = ops.l2norm_rows(up2.reshape(-1, Ch)).view(Bh, Hh, Wh, Ch)
+            up2n = l2(up2.reshape(-1, Ch)).view(Bh, Hh, Wh, Ch)
         # ---- point stream on the main stream
         pcs = self.pc_encoder(pc_data_dict, frames, taps)
-        pc_decode_3 = ops.l2norm_rows(pcs[0])                                            # network.py:82
+        pc_decode_3 = l2(pcs[0])                                                         # network.py:82
         pc_pos = self.pc_pos_encoding(pc_data_dict["points"][-1])                         # :107
-        f_pc = ops.l2norm_rows(self._pc_feature(pcs[3]), add=pc_pos)                      # :84,:114
+        f_pc = l2(self._pc_feature(pcs[3]), pc_pos)                                       # :84,:114
         main.wait_event(tokens_ready)
         f_img_side = f_img  # keep the side-stream allocation alive until the join (no cross-stream block reuse)
         f_img, f_pc = self.transformer(f_img, f_pc, frames)                               # :115
         pc_score = self._score_head(self.pc_score_layer, f_pc, frames)                    # :123
         img_score = self._score_head(self.img_score_layer, f_img, frames)                 # :124
-        pc_norm = ops.l2norm_rows(f_pc)                                                   # :125
-        img_norm = ops.l2norm_rows(f_img)                                                 # :126
+        pc_norm = l2(f_pc)                                                                # :125
+        img_norm = l2(f_img)                                                              # :126
         main.wait_stream(side)  # join: decoder output (and every side-stream temporary) is complete from here on
         del f_img_side
         if taps is not None:
@@ -152,8 +163,13 @@ class CoFiI2P(nn.Module):
 
     # ------------------------------------------------------------------------------------------ matching tails
     def _tail_val(self, core: Dict, b: int, n1: int, kpt_coors, inline_index):
-        fine_pc = ops.gather_rows(core["pc_decode_3"][b * n1:(b + 1) * n1], inline_index.to(torch.int64).contiguous())
         err = torch.zeros(1, dtype=torch.int32, device=kpt_coors.device)
+        idx = inline_index.to(torch.int64).contiguous()
+        if ad.active(self):
+            fine_pc = ad.gather(core["pc_decode_3"][b * n1:(b + 1) * n1], idx)
+            patch = ad.extract_patch(core["up2"], b, kpt_coors.to(torch.float32), err)
+            return patch, fine_pc, err
+        fine_pc = ops.gather_rows(core["pc_decode_3"][b * n1:(b + 1) * n1], idx)
         patch = ops.extract_patch(core["up2"], b, kpt_coors.to(torch.float32), err)
         return patch, fine_pc, err
 
@@ -191,8 +207,9 @@ class CoFiI2P(nn.Module):
         hw = self.pe_H * self.pe_W
         n4 = core["pc_norm"].shape[0] // frames
         imn = core["img_norm"][b * hw:(b + 1) * hw].view(1, self.pe_H, self.pe_W, 128)
-        img_feature_norm = ops.nhwc_to_nchw(imn)                                          # [1,128,20,64]
-        pc_feature_norm = ops.nhwc_to_nchw(core["pc_norm"][b * n4:(b + 1) * n4].view(1, 1, n4, 128)).view(128, n4)
+        t = ad.nhwc_to_nchw if ad.active(self) else ops.nhwc_to_nchw
+        img_feature_norm = t(imn)                                                         # [1,128,20,64]
+        pc_feature_norm = t(core["pc_norm"][b * n4:(b + 1) * n4].view(1, 1, n4, 128)).view(128, n4)
         img_score = core["img_score"][b * hw:(b + 1) * hw].view(1, 1, self.pe_H, self.pe_W)
         pc_score = core["pc_score"][b * n4:(b + 1) * n4].view(1, 1, n4)
         return img_feature_norm, pc_feature_norm, img_score, pc_score

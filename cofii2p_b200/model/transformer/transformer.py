@@ -5,6 +5,7 @@ import copy
 import torch
 import torch.nn as nn
 
+from ... import autograd as ad
 from ... import ops
 from .linear_attention import FullAttention
 
@@ -25,6 +26,15 @@ class LoFTREncoderLayer(nn.Module):
     def forward(self, x, source, frames: int = 1):
         """x [B*L,C], source [B*S,C] -> [B*L,C]."""
         C = x.shape[1]
+        if ad.active(self):  # training: differentiable kernels, SIMT attention with saved log-sum-exp
+            q = ad.colnorm(ad.linear(x, self.q_proj.weight), frames)
+            k = ad.linear(source, self.k_proj.weight)
+            v = ad.linear(source, self.v_proj.weight)
+            msg = ad.attention(q, k, v, frames, self.nhead, 1.0 / self.dim ** 0.5)
+            m = ad.layer_norm(ad.linear(msg, self.merge.weight), self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            h = ad.linear(torch.cat([x, m], 1), self.mlp[0].weight, None, ops.ACT_RELU)
+            h = ad.linear(h, self.mlp[2].weight)
+            return ad.layer_norm(h, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=x)
         # F.normalize(q) with default dim=1 == L2 over the sequence axis per (head, channel) (reference :53)
         q = ops.colnorm_rows(ops.gemm(x, self.q_proj.weight), frames)
         k = ops.gemm(source, self.k_proj.weight)

@@ -563,3 +563,190 @@ def fine_match(patch, pc):
     idx = torch.empty((n,), dtype=torch.int64, device=pc.device)
     _call("cofi_fine_match", _p(patch), _p(pc), n, C, _p(idx), _st())
     return idx
+
+
+# ============================================================================================ training (backward.cu)
+def transpose2d(x):
+    """[R, C] -> [C, R] (the tiled NHWC->NCHW transpose with B = H = 1)."""
+    x, _ = _rows(x.contiguous(), "x")
+    R, C = x.shape
+    y = torch.empty((C, R), dtype=torch.float32, device=x.device)
+    _call("cofi_nhwc_to_nchw", _p(x), 1, 1, R, C, _p(y), _st())
+    return y
+
+
+def act_bwd(dy, y, act: int):
+    dy, y = dy.contiguous(), y.contiguous()
+    dx = torch.empty_like(dy)
+    _call("cofi_act_bwd", _p(dy), _p(y), dy.numel(), act, _p(dx), _st())
+    return dx
+
+
+def rowscale(x, rowdiv):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _call("cofi_rowscale", _p(x), x.shape[0], x.shape[1], _p(rowdiv), _p(y), _st())
+    return y
+
+
+def colsum(x):
+    x, ldx = _rows(x, "x")
+    out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
+    ws = _ws(_lib.cofi_colsum_workspace(x.shape[1]), x.device)
+    _call("cofi_colsum", _p(x), ldx, x.shape[0], x.shape[1], _p(out), 0, _p(ws), _st())
+    return out
+
+
+def gemm_tn(a, b):
+    """a [R, Mo], b [R, No] -> a^T b [Mo, No] (fp32 SIMT, deterministic split over R)."""
+    a, lda = _rows(a, "a")
+    b, ldb = _rows(b, "b")
+    R, Mo = a.shape
+    No = b.shape[1]
+    out = torch.empty((Mo, No), dtype=torch.float32, device=a.device)
+    ws = _ws(_lib.cofi_gemm_tn_workspace(R, Mo, No), a.device)
+    _meta(2.0 * R * Mo * No, 4.0 * (R * Mo + R * No + Mo * No))
+    _call("cofi_gemm_tn", _p(a), lda, _p(b), ldb, _p(out), R, Mo, No, 0, _p(ws), _st())
+    return out
+
+
+def norm_rows_stats(x, frames: int, groups: int, eps: float):
+    x, ldx = _rows(x, "x")
+    rows, C = x.shape
+    ws = _ws(_lib.cofi_norm_rows_workspace(frames, C), x.device)
+    mr = torch.empty((frames * groups, 2), dtype=torch.float32, device=x.device)
+    _call("cofi_norm_rows_stats", _p(x), ldx, rows // frames, C, frames, groups, float(eps), _p(ws), _p(mr), _st())
+    return mr
+
+
+def norm_rows_bwd(x, dy, y, mean_rstd, frames: int, groups: int, gamma, act: int, want_res: bool):
+    x, dy, y = x.contiguous(), dy.contiguous(), y.contiguous()
+    rows, C = x.shape
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_res else None
+    dgamma = torch.empty((C,), dtype=torch.float32, device=x.device) if gamma is not None else None
+    dbeta = torch.empty((C,), dtype=torch.float32, device=x.device) if gamma is not None else None
+    ws = _ws(_lib.cofi_norm_rows_bwd_workspace(frames, C), x.device)
+    _call("cofi_norm_rows_bwd", _p(x), _p(dy), _p(y), rows // frames, C, frames, groups, _p(mean_rstd), _p(gamma), act, _p(dx),
+          _p(dres), _p(dgamma), _p(dbeta), 0, _p(ws), _st())
+    return dx, dres, dgamma, dbeta
+
+
+def layer_norm_bwd(x, dy, gamma, beta, eps: float, act: int):
+    x, dy = x.contiguous(), dy.contiguous()
+    dx, t1, t2 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    _call("cofi_layer_norm_bwd", _p(x), _p(dy), x.shape[0], x.shape[1], _p(gamma), _p(beta), float(eps), act, _p(dx), _p(t1),
+          _p(t2), _st())
+    return dx, colsum(t1), colsum(t2)
+
+
+def l2norm_bwd(x, dy):
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x)
+    _call("cofi_l2norm_bwd", _p(x), _p(dy), x.shape[0], x.shape[1], _p(dx), _st())
+    return dx
+
+
+def colnorm_bwd(x, dy, frames: int):
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x)
+    ws = _ws(_lib.cofi_colnorm_bwd_workspace(frames, x.shape[1]), x.device)
+    _call("cofi_colnorm_bwd", _p(x), _p(dy), x.shape[0] // frames, x.shape[1], frames, _p(dx), _p(ws), _st())
+    return dx
+
+
+def scatter_add_rows(dy, idx, idx_stride: int, frames: int, rows_src: int):
+    dy, ldy = _rows(dy, "dy")
+    C = dy.shape[1]
+    dx = torch.zeros((rows_src, C), dtype=torch.float32, device=dy.device)
+    _call("cofi_scatter_add_rows", _p(dy), ldy, C, _p(idx), idx_stride, dy.shape[0] // frames, rows_src // frames, frames, _p(dx),
+          _st())
+    return dx
+
+
+def maxpool_rows_bwd(x, nbr, dy, frames: int):
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.zeros_like(x)
+    _call("cofi_maxpool_rows_bwd", _p(x), x.shape[1], _p(nbr), nbr.shape[1], nbr.shape[0] // frames, x.shape[0] // frames, frames,
+          _p(dy), _p(dx), _st())
+    return dx
+
+
+def kpconv_aggregate_bwd(dagg, C: int, s_packed, q_points, nbr, kernel_points, sigma: float, frames: int, kp_reach: float):
+    dagg = dagg.contiguous()
+    rows_src = s_packed.shape[0]
+    dfeats = torch.zeros((rows_src, C), dtype=torch.float32, device=dagg.device)
+    _call("cofi_kpconv_aggregate_bwd", _p(dagg), C, _p(s_packed), _p(q_points), _p(nbr), nbr.shape[1], nbr.shape[0] // frames,
+          rows_src // frames, frames, _p(kernel_points), kernel_points.shape[0], float(sigma), float(kp_reach), _p(dfeats), _st())
+    return dfeats
+
+
+def upsample2x_cat_bwd(dy, C1: int):
+    dy = dy.contiguous()
+    B, Ho, Wo, Ct = dy.shape
+    dx1 = torch.zeros((B, Ho // 2, Wo // 2, C1), dtype=torch.float32, device=dy.device)
+    dx2 = torch.empty((B, Ho, Wo, Ct - C1), dtype=torch.float32, device=dy.device)
+    _call("cofi_upsample2x_cat_bwd", _p(dy), B, Ho // 2, Wo // 2, C1, Ct - C1, _p(dx1), _p(dx2), _st())
+    return dx1, dx2
+
+
+def maxpool2d_3x3s2_bwd(x, dy):
+    x, dy = x.contiguous(), dy.contiguous()
+    B, H, W, C = x.shape
+    dx = torch.zeros_like(x)
+    _call("cofi_maxpool2d_3x3s2_bwd", _p(x), _p(dy), B, H, W, C, _p(dx), _st())
+    return dx
+
+
+def dilate2_nhwc(x):
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=x.device)
+    _call("cofi_dilate2_nhwc", _p(x), B, H, W, C, _p(y), _st())
+    return y
+
+
+def extract_patch_bwd(dpatch, map_shape, b: int, centers):
+    dpatch = dpatch.contiguous()
+    B, H, W, C = map_shape
+    dmap = torch.zeros(map_shape, dtype=torch.float32, device=dpatch.device)
+    _call("cofi_extract_patch_bwd", _p(dpatch), H, W, C, b, _p(centers), centers.shape[1], _p(dmap), _st())
+    return dmap
+
+
+def conv2d_wgrad_nhwc(x, dy, kh: int, kw: int, stride: int, pad: int):
+    x, dy = x.contiguous(), dy.contiguous()
+    B, H, W, Cin = x.shape
+    _, Ho, Wo, Cout = dy.shape
+    dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=x.device)
+    ws = _ws(_lib.cofi_conv2d_wgrad_workspace(B, Ho, Wo, Cout, kh, kw, Cin), x.device)
+    _meta(2.0 * B * Ho * Wo * Cout * kh * kw * Cin, 4.0 * (x.numel() + dy.numel() + dw.numel()))
+    _call("cofi_conv2d_wgrad_nhwc", _p(x), B, H, W, Cin, _p(dy), Cout, kh, kw, stride, pad, _p(dw), 0, _p(ws), _st())
+    return dw
+
+
+def attention_fwd_lse(q, k, v, frames: int, heads: int, scale: float):
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    L, S = q.shape[0] // frames, k.shape[0] // frames
+    out = torch.empty_like(q)
+    lse = torch.empty((q.shape[0], heads), dtype=torch.float32, device=q.device)
+    _meta(4.0 * frames * L * S * q.shape[1], 4.0 * (2 * q.numel() + 2 * k.numel()))
+    _call("cofi_attention_fwd_lse", _p(q), _p(k), _p(v), L, S, frames, heads, q.shape[1] // heads, float(scale), _p(out), _p(lse),
+          _st())
+    return out, lse
+
+
+def attention_bwd(q, k, v, out, dout, lse, frames: int, heads: int, scale: float):
+    dout = dout.contiguous()
+    L, S = q.shape[0] // frames, k.shape[0] // frames
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dsum = torch.empty((q.shape[0], heads), dtype=torch.float32, device=q.device)
+    _meta(10.0 * frames * L * S * q.shape[1], 4.0 * (4 * q.numel() + 4 * k.numel()))
+    _call("cofi_attention_bwd", _p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), L, S, frames, heads, q.shape[1] // heads,
+          float(scale), _p(dq), _p(dk), _p(dv), _p(dsum), _st())
+    return dq, dk, dv
+
+
+def adam_step(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, step: int, grad_scale: float = 1.0):
+    _call("cofi_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
+          float(grad_scale), _st())

@@ -267,6 +267,60 @@ int cofi_extract_patch(const float* map, int H, int W, int C, int b, const float
  * similarity with the point feature; patch [n,C,16], pc [n,C] -> idx [n]. */
 int cofi_fine_match(const float* patch, const float* pc, int64_t n, int C, int64_t* idx, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Training: backward of every forward op (the reference trains through ATen autograd, train.py:285)
+ * All gradient outputs that are scattered into (dx of gathers, max-pools, bilinear up-sampling, patch extraction,
+ * KPConv aggregate) must be ZEROED by the caller; `accumulate` flags add into an existing gradient.
+ * ------------------------------------------------------------------------------------------------- */
+int cofi_act_bwd(const float* dy, const float* y, int64_t n, int act, float* dx, void* stream);
+int cofi_rowscale(const float* x, int64_t rows, int C, const float* rowdiv, float* y, void* stream);
+int64_t cofi_colsum_workspace(int C);
+int cofi_colsum(const float* x, int64_t ldx, int64_t rows, int C, float* out, int accumulate, void* work, void* stream);
+/* grouped-norm backward (GroupNorm / InstanceNorm / train BatchNorm of cofi_norm_rows): x = forward input, y = forward
+ * output (for the activation mask), mean_rstd = [frames*G] (mean, rstd) pairs from cofi_norm_rows_stats. */
+int cofi_norm_rows_stats(const float* x, int64_t ldx, int64_t R, int C, int frames, int G, float eps, void* partials,
+                         float* mean_rstd, void* stream);
+int64_t cofi_norm_rows_bwd_workspace(int frames, int C);
+int cofi_norm_rows_bwd(const float* x, const float* dy, const float* y, int64_t R, int C, int frames, int G,
+                       const float* mean_rstd, const float* gamma, int act, float* dx, float* dres, float* dgamma,
+                       float* dbeta, int accumulate, void* work, void* stream);
+/* LayerNorm backward: dx plus t1 = dz*xhat, t2 = dz whose column sums (cofi_colsum) are dgamma / dbeta. */
+int cofi_layer_norm_bwd(const float* x, const float* dy, int64_t rows, int C, const float* gamma, const float* beta,
+                        float eps, int act, float* dx, float* t1, float* t2, void* stream);
+int cofi_l2norm_bwd(const float* x, const float* dy, int64_t rows, int C, float* dx, void* stream);
+int64_t cofi_colnorm_bwd_workspace(int frames, int C);
+int cofi_colnorm_bwd(const float* x, const float* dy, int64_t L, int C, int frames, float* dx, void* work, void* stream);
+int cofi_scatter_add_rows(const float* dy, int64_t ldy, int C, const int64_t* idx, int64_t idx_stride, int64_t Mq,
+                          int64_t Ns, int frames, float* dx, void* stream);
+int cofi_maxpool_rows_bwd(const float* x, int C, const int64_t* nbr, int H, int64_t Mq, int64_t Ns, int frames,
+                          const float* dy, float* dx, void* stream);
+int cofi_kpconv_aggregate_bwd(const float* dagg, int C, const float* s_packed, const float* q_points, const int64_t* nbr,
+                              int H, int64_t Mq, int64_t Ns, int frames, const float* kernel_points, int K, float sigma,
+                              float kp_reach, float* dfeats, void* stream);
+int cofi_upsample2x_cat_bwd(const float* dy, int B, int H, int W, int C1, int C2, float* dx1, float* dx2, void* stream);
+int cofi_maxpool2d_3x3s2_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* dx, void* stream);
+int cofi_dilate2_nhwc(const float* x, int B, int H, int W, int C, float* y, void* stream);
+int cofi_extract_patch_bwd(const float* dpatch, int H, int W, int C, int b, const float* centers, int64_t n, float* dmap,
+                           void* stream);
+/* C[Mo,No] (+)= A[R,Mo]^T B[R,No]: weight gradient of a Linear without transposes (A = dY, B = X). */
+int64_t cofi_gemm_tn_workspace(int64_t R, int Mo, int No);
+int cofi_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t R, int Mo, int No,
+                 int accumulate, void* work, void* stream);
+/* weight gradient of cofi_conv2d_nhwc: dw[Cout, KH*KW*Cin] */
+int64_t cofi_conv2d_wgrad_workspace(int B, int Ho, int Wo, int Cout, int KH, int KW, int Cin);
+int cofi_conv2d_wgrad_nhwc(const float* x, int B, int H, int W, int Cin, const float* dy, int Cout, int KH, int KW,
+                           int stride, int pad, float* dw, int accumulate, void* work, void* stream);
+/* attention for training: forward that also returns the log-sum-exp [frames*L, heads], and its backward (D = 32). */
+int cofi_attention_fwd_lse(const float* q, const float* k, const float* v, int64_t L, int64_t S, int frames, int heads,
+                           int D, float scale, float* out, float* lse, void* stream);
+int cofi_attention_bwd(const float* q, const float* k, const float* v, const float* out, const float* dout,
+                       const float* lse, int64_t L, int64_t S, int frames, int heads, int D, float scale, float* dq,
+                       float* dk, float* dv, float* dsum_work /* [frames*L*heads] */, void* stream);
+/* fused Adam step (torch.optim.Adam semantics, reference train.py:154); grad_scale folds the 1/world_size of the
+ * data-parallel gradient average. */
+int cofi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,244 @@
+"""Training path: every forward op's hand-written backward (cofii2p_b200/autograd.py -> csrc/backward.cu) against torch
+autograd on the CPU oracle formulation, then the whole model's parameter gradients through the reference's three losses
+against the oracle's autograd (oracle/restate.py with requires_grad state dict).  Tolerance 2e-4 per op (fp32 engine)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import get_frame, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-4
+
+
+def _ad():
+    from cofii2p_b200 import autograd as ad, ops
+    ops.set_engine("fp32")
+    return ad, ops
+
+
+def _leaf(t):
+    return t.clone().requires_grad_(True)
+
+
+def _cuda_leaf(t):
+    return t.cuda().requires_grad_(True)
+
+
+def _check(pairs):
+    for name, got, ref in pairs:
+        assert rel_err(got, ref) < TOL, (name, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_linear_backward(act):
+    ad, ops = _ad()
+    g = torch.Generator().manual_seed(act)
+    x, w, b = torch.randn((300, 64), generator=g), torch.randn((48, 64), generator=g) / 8, torch.randn((48,), generator=g)
+    go = torch.randn((300, 48), generator=g)
+    xr, wr, br = _leaf(x), _leaf(w), _leaf(b)
+    y = F.linear(xr, wr, br)
+    y = [y, F.relu(y), F.leaky_relu(y, 0.1), torch.sigmoid(y)][act]
+    y.backward(go)
+    xc, wc, bc = _cuda_leaf(x), _cuda_leaf(w), _cuda_leaf(b)
+    yc = ad.linear(xc, wc, bc, act)
+    yc.backward(go.cuda())
+    _check([("y", yc, y), ("dx", xc.grad, xr.grad), ("dw", wc.grad, wr.grad), ("db", bc.grad, br.grad)])
+
+
+def test_kpconv_backward():
+    ad, ops = _ad()
+    from oracle import restate
+    g = torch.Generator().manual_seed(1)
+    n, c, co, sigma = 600, 32, 32, 0.4
+    pts = torch.rand((n, 3), generator=g) * 3
+    nbr = torch.cdist(pts.double(), pts.double()).topk(128, dim=1, largest=False).indices
+    nbr[:50, 100:] = n  # shadow tail
+    feats, w, b = torch.randn((n, c), generator=g), torch.randn((15, c, co), generator=g) / 6, torch.randn((co,), generator=g)
+    kp = torch.randn((15, 3), generator=g) * 0.3
+    go = torch.randn((n, co), generator=g)
+    fr, wr, br = _leaf(feats), _leaf(w), _leaf(b)
+    y = restate.kpconv(fr, pts, pts, nbr, wr, br, kp, sigma)
+    y.backward(go)
+    fc, wc, bc = _cuda_leaf(feats), _cuda_leaf(w), _cuda_leaf(b)
+    yc = ad.kpconv(fc, wc, bc, pts.cuda(), pts.cuda(), nbr.cuda(), kp.cuda(), sigma, 1, float(kp.norm(dim=1).max()))
+    yc.backward(go.cuda())
+    _check([("y", yc, y), ("dfeats", fc.grad, fr.grad), ("dw", wc.grad, wr.grad), ("db", bc.grad, br.grad)])
+
+
+@pytest.mark.parametrize("rows,c,groups,frames,affine,act,res", [(500, 64, 32, 2, True, 2, True), (700, 128, 128, 1, False, 1, False),
+                                                                (640, 32, 32, 1, True, 0, False)])
+def test_norm_rows_backward(rows, c, groups, frames, affine, act, res):
+    ad, ops = _ad()
+    g = torch.Generator().manual_seed(rows + c)
+    x = torch.randn((frames * rows, c), generator=g) * 2 + 1
+    gamma, beta = torch.randn((c,), generator=g), torch.randn((c,), generator=g)
+    r = torch.randn((frames * rows, c), generator=g)
+    go = torch.randn((frames * rows, c), generator=g)
+    xr, gr, br, rr = _leaf(x), _leaf(gamma), _leaf(beta), _leaf(r)
+    outs = []
+    for f in range(frames):
+        yy = F.group_norm(xr[f * rows:(f + 1) * rows].t().unsqueeze(0), groups, gr if affine else None, br if affine else None,
+                          1e-5).squeeze(0).t()
+        if res:
+            yy = yy + rr[f * rows:(f + 1) * rows]
+        outs.append([yy, F.relu(yy), F.leaky_relu(yy, 0.1)][act])
+    y = torch.cat(outs)
+    y.backward(go)
+    xc, gc, bc, rc = _cuda_leaf(x), _cuda_leaf(gamma), _cuda_leaf(beta), _cuda_leaf(r)
+    yc = ad.norm_rows(xc, frames, groups, gc if affine else None, bc if affine else None, 1e-5, rc if res else None, act)
+    yc.backward(go.cuda())
+    pairs = [("y", yc, y), ("dx", xc.grad, xr.grad)]
+    if affine:
+        pairs += [("dgamma", gc.grad, gr.grad), ("dbeta", bc.grad, br.grad)]
+    if res:
+        pairs += [("dres", rc.grad, rr.grad)]
+    _check(pairs)
+
+
+def test_row_norms_backward():
+    ad, ops = _ad()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((333, 256), generator=g) + 0.3
+    gamma, beta, r = torch.randn((256,), generator=g), torch.randn((256,), generator=g), torch.randn((333, 256), generator=g)
+    go = torch.randn((333, 256), generator=g)
+    for act in (0, 1):
+        xr, gr, br, rr = _leaf(x), _leaf(gamma), _leaf(beta), _leaf(r)
+        y = F.layer_norm(xr, (256,), gr, br, 1e-5)
+        y = (F.relu(y) if act else y) + rr
+        y.backward(go)
+        xc, gc, bc, rc = _cuda_leaf(x), _cuda_leaf(gamma), _cuda_leaf(beta), _cuda_leaf(r)
+        yc = ad.layer_norm(xc, gc, bc, 1e-5, act, rc)
+        yc.backward(go.cuda())
+        _check([("y", yc, y), ("dx", xc.grad, xr.grad), ("dgamma", gc.grad, gr.grad), ("dbeta", bc.grad, br.grad),
+                ("dres", rc.grad, rr.grad)])
+    xr, ar = _leaf(x), _leaf(r)
+    y = F.normalize(xr, dim=1) + ar
+    y.backward(go)
+    xc, ac = _cuda_leaf(x), _cuda_leaf(r)
+    yc = ad.l2norm(xc, ac)
+    yc.backward(go.cuda())
+    _check([("l2 y", yc, y), ("l2 dx", xc.grad, xr.grad), ("l2 dadd", ac.grad, ar.grad)])
+    q = torch.randn((2 * 320, 128), generator=g)
+    gq = torch.randn((2 * 320, 128), generator=g)
+    qr = _leaf(q)
+    y = torch.cat([F.normalize(qr[:320].view(1, 320, 4, 32)).view(320, 128), F.normalize(qr[320:].view(1, 320, 4, 32)).view(320, 128)])
+    y.backward(gq)
+    qc = _cuda_leaf(q)
+    yc = ad.colnorm(qc, 2)
+    yc.backward(gq.cuda())
+    _check([("colnorm y", yc, y), ("colnorm dx", qc.grad, qr.grad)])
+
+
+def test_gather_and_maxpool_backward():
+    ad, ops = _ad()
+    from oracle import restate
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((400, 96), generator=g)
+    up = torch.randint(0, 401, (900, 128), generator=g)  # duplicates + shadow index 400
+    go = torch.randn((900, 96), generator=g)
+    xr = _leaf(x)
+    restate.nearest_upsample(xr, up).backward(go)
+    xc = _cuda_leaf(x)
+    ad.gather(xc, up.cuda(), 128, 1, 900).backward(go.cuda())
+    _check([("gather dx", xc.grad, xr.grad)])
+    nbr = torch.randint(0, 401, (200, 128), generator=g)
+    go2 = torch.randn((200, 96), generator=g)
+    xr = _leaf(x)
+    restate.maxpool(xr, nbr).backward(go2)
+    xc = _cuda_leaf(x)
+    ad.maxpool_rows(xc, nbr.cuda(), 1).backward(go2.cuda())
+    _check([("maxpool dx", xc.grad, xr.grad)])
+
+
+def test_attention_backward():
+    ad, ops = _ad()
+    g = torch.Generator().manual_seed(5)
+    L, S, frames = 300, 260, 2
+    q, k, v = (torch.randn((frames * n, 128), generator=g) for n in (L, S, S))
+    go = torch.randn((frames * L, 128), generator=g)
+    qr, kr, vr = _leaf(q), _leaf(k), _leaf(v)
+    outs = []
+    for f in range(frames):
+        qq, kk, vv = qr[f * L:(f + 1) * L].view(1, L, 4, 32), kr[f * S:(f + 1) * S].view(1, S, 4, 32), vr[f * S:(f + 1) * S].view(1, S, 4, 32)
+        a = torch.softmax(torch.einsum("nlhd,nshd->nlsh", qq, kk) / 32 ** 0.5, dim=2)
+        outs.append(torch.einsum("nlsh,nshd->nlhd", a, vv).reshape(L, 128))
+    y = torch.cat(outs)
+    y.backward(go)
+    qc, kc, vc = _cuda_leaf(q), _cuda_leaf(k), _cuda_leaf(v)
+    yc = ad.attention(qc, kc, vc, frames, 4, 1.0 / 32 ** 0.5)
+    yc.backward(go.cuda())
+    _check([("y", yc, y), ("dq", qc.grad, qr.grad), ("dk", kc.grad, kr.grad), ("dv", vc.grad, vr.grad)])
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,h,w", [(64, 64, 3, 1, 1, 12, 16), (64, 128, 3, 2, 1, 12, 16), (64, 128, 1, 2, 0, 12, 16),
+                                                       (3, 64, 7, 2, 3, 16, 24), (192, 64, 3, 1, 1, 8, 12)])
+def test_conv_backward(cin, cout, k, stride, pad, h, w):
+    ad, ops = _ad()
+    g = torch.Generator().manual_seed(cin + cout + k)
+    x = torch.randn((2, cin, h, w), generator=g)
+    wt = torch.randn((cout, cin, k, k), generator=g) / math.sqrt(cin * k * k)
+    xr, wr = _leaf(x), _leaf(wt)
+    y = F.conv2d(xr, wr, None, stride, pad)
+    go = torch.randn(y.shape, generator=g)
+    y.backward(go)
+    cpad = (cin + 3) // 4 * 4
+    xn = ops.nchw_to_nhwc(x.cuda(), cpad=cpad).requires_grad_(cin % 4 == 0)
+    wc = _cuda_leaf(wt)
+    yc = ad.conv2d(xn, wc, stride, pad)
+    yc.backward(ops.nchw_to_nhwc(go.cuda()))
+    pairs = [("y", ops.nhwc_to_nchw(yc.detach()), y), ("dw", wc.grad, wr.grad)]
+    if cin % 4 == 0:
+        pairs.append(("dx", ops.nhwc_to_nchw(xn.grad), xr.grad))
+    _check(pairs)
+
+
+def test_image_helpers_backward():
+    ad, ops = _ad()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((2, 32, 10, 14), generator=g)
+    x2 = torch.randn((2, 16, 20, 28), generator=g)
+    xr, x2r = _leaf(x), _leaf(x2)
+    y = torch.cat((F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False), x2r), 1)
+    go = torch.randn(y.shape, generator=g)
+    y.backward(go)
+    xc = ops.nchw_to_nhwc(x.cuda()).requires_grad_(True)
+    x2c = ops.nchw_to_nhwc(x2.cuda()).requires_grad_(True)
+    ad.upsample2x_cat(xc, x2c).backward(ops.nchw_to_nhwc(go.cuda()))
+    _check([("up dx1", ops.nhwc_to_nchw(xc.grad), xr.grad), ("up dx2", ops.nhwc_to_nchw(x2c.grad), x2r.grad)])
+    xm = torch.randn((2, 16, 11, 13), generator=g)
+    xmr = _leaf(xm)
+    ym = F.max_pool2d(xmr, 3, 2, 1)
+    gm = torch.randn(ym.shape, generator=g)
+    ym.backward(gm)
+    xmc = ops.nchw_to_nhwc(xm.cuda()).requires_grad_(True)
+    ad.maxpool2d(xmc).backward(ops.nchw_to_nhwc(gm.cuda()))
+    _check([("maxpool2d dx", ops.nhwc_to_nchw(xmc.grad), xmr.grad)])
+    fmap = torch.randn((1, 64, 80, 256), generator=g)
+    ctr = torch.stack([torch.randint(2, 254, (64,), generator=g), torch.randint(2, 78, (64,), generator=g)]).float()
+    fr = _leaf(fmap)
+    from oracle import restate
+    p = torch.squeeze(restate.extract_patch(fr, ctr))
+    gp = torch.randn(p.shape, generator=g)
+    p.backward(gp)
+    fc = ops.nchw_to_nhwc(fmap.cuda()).requires_grad_(True)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ad.extract_patch(fc, 0, ctr.cuda(), err).backward(gp.cuda())
+    _check([("patch dmap", ops.nhwc_to_nchw(fc.grad), fr.grad)])
+
+
+def test_adam_kernel_matches_torch():
+    ad, ops = _ad()
+    g = torch.Generator().manual_seed(7)
+    p0 = torch.randn((1000,), generator=g)
+    pr = _leaf(p0)
+    opt = torch.optim.Adam([pr], lr=1e-3)
+    pc, m, v = p0.cuda().clone(), torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
+    for step in range(1, 4):
+        grad = torch.randn((1000,), generator=g)
+        pr.grad = grad.clone()
+        opt.step()
+        ops.adam_step(pc, grad.cuda(), m, v, 1e-3, 0.9, 0.999, 1e-8, step)
+    assert rel_err(pc, pr.detach()) < 1e-6
