@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cofi", choices=["cofi", "reference"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer = BASELINE configs[1] (the headline metric); train = configs[4] (tools/train_bench.py)")
+    ap.add_argument("--train-batch", type=int, default=4, help="training frames per GPU per step (configs[4])")
     ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
     ap.add_argument("--num-pc", type=int, default=20480)
     ap.add_argument("--engine", default=os.environ.get("COFI_ENGINE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
@@ -349,7 +352,11 @@ def run_cofi(args):
 
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.workload == "train":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_bench
+        (train_bench.run_reference if args.impl == "reference" else train_bench.run_train)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_cofi(args)

@@ -34,13 +34,34 @@ class _Linear(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         g = dy.contiguous() if ctx.act == ACT_NONE else ops.act_bwd(dy, y, ctx.act)
         dx = dw = db = None
+        n = w.shape[0]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(_pad_cols(g))[:n]
+        if n % 4:                                          # the 1-channel score heads: contract over a zero-padded width
+            g, w = _pad_cols(g), _pad_rows(w)
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(g, ops.transpose2d(w))          # [M,N] x [K,N]^T
         if ctx.needs_input_grad[1]:
-            dw = ops.gemm_tn(g, x)                         # dY^T X, no transposes
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = ops.colsum(g)
+            dw = ops.gemm_tn(g, x)[:n]                     # dY^T X, no transposes
         return dx, dw, db, None
+
+
+def _pad_cols(t):
+    pad = -t.shape[1] % 4
+    if not pad:
+        return t
+    out = torch.zeros((t.shape[0], t.shape[1] + pad), dtype=t.dtype, device=t.device)
+    out[:, :t.shape[1]] = t
+    return out
+
+
+def _pad_rows(t):
+    pad = -t.shape[0] % 4
+    if not pad:
+        return t
+    out = torch.zeros((t.shape[0] + pad, t.shape[1]), dtype=t.dtype, device=t.device)
+    out[:t.shape[0]] = t
+    return out
 
 
 def linear(x, w, b=None, act: int = ACT_NONE):

@@ -195,7 +195,23 @@ def make_frame(seed: int, num_pc: int = 20480, levels: int = LEVELS, knn: int = 
     P = np.eye(4)
     P[:3, :3] = R
     P[:3, 3] = [tx, 0.0, tz]
+    # training supervision of the reference's loader (reference data/kitti.py:334-371, consumed at train.py:204-246):
+    # in-frustum super points (= the key points), as many out-of-frustum ones, their 1/8-resolution pixel index,
+    # and the camera model at 1/8 resolution with the cloud->camera pose.  Drawn after every other random number.
+    out_cand = np.nonzero(~ok)[0]
+    if out_cand.shape[0] == 0:
+        out_cand = np.arange(lat[-1].shape[0])
+    outline = rng.choice(out_cand, num_kpt, replace=out_cand.shape[0] < num_kpt)
+    coarse_pix = (np.floor(v[sel] / 4.0) * (IMG_W // 8) + np.floor(u[sel] / 4.0)).astype(np.int64)
+    P_cam = np.eye(4)
+    P_cam[:3, :3] = R.T
+    P_cam[:3, 3] = -R.T @ np.array([tx, 0.0, tz])
     return {
+        "pc_kpt_idx": torch.from_numpy(sel.astype(np.int64)),
+        "pc_outline_idx": torch.from_numpy(outline.astype(np.int64)),
+        "coarse_img_kpt_idx": torch.from_numpy(coarse_pix),
+        "K_4": torch.tensor([[fx / 4, 0, cx / 4], [0, fy / 4, cy / 4], [0, 0, 1]], dtype=torch.float32),
+        "P": torch.from_numpy(P_cam.astype(np.float32)),
         "pc_data_dict": {
             "points": points,
             "neighbors": neighbors,
@@ -247,4 +263,6 @@ def stack_frames(frames: List[Dict]) -> Dict:
         "img": torch.cat([f["img"] for f in frames], 0),
         "fine_center_kpt_coors": [f["fine_center_kpt_coors"] for f in frames],
         "fine_pc_inline_index": [f["fine_pc_inline_index"] for f in frames],
+        **{k: [f[k] for f in frames] for k in ("fine_xy", "pc_kpt_idx", "pc_outline_idx", "coarse_img_kpt_idx", "K_4", "P")
+           if k in frames[0]},
     }

@@ -167,24 +167,33 @@ def _bn_fold(bn: nn.BatchNorm2d):
     return scale, shift
 
 
+# forward_batch stacks B independent frames: train-mode BatchNorm then keeps per-frame statistics (the reference
+# feeds one frame per call, train.py:226), instead of pooling the stack like a B-image batch would.
+PER_FRAME_BN = [False]
+
+
 def _bn_train(bn: nn.BatchNorm2d, y_nhwc, act, residual=None):
-    """train-mode BatchNorm: batch statistics over B*H*W rows (+ running-stat update like nn.BatchNorm2d)."""
+    """train-mode BatchNorm: batch statistics over the H*W rows of each call's batch (+ running-stat update like
+    nn.BatchNorm2d); with PER_FRAME_BN every image of the stack is its own batch, updated in order."""
     B, H, W, C = y_nhwc.shape
     res = None if residual is None else residual.reshape(B * H * W, C)
     flat = y_nhwc.reshape(B * H * W, C)
+    fr = B if PER_FRAME_BN[0] else 1
     if ad.active(bn):
-        out = ad.norm_rows(flat, 1, C, bn.weight, bn.bias, bn.eps, res, act)
+        out = ad.norm_rows(flat, fr, C, bn.weight, bn.bias, bn.eps, res, act)
         with torch.no_grad():
-            mr = ops.norm_rows_stats(flat.detach(), 1, C, bn.eps)
+            mr = ops.norm_rows_stats(flat.detach(), fr, C, bn.eps)
             mean, var = mr[:, 0], 1.0 / (mr[:, 1] * mr[:, 1]) - bn.eps
     else:
-        out, mean, var = ops.norm_rows(flat, 1, C, bn.weight, bn.bias, bn.eps, residual=res, act=act, want_stats=True)
+        out, mean, var = ops.norm_rows(flat, fr, C, bn.weight, bn.bias, bn.eps, residual=res, act=act, want_stats=True)
     with torch.no_grad():
-        n = B * H * W
+        n = B * H * W // fr
         m = bn.momentum
-        bn.running_mean.mul_(1 - m).add_(mean.view(-1), alpha=m)
-        bn.running_var.mul_(1 - m).add_(var.view(-1) * (n / max(n - 1, 1)), alpha=m)
-        bn.num_batches_tracked += 1
+        mean, var = mean.reshape(fr, C), var.reshape(fr, C) * (n / max(n - 1, 1))
+        for f in range(fr):
+            bn.running_mean.mul_(1 - m).add_(mean[f], alpha=m)
+            bn.running_var.mul_(1 - m).add_(var[f], alpha=m)
+        bn.num_batches_tracked += fr
     return out.view(B, H, W, C)
 
 

@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from .. import autograd as ad
 from .. import ops
+from . import imagenet
 from .imagenet import ImageEncoder, ImageUpSample, ResidualConv  # noqa: F401  (ResidualConv: reference import surface)
 from .kpconv.kp_backbone import KPConvFPN
 from .transformer.position_encoding import PositionEmbeddingCoordsSine, PositionEmbeddingLearned
@@ -288,7 +289,11 @@ class CoFiI2P(nn.Module):
     def forward_batch(self, batch: Dict, mode: str = "val"):
         """B frames stacked along rows (see cofii2p_b200.frames.stack_frames). Returns a list of 8-tuples."""
         B = batch["frames"]
-        core = self.core(batch["pc_data_dict"], batch["img"], B)
+        imagenet.PER_FRAME_BN[0] = True
+        try:
+            core = self.core(batch["pc_data_dict"], batch["img"], B)
+        finally:
+            imagenet.PER_FRAME_BN[0] = False
         n1 = core["pc_decode_3"].shape[0] // B
         outs, errs = [], []
         for b in range(B):

@@ -1,0 +1,125 @@
+"""Data-parallel training step of the hot path (BASELINE.json configs[4]).
+
+What the reference does per iteration (reference train.py:186-285): one frame through `CoFiI2P.forward(mode='train')`,
+three losses (`model/loss.py`), `loss.backward()`, `torch.optim.Adam.step()` -- single GPU, batch 1.  Here:
+
+* `training_losses` restates train.py:233-283 (the gathers that pick the supervised rows and the three losses);
+* `TrainStep` runs B stacked frames per rank through `CoFiI2P.forward_batch(mode='train')`.  Every normalisation keeps
+  per-frame statistics, so the step equals B reference iterations whose gradients are averaged (gradient accumulation)
+  -- the only batching the reference's batch-1 model admits;
+* forward and backward are the library's kernels (cofii2p_b200/autograd.py); parameters, gradients and the Adam moments
+  live in three flat fp32 buffers: one NCCL all-reduce over NVLink for the gradient, one fused Adam kernel for the update;
+* frames shard across ranks (cofii2p_b200/shard.py); there is no other collective on the path.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .model.loss import desc_loss, fine_circle_loss, overlap_loss
+
+__all__ = ["training_losses", "TrainStep"]
+
+
+def training_losses(out, sup: Dict, opt, points4: torch.Tensor):
+    """Losses of one frame (reference train.py:233-283). `out` is the model's 8-tuple in train mode, `sup` the frame's
+    supervision (pc_kpt_idx, pc_outline_idx, coarse_img_kpt_idx, K_4, P, fine_xy, fine_center_kpt_coors), `points4`
+    the frame's coarsest-level points [n4,3]."""
+    img_features, pc_features, _, coarse_pc_score, fine_patch, fine_pc = out[:6]
+    dev = pc_features.device
+    n = opt.num_kpt
+    kpt, outl, pix = sup["pc_kpt_idx"], sup["pc_outline_idx"], sup["coarse_img_kpt_idx"]
+    pc_in = pc_features[:, kpt]                                                          # :233
+    xyz_in = points4[kpt].t()                                                            # :237
+    C, H, W = img_features.shape[1:]
+    img_in = img_features.reshape(C, H * W)[:, pix]                                      # :239-243
+    gx = (pix % W).to(torch.float32)
+    gy = torch.div(pix, W, rounding_mode="floor").to(torch.float32)
+    img_xy = torch.stack((gx, gy), 0)                                                    # :245
+    P, K4 = sup["P"], sup["K_4"]
+    proj = K4 @ (P[0:3, 0:3] @ xyz_in + P[0:3, 3:])                                      # :247
+    proj_xy = proj[0:2] / proj[2:]
+    mask = (torch.sqrt(torch.sum(torch.square(img_xy.unsqueeze(-1) - proj_xy.unsqueeze(-2)), dim=0))
+            <= opt.dist_thres).float()                                                   # :251
+    loss_desc, _ = desc_loss(dev, img_in, pc_in, mask, pos_margin=opt.pos_margin, neg_margin=opt.neg_margin)   # :254
+    score = coarse_pc_score.reshape(-1)
+    loss_coarse = overlap_loss(dev, score[kpt], score[outl])                             # :256-260
+    rel = torch.floor(sup["fine_xy"]) - sup["fine_center_kpt_coors"].to(torch.float32) + 2   # :267 (integer pixels)
+    rel_index = (rel[1] * 4 + rel[0]).long().clamp_(0, 15)
+    loss_fine = fine_circle_loss(dev, fine_patch, fine_pc, rel_index, n)                 # :283
+    return loss_desc + loss_coarse + loss_fine, (loss_desc.detach(), loss_coarse.detach(), loss_fine.detach())
+
+
+class TrainStep:
+    """One optimisation step over B stacked frames per rank (Adam, reference train.py:156 defaults)."""
+
+    def __init__(self, model, opt, lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8, group=None):
+        self.model, self.opt = model, opt
+        self.lr = float(opt.lr if lr is None else lr)
+        self.betas, self.eps = betas, eps
+        self.group = group
+        self.world = torch.distributed.get_world_size(group) if torch.distributed.is_initialized() else 1
+        self.step_count = 0
+        self.live: Optional[List[torch.nn.Parameter]] = None
+        self.flat_p = self.flat_g = self.m = self.v = None
+
+    # -------------------------------------------------------------------------------------------------------------
+    def _flatten(self, live: List[torch.nn.Parameter]) -> None:
+        """Move the live parameters into one flat buffer (each parameter becomes a view of it), and give every one a
+        view of the flat gradient buffer as its `.grad`, so autograd accumulates in place and the all-reduce and
+        Adam each touch one contiguous range.  Parameters that never receive a gradient (about 40 % of the
+        reference's 51.6 M: dead layers) stay where they are, as under torch.optim.Adam."""
+        dev = live[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in live]                                 # 16-byte aligned slots
+        total = sum(sizes)
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m, self.v = torch.zeros_like(self.flat_p), torch.zeros_like(self.flat_p)
+        off = 0
+        for p, sz in zip(live, sizes):
+            n = p.numel()
+            self.flat_p[off:off + n].copy_(p.data.reshape(-1))
+            g = self.flat_g[off:off + n].view_as(p)
+            if p.grad is not None:
+                g.copy_(p.grad)
+            p.data = self.flat_p[off:off + n].view_as(p)
+            p.grad = g
+            off += sz
+        self.live = live
+
+    def loss(self, batch: Dict):
+        """Mean over the rank's frames of the reference's per-frame loss."""
+        model, B = self.model, batch["frames"]
+        outs = model.forward_batch(batch, "train")
+        n4 = batch["pc_data_dict"]["points"][-1].shape[0] // B
+        total, parts = None, []
+        for b in range(B):
+            sup = {k: batch[k][b] for k in ("pc_kpt_idx", "pc_outline_idx", "coarse_img_kpt_idx", "K_4", "P", "fine_xy",
+                                           "fine_center_kpt_coors")}
+            l, p = training_losses(outs[b], sup, self.opt, batch["pc_data_dict"]["points"][-1][b * n4:(b + 1) * n4])
+            total = l if total is None else total + l
+            parts.append(torch.stack(p))
+        return total / B, torch.stack(parts).mean(0)
+
+    def backward(self, batch: Dict):
+        """forward + loss + backward; the rank's gradient is left in the parameters' `.grad` (flat after step 1)."""
+        self.model.train()
+        if self.flat_g is not None:
+            self.flat_g.zero_()
+        else:
+            for p in self.model.parameters():
+                p.grad = None
+        loss, parts = self.loss(batch)
+        loss.backward()
+        if self.live is None:
+            self._flatten([p for p in self.model.parameters() if p.requires_grad and p.grad is not None])
+        return loss.detach(), parts
+
+    def step(self, batch: Dict):
+        loss, parts = self.backward(batch)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.group)                  # NCCL sum over NVLink
+        self.step_count += 1
+        ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.step_count, grad_scale=1.0 / self.world)
+        return loss, parts
