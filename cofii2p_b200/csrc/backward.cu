@@ -895,14 +895,35 @@ static int tn_splits(int64_t R) {
     if (s > 64) s = 64;
     return (int)s;
 }
-extern "C" int64_t cofi_gemm_tn_workspace(int64_t R, int Mo, int No) { return (int64_t)tn_splits(R) * Mo * No * 4; }
+namespace cofi { namespace tc {
+int64_t tn_tc_per(int64_t R, int Mo, int No, int* splits);
+int gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t R, int Mo, int No, float* partial,
+               int* splits_out, cudaStream_t st);
+bool conv_wgrad_tc_ok(int Cin, int Cout, int Wo, int stride);
+int conv_wgrad_tc(const float* x, int B, int H, int W, int Cin, const float* dy, int Cout, int KH, int KW, int stride, int pad,
+                  int Ho, int Wo, float* partial, int* splits_out, cudaStream_t st);
+}}
+static int tn_splits_any(int64_t R, int Mo, int No) {  // workspace covers either engine
+    int tcs = 1;
+    cofi::tc::tn_tc_per(R, Mo, No, &tcs);
+    const int s = tn_splits(R);
+    return s > tcs ? s : tcs;
+}
+extern "C" int64_t cofi_gemm_tn_workspace(int64_t R, int Mo, int No) { return (int64_t)tn_splits_any(R, Mo, No) * Mo * No * 4; }
 
 // C[Mo,No] (+)= A[R,Mo]^T B[R,No]   (weight gradient of a Linear: A = dY, B = X)
 extern "C" int cofi_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t R, int Mo, int No,
-                            int accumulate, void* work, void* stream) {
+                            int accumulate, int engine, void* work, void* stream) {
     COFI_REQUIRE(A && B && C && work && R > 0 && Mo > 0 && No > 0, "cofi_gemm_tn: bad argument");
     COFI_REQUIRE(Mo % 4 == 0 && No % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0, "cofi_gemm_tn: Mo, No, lda, ldb multiples of 4");
     COFI_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, "cofi_gemm_tn: 16-byte alignment");
+    if (engine == COFI_GEMM_TF32) {  // tcgen05, MN-major operands (gemm_tn_tc.cu)
+        int sp = 1;
+        int rc = cofi::tc::gemm_tn_tc(A, lda, B, ldb, R, Mo, No, (float*)work, &sp, ST);
+        if (rc) return rc;
+        split_sum_kernel<<<ew_blocks_b((int64_t)Mo * No, 256), 256, 0, ST>>>((const float*)work, sp, (int64_t)Mo * No, C, accumulate);
+        return check_launch("cofi_gemm_tn(sum)");
+    }
     const int splits = tn_splits(R);
     const int64_t per = ceil_div(ceil_div(R, splits), TN_BK) * TN_BK;
     DenseB bl{B, ldb, R, No};
@@ -916,13 +937,25 @@ extern "C" int cofi_gemm_tn(const float* A, int64_t lda, const float* B, int64_t
 }
 
 extern "C" int64_t cofi_conv2d_wgrad_workspace(int B, int Ho, int Wo, int Cout, int KH, int KW, int Cin) {
-    return (int64_t)tn_splits((int64_t)B * Ho * Wo) * Cout * KH * KW * Cin * 4;
+    return (int64_t)tn_splits_any((int64_t)B * Ho * Wo, Cout, KH * KW * Cin) * Cout * KH * KW * Cin * 4;
 }
 // dw[Cout, KH*KW*Cin] (+)= sum over output pixels of dy[p, co] * x[p shifted by the tap, ci]
 extern "C" int cofi_conv2d_wgrad_nhwc(const float* x, int B, int H, int W, int Cin, const float* dy, int Cout, int KH,
-                                      int KW, int stride, int pad, float* dw, int accumulate, void* work, void* stream) {
+                                      int KW, int stride, int pad, float* dw, int accumulate, int engine, void* work,
+                                      void* stream) {
     COFI_REQUIRE(x && dy && dw && work, "cofi_conv2d_wgrad_nhwc: null pointer");
     COFI_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "cofi_conv2d_wgrad_nhwc: channel counts must be multiples of 4");
+    {
+        const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+        if (engine == COFI_GEMM_TF32 && cofi::tc::conv_wgrad_tc_ok(Cin, Cout, Wo, stride)) {
+            int sp = 1;
+            int rc = cofi::tc::conv_wgrad_tc(x, B, H, W, Cin, dy, Cout, KH, KW, stride, pad, Ho, Wo, (float*)work, &sp, ST);
+            if (rc) return rc;
+            const int64_t n = (int64_t)Cout * KH * KW * Cin;
+            split_sum_kernel<<<ew_blocks_b(n, 256), 256, 0, ST>>>((const float*)work, sp, n, dw, accumulate);
+            return check_launch("cofi_conv2d_wgrad_nhwc(sum)");
+        }
+    }
     ConvTapB bl;
     bl.x = x; bl.B = B; bl.H = H; bl.W = W; bl.Cin = Cin; bl.KH = KH; bl.KW = KW; bl.stride = stride; bl.pad = pad;
     bl.Ho = (H + 2 * pad - KH) / stride + 1;

@@ -80,15 +80,17 @@ struct KeyHash {
 };
 
 static const CUtensorMap* get_tmap_any(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                       const uint32_t* box, int half) {
+                                       const uint32_t* box, int half, const uint32_t* elem_strides = nullptr,
+                                       int atom32 = 0 /* SWIZZLE_128B with a 32-byte atom (MN-major tf32 operands) */) {
     static std::mutex mu;
     static std::unordered_map<Key, CUtensorMap*, KeyHash> cache;
     Key k{};
     k.v[0] = (uint64_t)(uintptr_t)base;
-    k.v[1] = (uint64_t)rank | ((uint64_t)half << 8);
+    k.v[1] = (uint64_t)rank | ((uint64_t)half << 8) | ((uint64_t)atom32 << 16);
     for (int i = 0; i < rank; ++i) {
         k.v[2 + i] = dims[i];
         k.v[6 + i] = ((uint64_t)box[i] << 40) | (i > 0 ? strides_bytes[i - 1] : 0);
+        if (elem_strides) k.v[10] |= (uint64_t)elem_strides[i] << (8 * i);
     }
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(k);
@@ -109,11 +111,12 @@ static const CUtensorMap* get_tmap_any(const void* base, int rank, const uint64_
     for (int i = 0; i < rank; ++i) {
         gdim[i] = dims[i];
         bx[i] = box[i];
-        es[i] = 1;
+        es[i] = elem_strides ? elem_strides[i] : 1;
         if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
     }
     CUresult r = fn(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         delete m;
@@ -128,6 +131,10 @@ static const CUtensorMap* get_tmap_any(const void* base, int rank, const uint64_
 const CUtensorMap* get_tmap_f32(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                                 const uint32_t* box) {
     return get_tmap_any(base, rank, dims, strides_bytes, box, 0);
+}
+const CUtensorMap* get_tmap_f32_mn(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                   const uint32_t* box, const uint32_t* elem_strides) {
+    return get_tmap_any(base, rank, dims, strides_bytes, box, 0, elem_strides, 1);
 }
 const CUtensorMap* get_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                                 const uint32_t* box) {

@@ -72,9 +72,9 @@ SIGNATURES = {
     "cofi_dilate2_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "cofi_extract_patch_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp]),
     "cofi_gemm_tn_workspace": (_l, [_l, _i, _i]),
-    "cofi_gemm_tn": (_i, [_vp, _l, _vp, _l, _vp, _l, _i, _i, _i, _vp, _vp]),
+    "cofi_gemm_tn": (_i, [_vp, _l, _vp, _l, _vp, _l, _i, _i, _i, _i, _vp, _vp]),
     "cofi_conv2d_wgrad_workspace": (_l, [_i, _i, _i, _i, _i, _i, _i]),
-    "cofi_conv2d_wgrad_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "cofi_conv2d_wgrad_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "cofi_attention_fwd_lse": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
     "cofi_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "cofi_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),

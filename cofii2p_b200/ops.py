@@ -598,7 +598,8 @@ def colsum(x):
 
 
 def gemm_tn(a, b):
-    """a [R, Mo], b [R, No] -> a^T b [Mo, No] (fp32 SIMT, deterministic split over R)."""
+    """a [R, Mo], b [R, No] -> a^T b [Mo, No] (tcgen05 MN-major under the tf32 engine, SIMT fp32 otherwise; deterministic
+    split over R)."""
     a, lda = _rows(a, "a")
     b, ldb = _rows(b, "b")
     R, Mo = a.shape
@@ -606,7 +607,7 @@ def gemm_tn(a, b):
     out = torch.empty((Mo, No), dtype=torch.float32, device=a.device)
     ws = _ws(_lib.cofi_gemm_tn_workspace(R, Mo, No), a.device)
     _meta(2.0 * R * Mo * No, 4.0 * (R * Mo + R * No + Mo * No))
-    _call("cofi_gemm_tn", _p(a), lda, _p(b), ldb, _p(out), R, Mo, No, 0, _p(ws), _st())
+    _call("cofi_gemm_tn", _p(a), lda, _p(b), ldb, _p(out), R, Mo, No, 0, _engine, _p(ws), _st())
     return out
 
 
@@ -721,7 +722,7 @@ def conv2d_wgrad_nhwc(x, dy, kh: int, kw: int, stride: int, pad: int):
     dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=x.device)
     ws = _ws(_lib.cofi_conv2d_wgrad_workspace(B, Ho, Wo, Cout, kh, kw, Cin), x.device)
     _meta(2.0 * B * Ho * Wo * Cout * kh * kw * Cin, 4.0 * (x.numel() + dy.numel() + dw.numel()))
-    _call("cofi_conv2d_wgrad_nhwc", _p(x), B, H, W, Cin, _p(dy), Cout, kh, kw, stride, pad, _p(dw), 0, _p(ws), _st())
+    _call("cofi_conv2d_wgrad_nhwc", _p(x), B, H, W, Cin, _p(dy), Cout, kh, kw, stride, pad, _p(dw), 0, _engine, _p(ws), _st())
     return dw
 
 

@@ -302,14 +302,16 @@ int cofi_maxpool2d_3x3s2_bwd(const float* x, const float* dy, int B, int H, int 
 int cofi_dilate2_nhwc(const float* x, int B, int H, int W, int C, float* y, void* stream);
 int cofi_extract_patch_bwd(const float* dpatch, int H, int W, int C, int b, const float* centers, int64_t n, float* dmap,
                            void* stream);
-/* C[Mo,No] (+)= A[R,Mo]^T B[R,No]: weight gradient of a Linear without transposes (A = dY, B = X). */
+/* C[Mo,No] (+)= A[R,Mo]^T B[R,No]: weight gradient of a Linear without transposes (A = dY, B = X).
+ * engine COFI_GEMM_TF32: tcgen05 with both operands MN-major (the reduction index is the outer one in HBM), split over R;
+ * any other engine: SIMT fp32.  Partial tiles are folded by a deterministic reduction. */
 int64_t cofi_gemm_tn_workspace(int64_t R, int Mo, int No);
 int cofi_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t R, int Mo, int No,
-                 int accumulate, void* work, void* stream);
+                 int accumulate, int engine, void* work, void* stream);
 /* weight gradient of cofi_conv2d_nhwc: dw[Cout, KH*KW*Cin] */
 int64_t cofi_conv2d_wgrad_workspace(int B, int Ho, int Wo, int Cout, int KH, int KW, int Cin);
 int cofi_conv2d_wgrad_nhwc(const float* x, int B, int H, int W, int Cin, const float* dy, int Cout, int KH, int KW,
-                           int stride, int pad, float* dw, int accumulate, void* work, void* stream);
+                           int stride, int pad, float* dw, int accumulate, int engine, void* work, void* stream);
 /* attention for training: forward that also returns the log-sum-exp [frames*L, heads], and its backward (D = 32). */
 int cofi_attention_fwd_lse(const float* q, const float* k, const float* v, int64_t L, int64_t S, int frames, int heads,
                            int D, float scale, float* out, float* lse, void* stream);
