@@ -109,23 +109,26 @@ def kpconv(feats, weights, bias, q_points, s_points, nbr, kernel_points, sigma, 
 class _NormRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, residual, frames, groups, eps, act):
-        y = ops.norm_rows(x, frames, groups, gamma, beta, eps, residual=residual, act=act)
-        ctx.save_for_backward(x, gamma, y)
+        y, mean, var = ops.norm_rows(x, frames, groups, gamma, beta, eps, residual=residual, act=act, want_stats=True)
+        mr = torch.stack((mean.reshape(-1), torch.rsqrt(var.reshape(-1) + eps)), 1)   # (mean, rstd) per (frame, group)
+        ctx.save_for_backward(x, gamma, y, mr)
         ctx.meta = (frames, groups, eps, act, residual is not None)
-        return y
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
 
     @staticmethod
-    def backward(ctx, dy):
-        x, gamma, y = ctx.saved_tensors
+    def backward(ctx, dy, _dmean, _dvar):
+        x, gamma, y, mr = ctx.saved_tensors
         frames, groups, eps, act, has_res = ctx.meta
-        mr = ops.norm_rows_stats(x, frames, groups, eps)
-        dx, dres, dgamma, dbeta = ops.norm_rows_bwd(x, dy, y, mr, frames, groups, gamma, act, has_res)
+        dx, dres, dgamma, dbeta = ops.norm_rows_bwd(x, dy.contiguous(), y, mr, frames, groups, gamma, act, has_res)
         return dx, dgamma, dbeta, dres, None, None, None, None
 
 
-def norm_rows(x, frames, groups, gamma=None, beta=None, eps=1e-5, residual=None, act=ACT_NONE):
-    return _NormRows.apply(x.contiguous(), gamma, beta, None if residual is None else residual.contiguous(), frames,
-                           groups, eps, act)
+def norm_rows(x, frames, groups, gamma=None, beta=None, eps=1e-5, residual=None, act=ACT_NONE, return_stats=False):
+    """return_stats: also the per-(frame, group) mean and biased variance the forward computed (BatchNorm running stats)."""
+    y, mean, var = _NormRows.apply(x.contiguous(), gamma, beta, None if residual is None else residual.contiguous(), frames,
+                                   groups, eps, act)
+    return (y, mean, var) if return_stats else y
 
 
 class _LayerNorm(torch.autograd.Function):

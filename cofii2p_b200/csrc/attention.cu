@@ -99,7 +99,7 @@ attention_simt_kernel(const float* __restrict__ q, const float* __restrict__ k, 
 }
 
 int attention_tc_launch(const float* q, const float* k, const float* vt, int64_t L, int64_t S, int frames, int heads,
-                        int D, float scale, float* out, cudaStream_t st);
+                        int D, float scale, float* out, float* lse, cudaStream_t st);
 bool attention_tc_supported(int64_t L, int64_t S, int heads, int D);
 
 }  // namespace cofi
@@ -131,5 +131,19 @@ extern "C" int cofi_attention_vt(const float* q, const float* k, const float* vt
         set_error("cofi_attention_vt: unsupported shape (D=%d must be 32 or 64, frames*S*4 bytes must be 16-byte aligned)", D);
         return COFI_EUNSUPPORTED;
     }
-    return attention_tc_launch(q, k, vt, L, S, frames, heads, D, scale, out, (cudaStream_t)stream);
+    return attention_tc_launch(q, k, vt, L, S, frames, heads, D, scale, out, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cofi_attention_vt_lse(const float* q, const float* k, const float* vt, int64_t L, int64_t S, int frames,
+                                     int heads, int D, float scale, float* out, float* lse, void* stream) {
+    COFI_REQUIRE(q && k && vt && out && lse, "cofi_attention_vt_lse: null pointer");
+    COFI_REQUIRE(L > 0 && S > 0 && frames > 0 && heads > 0, "cofi_attention_vt_lse: bad shape");
+    COFI_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)vt % 16) == 0 &&
+                     ((uintptr_t)out % 16) == 0,
+                 "cofi_attention_vt_lse: 16-byte alignment required");
+    if (!attention_tc_supported(L, S, heads, D)) {
+        set_error("cofi_attention_vt_lse: unsupported shape (D=%d must be 32 or 64, frames*S*4 bytes must be 16-byte aligned)", D);
+        return COFI_EUNSUPPORTED;
+    }
+    return attention_tc_launch(q, k, vt, L, S, frames, heads, D, scale, out, lse, (cudaStream_t)stream);
 }

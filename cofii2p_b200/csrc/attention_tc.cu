@@ -39,6 +39,7 @@ struct AttParams {
     int heads;
     float scale;
     int num_tiles;
+    float* lse;  // optional [frames*L, heads] log-sum-exp of the scaled scores (training forward)
 };
 
 template <int AD>
@@ -218,6 +219,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int d = 0; d < AD; d += 4)
                 *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+            if (p.lse) p.lse[((int64_t)frame * p.L + q0 + r) * p.heads + head] = mrun + logf(lrun);
         }
     }
     __syncthreads();
@@ -238,7 +240,7 @@ bool attention_tc_supported(int64_t L, int64_t S, int heads, int D) {
 
 // vt: V^T [heads*D, frames*S] row-major (keys contiguous): produced by the v_proj GEMM with swapped operands
 int attention_tc_launch(const float* q, const float* k, const float* vt, int64_t L, int64_t S, int frames, int heads,
-                        int D, float scale, float* out, cudaStream_t st) {
+                        int D, float scale, float* out, float* lse, cudaStream_t st) {
     using namespace tc;
     const int64_t C = (int64_t)heads * D;
     uint64_t dq[2] = {(uint64_t)C, (uint64_t)(frames * L)}, sq[1] = {(uint64_t)C * 4};
@@ -251,7 +253,7 @@ int attention_tc_launch(const float* q, const float* k, const float* vt, int64_t
     const CUtensorMap* tk = get_tmap_f32(k, 2, dk, sk, bk);
     const CUtensorMap* tv = get_tmap_f32(vt, 2, dv, sv, bv);
     if (!tq || !tk || !tv) return COFI_ECUDA;
-    AttParams p{out, L, S, heads, scale, (int)ceil_div(S, AK)};
+    AttParams p{out, L, S, heads, scale, (int)ceil_div(S, AK), lse};
     dim3 grid((unsigned)ceil_div(L, AQ), heads, frames);
     static bool attr_done[2] = {false, false};
     auto set_attr = [&](auto kern, int smem, int slot) -> int {

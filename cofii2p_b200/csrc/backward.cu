@@ -54,6 +54,39 @@ colsum_partial_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, in
         part[(int64_t)blockIdx.y * C + c] = s;
     }
 }
+// 4 columns per thread (float4), two rows in flight, fp32 partials folded into fp64 across threads
+__global__ void __launch_bounds__(256)
+colsum_partial_v4_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C, double* __restrict__ part) {
+    const int cl = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + cl) * 4;
+    const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = blockIdx.y * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (c < C) {
+        int64_t r = r0 + ty;
+        for (; r + 8 < r1; r += 16) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + (r + 8) * ldx + c));
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+            b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+        }
+        if (r < r1) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c));
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+        }
+    }
+    __shared__ double sh[8][32][4];
+    sh[ty][cl][0] = (double)a.x + (double)b.x;
+    sh[ty][cl][1] = (double)a.y + (double)b.y;
+    sh[ty][cl][2] = (double)a.z + (double)b.z;
+    sh[ty][cl][3] = (double)a.w + (double)b.w;
+    __syncthreads();
+    if (ty < 4 && c < C) {  // thread (ty, cl) folds component ty of column group cl
+        double s = 0.0;
+        for (int k = 0; k < 8; ++k) s += sh[k][cl][ty];
+        part[(int64_t)blockIdx.y * C + c + ty] = s;
+    }
+}
 __global__ void __launch_bounds__(128)
 colsum_final_kernel(const double* __restrict__ part, int chunks, int C, float* __restrict__ out, int accumulate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,39 +357,128 @@ maxpool_rows_bwd_kernel(const float* __restrict__ x, int C, const int64_t* __res
 }
 
 // KPConv aggregate backward: dfeats[nbr[m,h], c] += sum_k w[m,h,k] * dagg[m,k,c]  (same influence arithmetic as forward)
+template <int VEC>
+struct BVec;
+template <>
+struct BVec<1> { using T = float; };
+template <>
+struct BVec<2> { using T = float2; };
+template <>
+struct BVec<4> { using T = float4; };
+
+// Mirror of the forward kernel (kpconv.cu): one warp per query point.  (1) the 128 neighbour ids / packed points are loaded
+// 4 per lane and the ones inside the kernel's reach are compacted into shared memory; (2) the (neighbour, kernel point)
+// pairs are evaluated 32 at a time, neighbour-major; (3) for every pair with a non-zero influence the warp accumulates
+// w * dagg[m, k, :] (a row of THIS query: coalesced, L1-resident), and when the neighbour changes the finished sum goes to
+// dfeats[neighbour] with one vector atomic per lane (red.global.add.v4.f32).
+template <int VEC, int NCH>
 __global__ void __launch_bounds__(128)
 kpconv_aggregate_bwd_kernel(const float* __restrict__ dagg, int C, const float4* __restrict__ s_packed,
                             const float* __restrict__ q_points, const int64_t* __restrict__ nbr, int H, int64_t Mq,
                             int64_t Ns, int64_t total_q, const float* __restrict__ kernel_points, int K, float sigma,
                             float reach2, float* __restrict__ dfeats) {
     __shared__ float skp[32 * 3];
+    __shared__ float4 snear[4][128];
     if (threadIdx.x < K * 3) skp[threadIdx.x] = kernel_points[threadIdx.x];
     __syncthreads();
-    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (m >= total_q) return;
     const int64_t frame = m / Mq;
     const float4* sp = s_packed + frame * Ns;
     float* db = dfeats + frame * Ns * C;
     const float qx = __ldg(q_points + m * 3), qy = __ldg(q_points + m * 3 + 1), qz = __ldg(q_points + m * 3 + 2);
+    float4* near = snear[wib];
+    int n_near = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int h = j * 32 + lane;
+        const int64_t id = (h < H) ? __ldg(nbr + m * H + h) : Ns;
+        bool is_near = false;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        if (id >= 0 && id < Ns) {
+            const float4 p = __ldg(sp + id);
+            rx = p.x - qx;
+            ry = p.y - qy;
+            rz = p.z - qz;
+            is_near = rx * rx + ry * ry + rz * rz <= reach2;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, is_near);
+        if (is_near) near[n_near + __popc(bal & ((1u << lane) - 1u))] = make_float4(rx, ry, rz, __int_as_float((int)id));
+        n_near += __popc(bal);
+    }
+    __syncwarp();
+
+    using V = typename BVec<VEC>::T;
     const float* drow = dagg + m * (int64_t)K * C;
-    for (int h = 0; h < H; ++h) {  // neighbour loop is warp-uniform; lanes cover channels
-        const int64_t id = __ldg(nbr + m * H + h);
-        if (id < 0 || id >= Ns) continue;
-        const float4 p = __ldg(sp + id);
-        const float rx = p.x - qx, ry = p.y - qy, rz = p.z - qz;
-        if (rx * rx + ry * ry + rz * rz > reach2) continue;
-        for (int c = lane; c < C; c += 32) {
-            float acc = 0.0f;
-            for (int k = 0; k < K; ++k) {
-                const float dx = rx - skp[k * 3], dy = ry - skp[k * 3 + 1], dz = rz - skp[k * 3 + 2];
-                const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                const float w = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsqrt_rn(sq), sigma)), 0.0f);
-                if (w > 0.0f) acc = fmaf(w, __ldg(drow + (int64_t)k * C + c), acc);
+    const bool lane_active = (lane * VEC) < C;
+    float acc[NCH][VEC];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[c][v] = 0.0f;
+
+    auto flush = [&](int row) {  // dfeats[row] += acc; acc = 0
+        if (lane_active) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float* dst = db + (int64_t)row * C + (c * 32 + lane) * VEC;
+                if constexpr (VEC == 4) {
+                    atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]));
+                } else if constexpr (VEC == 2) {
+                    atomicAdd(reinterpret_cast<float2*>(dst), make_float2(acc[c][0], acc[c][1]));
+                } else {
+                    atomicAdd(dst, acc[c][0]);
+                }
             }
-            if (acc != 0.0f) atomicAdd(db + id * C + c, acc);
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[c][v] = 0.0f;
+    };
+
+    int cur_j = -1, cur_row = 0;
+    const int total_pairs = n_near * K;
+    for (int base = 0; base < total_pairs; base += 32) {
+        const int pidx = base + lane;
+        float w = 0.0f;
+        int pj = 0, pk = 0, prow = 0;
+        if (pidx < total_pairs) {
+            pj = pidx / K;
+            pk = pidx - pj * K;
+            const float4 nb = near[pj];
+            prow = __float_as_int(nb.w);
+            const float dx = nb.x - skp[pk * 3 + 0], dy = nb.y - skp[pk * 3 + 1], dz = nb.z - skp[pk * 3 + 2];
+            const float sq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            w = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsqrt_rn(sq), sigma)), 0.0f);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, w > 0.0f);
+        while (mask) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int ej = __shfl_sync(0xffffffffu, pj, l);
+            const int ek = __shfl_sync(0xffffffffu, pk, l);
+            const int er = __shfl_sync(0xffffffffu, prow, l);
+            const float ew = __shfl_sync(0xffffffffu, w, l);
+            if (ej != cur_j) {
+                if (cur_j >= 0) flush(cur_row);
+                cur_j = ej;
+                cur_row = er;
+            }
+            if (lane_active) {
+                const float* row = drow + (int64_t)ek * C;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const V f = __ldg(reinterpret_cast<const V*>(row + (c * 32 + lane) * VEC));
+                    const float* fv = reinterpret_cast<const float*>(&f);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(ew, fv[v], acc[c][v]);
+                }
+            }
         }
     }
+    if (cur_j >= 0) flush(cur_row);
 }
 
 // ------------------------------------------------------------------------------------------ image helpers backward
@@ -751,8 +873,13 @@ extern "C" int cofi_colsum(const float* x, int64_t ldx, int64_t rows, int C, flo
     COFI_REQUIRE(((uintptr_t)work % 8) == 0, "cofi_colsum: workspace alignment");
     int64_t want = (rows + 7) / 8;
     const int chunks = (int)(want < 1 ? 1 : (want > kColChunks ? kColChunks : want));
-    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
-    colsum_partial_kernel<<<grid, 256, 0, ST>>>(x, ldx, rows, C, (double*)work);
+    if (C % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)x % 16) == 0) {
+        dim3 grid4((unsigned)ceil_div(C, 128), (unsigned)chunks);
+        colsum_partial_v4_kernel<<<grid4, 256, 0, ST>>>(x, ldx, rows, C, (double*)work);
+    } else {
+        dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
+        colsum_partial_kernel<<<grid, 256, 0, ST>>>(x, ldx, rows, C, (double*)work);
+    }
     int rc = check_launch("cofi_colsum(partial)");
     if (rc) return rc;
     colsum_final_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, ST>>>((const double*)work, chunks, C, out, accumulate);
@@ -854,8 +981,28 @@ extern "C" int cofi_kpconv_aggregate_bwd(const float* dagg, int C, const float* 
     const int64_t total = Mq * frames;
     if (total == 0) return COFI_OK;
     const float reach = kp_reach > 0.0f ? (kp_reach + sigma) * 1.001f : 1e18f;
-    kpconv_aggregate_bwd_kernel<<<(unsigned)ceil_div(total, 4), 128, 0, ST>>>(
-        dagg, C, (const float4*)s_packed, q_points, nbr, H, Mq, Ns, total, kernel_points, K, sigma, reach * reach, dfeats);
+    COFI_REQUIRE(H <= 128, "cofi_kpconv_aggregate_bwd: H must be <= 128");
+#define BLAUNCH(VEC, NCH)                                                                                                  \
+    kpconv_aggregate_bwd_kernel<VEC, NCH><<<(unsigned)ceil_div(total, 4), 128, 0, ST>>>(                                   \
+        dagg, C, (const float4*)s_packed, q_points, nbr, H, Mq, Ns, total, kernel_points, K, sigma, reach * reach, dfeats)
+    if (C <= 32) {
+        BLAUNCH(1, 1);
+    } else if (C == 64) {
+        BLAUNCH(2, 1);
+    } else if (C % 128 == 0 && C <= 1024) {
+        switch (C / 128) {
+            case 1: BLAUNCH(4, 1); break;
+            case 2: BLAUNCH(4, 2); break;
+            case 3: BLAUNCH(4, 3); break;
+            case 4: BLAUNCH(4, 4); break;
+            case 8: BLAUNCH(4, 8); break;
+            default: set_error("cofi_kpconv_aggregate_bwd: unsupported channel count C=%d", C); return COFI_EUNSUPPORTED;
+        }
+    } else {
+        set_error("cofi_kpconv_aggregate_bwd: unsupported channel count C=%d", C);
+        return COFI_EUNSUPPORTED;
+    }
+#undef BLAUNCH
     return check_launch("cofi_kpconv_aggregate_bwd");
 }
 

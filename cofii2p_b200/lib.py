@@ -45,6 +45,7 @@ SIGNATURES = {
     "cofi_posenc_sine": (_i, [_vp, _l, _i, _i, _vp, _vp, _vp]),
     "cofi_attention": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _i, _vp]),
     "cofi_attention_vt": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp]),
+    "cofi_attention_vt_lse": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
     "cofi_sim_argmin": (_i, [_vp, _l, _vp, _l, _l, _l, _i, _i, _vp, _vp, _i, _vp]),
     "cofi_sim_argmin_f16": (_i, [_vp, _l, _vp, _l, _l, _l, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "cofi_cast_f16": (_i, [_vp, _l, _l, _i, _vp, _l, _vp]),

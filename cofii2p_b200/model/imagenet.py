@@ -180,10 +180,7 @@ def _bn_train(bn: nn.BatchNorm2d, y_nhwc, act, residual=None):
     flat = y_nhwc.reshape(B * H * W, C)
     fr = B if PER_FRAME_BN[0] else 1
     if ad.active(bn):
-        out = ad.norm_rows(flat, fr, C, bn.weight, bn.bias, bn.eps, res, act)
-        with torch.no_grad():
-            mr = ops.norm_rows_stats(flat.detach(), fr, C, bn.eps)
-            mean, var = mr[:, 0], 1.0 / (mr[:, 1] * mr[:, 1]) - bn.eps
+        out, mean, var = ad.norm_rows(flat, fr, C, bn.weight, bn.bias, bn.eps, res, act, return_stats=True)
     else:
         out, mean, var = ops.norm_rows(flat, fr, C, bn.weight, bn.bias, bn.eps, residual=res, act=act, want_stats=True)
     with torch.no_grad():

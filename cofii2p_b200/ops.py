@@ -732,6 +732,12 @@ def attention_fwd_lse(q, k, v, frames: int, heads: int, scale: float):
     out = torch.empty_like(q)
     lse = torch.empty((q.shape[0], heads), dtype=torch.float32, device=q.device)
     _meta(4.0 * frames * L * S * q.shape[1], 4.0 * (2 * q.numel() + 2 * k.numel()))
+    if _engine == ENGINE_TF32 and (frames * S) % 4 == 0:  # tcgen05 flash attention (K-major V^T operand)
+        vt = transpose2d(v)
+        _meta(4.0 * frames * L * S * q.shape[1], 4.0 * (2 * q.numel() + 2 * k.numel()))
+        _call("cofi_attention_vt_lse", _p(q), _p(k), _p(vt), L, S, frames, heads, q.shape[1] // heads, float(scale), _p(out),
+              _p(lse), _st())
+        return out, lse
     _call("cofi_attention_fwd_lse", _p(q), _p(k), _p(v), L, S, frames, heads, q.shape[1] // heads, float(scale), _p(out), _p(lse),
           _st())
     return out, lse

@@ -221,6 +221,10 @@ int cofi_attention(const float* q, const float* k, const float* v, int64_t L, in
  * swapped operands (cofi_gemm(A = W_v, W = source)), so no transpose pass exists.  (frames*S) % 4 == 0. */
 int cofi_attention_vt(const float* q, const float* k, const float* vt, int64_t L, int64_t S, int frames, int heads,
                       int D, float scale, float* out, void* stream);
+/* Training forward of the same kernel: also writes lse [frames*L, heads] = log sum_s exp(scale * q.k_s), the one
+ * statistic cofi_attention_bwd needs to rebuild the probabilities. */
+int cofi_attention_vt_lse(const float* q, const float* k, const float* vt, int64_t L, int64_t S, int frames, int heads,
+                          int D, float scale, float* out, float* lse, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Matching (model/network.py:167-264, evaluation/eval_all.py:99-105)
