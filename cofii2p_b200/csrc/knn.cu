@@ -1,0 +1,592 @@
+// knn.cu -- exact KNN-k tables of the point pyramid, built on the device.
+//
+// Replaces the table builder that runs immediately before the hot path: the reference's dataset calls
+// precompute_point_cloud_stack_mode (model/kpconv/preprocess_data.py:36-107; open3d KNNSearch: true squared distance,
+// ascending, self first) and offers precompute_point_cloud_cuda (:131-203; `knn()` = expanded-form distance + topk).
+// 13 tables per frame (5 x neighbors, 4 x subsampling, 4 x upsampling), k = 128, about 1.1 G point pairs brute force.
+//
+// Design (no tensor cores: integer/selection work, ALU + L1/L2 bound):
+//   1. knn_sort_kernel: one CTA per (point set, frame).  Bounding box -> 30-bit Morton code -> bitonic sort of
+//      (code << 32 | index) keys (shared-memory chunks of 8192 keys, the few long-stride stages through L2) ->
+//      the set re-ordered as float4 (x, y, z, original index), the sorted codes, and one AABB per 32 consecutive points.
+//   2. knn_query_kernel: one warp per query, queries taken in their own Morton order so that the 8 warps of a CTA touch
+//      the same tiles.  The warp seeds its candidate list from the 4 tiles around the query's position in the source
+//      order, tightens it on the 8 tiles next to those, then sweeps all remaining tiles 32 AABBs at a time (one per
+//      lane) and opens only tiles whose box can still beat the current k-th key.  Candidates are 64-bit keys
+//      (distance bits << 32 | index): ascending key order IS the reference order (distance, then index), so the result
+//      does not depend on the visiting order, on the sort, or on the culling -- it is the exact brute-force table.
+//      Survivors are appended to a 128-entry shared-memory buffer by ballot/popc and folded into the sorted best list,
+//      which lives in registers (4 keys per lane), by a fully unrolled bitonic sort + half-cleaner + bitonic merge whose
+//      long strides are warp shuffles.
+// The culling test is exact: in COFI_KNN_DIRECT the box distance is evaluated with the same rounded operations as a
+// point distance and IEEE rounding is monotonic, so box <= every point inside, in floating point; in
+// COFI_KNN_EXPANDED (the |a|^2+|b|^2-2ab form, whose fp32 cancellation noise reaches 1e-3 m^2 at 80 m) a margin
+// bounding that noise is added.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cofi {
+namespace {
+
+constexpr int KB = 128;  // capacity of the best list and of the candidate buffer (k <= 128)
+constexpr int QWARPS = 8;
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_CHUNK = 8192;
+constexpr int MAX_SETS = 8;
+constexpr int MAX_JOBS = 16;
+constexpr unsigned long long KMAX = ~0ull;
+
+struct SetDesc {
+    const float* pts;          // [frames*n, 3]
+    unsigned long long* keys;  // [frames, P]
+    float4* sorted;            // [frames, npad]  (x, y, z, original index as int bits; pad = +inf / -1)
+    uint32_t* codes;           // [frames, npad]
+    float4* tmin;              // [frames, npad/32]  (min x, min y, min z, max |s|^2)
+    float4* tmax;              // [frames, npad/32]
+    float4* info;              // [frames]  (bbox min xyz, cells per metre)
+    int n, npad, P;
+};
+struct SortParams {
+    SetDesc set[MAX_SETS];
+};
+struct JobDesc {
+    int64_t* out;  // [frames*nq, k]
+    int src, qry, block_begin, pad;
+};
+struct QueryParams {
+    SetDesc set[MAX_SETS];
+    JobDesc job[MAX_JOBS];
+    int njobs, k, cull;
+};
+
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton_code(float x, float y, float z, const float4 info) {
+    const float fx = fminf(fmaxf((x - info.x) * info.w, 0.0f), 1023.0f);
+    const float fy = fminf(fmaxf((y - info.y) * info.w, 0.0f), 1023.0f);
+    const float fz = fminf(fmaxf((z - info.z) * info.w, 0.0f), 1023.0f);
+    return spread10((uint32_t)fx) | (spread10((uint32_t)fy) << 1) | (spread10((uint32_t)fz) << 2);
+}
+
+// ------------------------------------------------------------------------------------------------ sort
+__device__ __forceinline__ void bitonic_stage_smem(unsigned long long* sm, int len, int base, int k, int j) {
+    for (int p = threadIdx.x; p < (len >> 1); p += SORT_THREADS) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const int l = i | j;
+        const bool asc = (((base + i) & k) == 0);
+        const unsigned long long a = sm[i], b = sm[l];
+        if ((a > b) == asc) {
+            sm[i] = b;
+            sm[l] = a;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) knn_sort_kernel(const __grid_constant__ SortParams P) {
+    extern __shared__ unsigned long long sm[];  // SORT_CHUNK keys
+    __shared__ float red[6][32];
+    __shared__ float4 s_info;
+    const SetDesc& S = P.set[blockIdx.x];
+    const int frame = blockIdx.y, n = S.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* pts = S.pts + (size_t)frame * n * 3;
+
+    // bounding box of the set
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < n; i += SORT_THREADS) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = __ldg(pts + (size_t)i * 3 + a);
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if (lane == 0) {
+            red[a][warp] = mn[a];
+            red[3 + a][warp] = mx[a];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = red[a][0];
+            hi[a] = red[3 + a][0];
+            for (int w = 1; w < 32; ++w) {
+                lo[a] = fminf(lo[a], red[a][w]);
+                hi[a] = fmaxf(hi[a], red[3 + a][w]);
+            }
+        }
+        const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+        s_info = make_float4(lo[0], lo[1], lo[2], ext > 0.0f ? 1023.5f / ext : 0.0f);
+        S.info[frame] = s_info;
+    }
+    __syncthreads();
+    const float4 info = s_info;
+
+    // keys = (morton << 32 | index), padded to a power of two with KMAX
+    unsigned long long* keys = S.keys + (size_t)frame * S.P;
+    for (int i = tid; i < S.P; i += SORT_THREADS) {
+        unsigned long long key = KMAX;
+        if (i < n) {
+            const float x = __ldg(pts + (size_t)i * 3), y = __ldg(pts + (size_t)i * 3 + 1), z = __ldg(pts + (size_t)i * 3 + 2);
+            key = ((unsigned long long)morton_code(x, y, z, info) << 32) | (unsigned)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+
+    // bitonic sort: all strides below the chunk size run in shared memory
+    const int CH = S.P < SORT_CHUNK ? S.P : SORT_CHUNK;
+    for (int base = 0; base < S.P; base += CH) {
+        for (int i = tid; i < CH; i += SORT_THREADS) sm[i] = keys[base + i];
+        __syncthreads();
+        for (int k = 2; k <= CH; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                bitonic_stage_smem(sm, CH, base, k, j);
+                __syncthreads();
+            }
+        for (int i = tid; i < CH; i += SORT_THREADS) keys[base + i] = sm[i];
+        __syncthreads();
+    }
+    for (int k = CH << 1; k <= S.P; k <<= 1) {
+        for (int j = k >> 1; j >= CH; j >>= 1) {
+            for (int p = tid; p < (S.P >> 1); p += SORT_THREADS) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                const int l = i | j;
+                const bool asc = ((i & k) == 0);
+                const unsigned long long a = keys[i], b = keys[l];
+                if ((a > b) == asc) {
+                    keys[i] = b;
+                    keys[l] = a;
+                }
+            }
+            __syncthreads();
+        }
+        for (int base = 0; base < S.P; base += CH) {
+            for (int i = tid; i < CH; i += SORT_THREADS) sm[i] = keys[base + i];
+            __syncthreads();
+            for (int j = CH >> 1; j > 0; j >>= 1) {
+                bitonic_stage_smem(sm, CH, base, k, j);
+                __syncthreads();
+            }
+            for (int i = tid; i < CH; i += SORT_THREADS) keys[base + i] = sm[i];
+            __syncthreads();
+        }
+    }
+
+    // emit the re-ordered set, its codes and one box per 32 points (npad is a multiple of 32: warps stay whole)
+    float4* sorted = S.sorted + (size_t)frame * S.npad;
+    uint32_t* codes = S.codes + (size_t)frame * S.npad;
+    float4* tmin = S.tmin + (size_t)frame * (S.npad >> 5);
+    float4* tmax = S.tmax + (size_t)frame * (S.npad >> 5);
+    for (int i = tid; i < S.npad; i += SORT_THREADS) {
+        float x = INFINITY, y = INFINITY, z = INFINITY;
+        int idx = -1;
+        uint32_t code = 0xffffffffu;
+        if (i < n) {
+            const unsigned long long key = keys[i];
+            idx = (int)(unsigned)key;
+            code = (uint32_t)(key >> 32);
+            x = __ldg(pts + (size_t)idx * 3);
+            y = __ldg(pts + (size_t)idx * 3 + 1);
+            z = __ldg(pts + (size_t)idx * 3 + 2);
+        }
+        sorted[i] = make_float4(x, y, z, __int_as_float(idx));
+        codes[i] = code;
+        float lx = x, ly = y, lz = z;
+        float hx = idx >= 0 ? x : -INFINITY, hy = idx >= 0 ? y : -INFINITY, hz = idx >= 0 ? z : -INFINITY;
+        float ss = idx >= 0 ? x * x + y * y + z * z : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o));
+            ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+            lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+            hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+            hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+            hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+            ss = fmaxf(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+        }
+        if (lane == 0) {
+            tmin[i >> 5] = make_float4(lx, ly, lz, ss);
+            tmax[i >> 5] = make_float4(hx, hy, hz, 0.0f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ query
+template <int MODE>
+__device__ __forceinline__ float dist2(float qx, float qy, float qz, float qq, const float4 s) {
+    if (MODE == COFI_KNN_DIRECT) {
+        const float dx = __fsub_rn(qx, s.x), dy = __fsub_rn(qy, s.y), dz = __fsub_rn(qz, s.z);
+        return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    } else {
+        // model/kpconv/preprocess_data.py:120-129: -2 q.s, += |q|^2, += |s|^2, clamp(min=1e-12)
+        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(qx, s.x), __fmul_rn(qy, s.y)), __fmul_rn(qz, s.z));
+        const float ss = __fadd_rn(__fadd_rn(__fmul_rn(s.x, s.x), __fmul_rn(s.y, s.y)), __fmul_rn(s.z, s.z));
+        float d = __fmul_rn(-2.0f, dot);
+        d = __fadd_rn(d, qq);
+        d = __fadd_rn(d, ss);
+        return fmaxf(d, 1e-12f);
+    }
+}
+
+typedef unsigned long long u64;
+
+// 128 keys of a warp held in registers, element e = lane * 4 + r
+struct Keys4 {
+    u64 v[4];
+};
+
+// one compare-exchange stage (stride J) of the bitonic network of block size K over the 128 register-resident keys:
+// strides 1, 2 stay inside a lane, strides 4..64 are lane-xor shuffles.  Fully unrolled: no index arithmetic, no
+// shared memory.
+template <int J, int K>
+__device__ __forceinline__ void bitonic_stage_reg(Keys4& x, int lane) {
+    if constexpr (J >= 4) {
+        const bool keep_min = ((lane & (J >> 2)) == 0) == (((lane << 2) & K) == 0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const u64 p = __shfl_xor_sync(0xffffffffu, x.v[r], J >> 2);
+            x.v[r] = ((x.v[r] < p) == keep_min) ? x.v[r] : p;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if ((r & J) == 0) {
+                const bool asc = ((((lane << 2) | r) & K) == 0);
+                const u64 a = x.v[r], b = x.v[r | J];
+                const bool sw = (a > b) == asc;
+                x.v[r] = sw ? b : a;
+                x.v[r | J] = sw ? a : b;
+            }
+    }
+}
+template <int J, int K>
+__device__ __forceinline__ void bitonic_stages_reg(Keys4& x, int lane) {
+    bitonic_stage_reg<J, K>(x, lane);
+    if constexpr (J > 1) bitonic_stages_reg<J / 2, K>(x, lane);
+}
+template <int K>
+__device__ __forceinline__ void bitonic_sort_reg(Keys4& x, int lane) {
+    if constexpr (K > 2) bitonic_sort_reg<K / 2>(x, lane);
+    bitonic_stages_reg<K / 2, K>(x, lane);
+}
+
+// fold `cnt` pending candidates (shared memory) into the sorted best list (registers): sort the candidates ascending,
+// half-cleaner against the reversed candidates (the 128 smallest of both, as a bitonic sequence), bitonic merge.
+__device__ __forceinline__ Keys4 knn_merge_keys(Keys4 best, const u64* cand, int cnt, int lane) {
+    __syncwarp();
+    Keys4 c;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) c.v[r] = (lane * 4 + r) < cnt ? cand[lane * 4 + r] : KMAX;
+    bitonic_sort_reg<KB>(c, lane);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const u64 p = __shfl_sync(0xffffffffu, c.v[3 - r], 31 - lane);  // element 127 - e
+        best.v[r] = best.v[r] < p ? best.v[r] : p;
+    }
+    bitonic_stages_reg<KB / 2, KB>(best, lane);
+    __syncwarp();
+    return best;
+}
+
+struct WarpState {
+    Keys4 best;  // ascending, element e = lane * 4 + r
+    u64* cand;   // [KB] pending candidates (shared memory)
+    u64 thresh;  // current k-th key
+    int cnt, k, lane;
+};
+
+__device__ __forceinline__ u64 knn_best_at(const WarpState& w, int e) {  // e is warp-uniform
+    const int r = e & 3;
+    const u64 t = r == 0 ? w.best.v[0] : (r == 1 ? w.best.v[1] : (r == 2 ? w.best.v[2] : w.best.v[3]));
+    return __shfl_sync(0xffffffffu, t, e >> 2);
+}
+
+__device__ __forceinline__ void knn_merge(WarpState& w) {
+    w.best = knn_merge_keys(w.best, w.cand, w.cnt, w.lane);
+    w.thresh = knn_best_at(w, w.k - 1);
+    w.cnt = 0;
+}
+
+template <int MODE>
+__device__ __forceinline__ void knn_open_tile(WarpState& w, const float4* __restrict__ ssort, int t, float qx, float qy,
+                                              float qz, float qq) {
+    const float4 s = __ldg(ssort + ((size_t)t << 5) + w.lane);
+    const int si = __float_as_int(s.w);
+    const float d = dist2<MODE>(qx, qy, qz, qq, s);
+    const u64 key = ((u64)__float_as_uint(d) << 32) | (unsigned)si;
+    const bool pass = si >= 0 && key < w.thresh;
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+        if (pass) w.cand[w.cnt + __popc(m & ((1u << w.lane) - 1u))] = key;
+        w.cnt += __popc(m);
+    }
+}
+
+// squared distance from the query to the box of tile t, with the rounded operations of a point distance
+__device__ __forceinline__ float knn_box_dist(const float4* __restrict__ tmin, const float4* __restrict__ tmax, int t,
+                                              float qx, float qy, float qz, float& smax) {
+    const float4 lo = __ldg(tmin + t), hi = __ldg(tmax + t);
+    const float dx = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.0f);
+    const float dy = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.0f);
+    const float dz = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.0f);
+    smax = lo.w;
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// can a tile whose box is at squared distance d still hold a key below the current k-th key?
+template <int MODE>
+__device__ __forceinline__ bool knn_box_pass(const WarpState& w, float d, float qq, float smax) {
+    if (w.thresh == KMAX) return true;
+    const float td = __uint_as_float((unsigned)(w.thresh >> 32));
+    if (MODE == COFI_KNN_DIRECT) return d <= td;  // rounding is monotonic: box <= any point inside, exactly
+    return !(d > td + 4e-6f * (qq + smax) + 1e-12f);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(QWARPS * 32) knn_query_kernel(const __grid_constant__ QueryParams P) {
+    __shared__ unsigned long long s_cand[QWARPS][KB];
+    int j = 0;
+    while (j + 1 < P.njobs && (int)blockIdx.x >= P.job[j + 1].block_begin) ++j;
+    const JobDesc& J = P.job[j];
+    const SetDesc& S = P.set[J.src];
+    const SetDesc& Q = P.set[J.qry];
+    const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qp = ((int)blockIdx.x - J.block_begin) * QWARPS + warp;
+    if (qp >= Q.n) return;  // whole warp; no block-level barrier below
+
+    const float4 q4 = __ldg(Q.sorted + (size_t)frame * Q.npad + qp);
+    const int qi = __float_as_int(q4.w);
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
+    const float qq = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz));
+    const int ns = S.n, T = S.npad >> 5;
+    const float4* ssort = S.sorted + (size_t)frame * S.npad;
+    const float4* tmin = S.tmin + (size_t)frame * T;
+    const float4* tmax = S.tmax + (size_t)frame * T;
+
+    WarpState w;
+    w.cand = s_cand[warp];
+    w.thresh = KMAX;
+    w.cnt = 0;
+    w.k = P.k;
+    w.lane = lane;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) w.best.v[r] = KMAX;
+
+    // position of the query in the source's Morton order
+    int home = qp;
+    if (J.src != J.qry) {
+        const uint32_t code = morton_code(qx, qy, qz, __ldg(S.info + frame));
+        const uint32_t* codes = S.codes + (size_t)frame * S.npad;
+        int lo = 0, hi = ns;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(codes + mid) < code) lo = mid + 1;
+            else hi = mid;
+        }
+        home = lo;
+    }
+    const int ht = min(home >> 5, T - 1);
+    const int s0 = max(0, min(ht - 1, T - 4)), s1 = min(T, s0 + 4);
+    const int r0 = max(0, s0 - 4), r1 = min(T, s1 + 4);
+
+    // Four phases through ONE loop body (so that the unrolled merge network exists once in the code):
+    //   0  seeds: the 4 tiles around the query's position in the source order, no culling
+    //   1  the 8 tiles next to the seeds, culled against the seed threshold
+    //   2  sweep of every other tile, 32 boxes per step, restricted to the radius at which a uniform surface would hold
+    //      k points (twice the radius of the current 32nd key, i.e. 4x its squared distance): after it the k-th key is
+    //      close to final
+    //   3  second sweep: whatever else the tightened k-th key still admits
+    // Pending candidates are folded in when the buffer could overflow and at the end of every phase.
+    float near_d = INFINITY;
+    for (int phase = 0; phase < 4; ++phase) {
+        if (phase == 2 && P.cull && w.thresh != KMAX)
+            near_d = 4.0f * __uint_as_float((unsigned)(knn_best_at(w, min(31, w.k - 1)) >> 32));
+        if (phase == 3 && near_d == INFINITY) break;  // the first sweep already covered every tile
+        const int rounds = phase < 2 ? 1 : (T + 31) >> 5;
+        for (int rd = 0; rd < rounds; ++rd) {
+            int t;
+            bool ok;
+            if (phase == 0) {
+                t = s0 + lane;
+                ok = t < s1;
+            } else if (phase == 1) {
+                t = lane < 4 ? s0 - 4 + lane : s1 + lane - 4;
+                ok = lane < 8 && t >= 0 && t < T;
+            } else {
+                t = (rd << 5) + lane;
+                ok = t < T && (t < r0 || t >= r1);
+            }
+            if (ok && phase > 0 && P.cull) {
+                float smax;
+                const float d = knn_box_dist(tmin, tmax, t, qx, qy, qz, smax);
+                ok = (phase == 1 || (phase == 2 ? d <= near_d : d > near_d)) && knn_box_pass<MODE>(w, d, qq, smax);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, ok);
+            for (;;) {
+                if (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    knn_open_tile<MODE>(w, ssort, __shfl_sync(0xffffffffu, t, b), qx, qy, qz, qq);
+                }
+                if (w.cnt > KB - 32 || (m == 0 && rd == rounds - 1 && w.cnt > 0)) knn_merge(w);
+                if (m == 0) break;
+            }
+        }
+    }
+
+    int64_t* out = J.out + ((size_t)frame * Q.n + qi) * P.k;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const u64 key = w.best.v[r];
+        if (lane * 4 + r < P.k) out[lane * 4 + r] = key == KMAX ? (int64_t)ns : (int64_t)(unsigned)key;  // shadow index
+    }
+}
+
+inline int next_pow2(int64_t n) {
+    int p = 32;
+    while (p < n) p <<= 1;
+    return p;
+}
+inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
+
+int64_t set_bytes(int64_t n, int frames) {
+    const int64_t P = next_pow2(n), npad = (n + 31) / 32 * 32;
+    return align256(frames * P * 8) + align256(frames * npad * 16) + align256(frames * npad * 4) +
+           2 * align256(frames * (npad / 32) * 16) + align256((int64_t)frames * 16);
+}
+
+char* carve_set(SetDesc& S, const float* pts, int64_t n, int frames, char* w) {
+    S.pts = pts;
+    S.n = (int)n;
+    S.P = next_pow2(n);
+    S.npad = (int)((n + 31) / 32 * 32);
+    S.keys = (unsigned long long*)w;
+    w += align256((int64_t)frames * S.P * 8);
+    S.sorted = (float4*)w;
+    w += align256((int64_t)frames * S.npad * 16);
+    S.codes = (uint32_t*)w;
+    w += align256((int64_t)frames * S.npad * 4);
+    S.tmin = (float4*)w;
+    w += align256((int64_t)frames * (S.npad / 32) * 16);
+    S.tmax = (float4*)w;
+    w += align256((int64_t)frames * (S.npad / 32) * 16);
+    S.info = (float4*)w;
+    w += align256((int64_t)frames * 16);
+    return w;
+}
+
+int run(QueryParams& Q, int nsets, int frames, int mode, cudaStream_t st) {
+    static bool attr_done = false;
+    const int smem = SORT_CHUNK * 8;
+    if (!attr_done) {
+        cudaFuncSetAttribute(knn_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_done = true;
+    }
+    SortParams SP;
+    for (int s = 0; s < nsets; ++s) SP.set[s] = Q.set[s];
+    knn_sort_kernel<<<dim3(nsets, frames), SORT_THREADS, smem, st>>>(SP);
+    int rc = check_launch("cofi_knn: sort");
+    if (rc) return rc;
+    int blocks = 0;
+    for (int j = 0; j < Q.njobs; ++j) {
+        Q.job[j].block_begin = blocks;
+        blocks += (int)ceil_div(Q.set[Q.job[j].qry].n, QWARPS);
+    }
+    if ((mode & 0xff) == COFI_KNN_DIRECT)
+        knn_query_kernel<COFI_KNN_DIRECT><<<dim3(blocks, frames), QWARPS * 32, 0, st>>>(Q);
+    else
+        knn_query_kernel<COFI_KNN_EXPANDED><<<dim3(blocks, frames), QWARPS * 32, 0, st>>>(Q);
+    return check_launch("cofi_knn: query");
+}
+
+}  // namespace
+}  // namespace cofi
+
+using namespace cofi;
+
+extern "C" int64_t cofi_knn_pyramid_workspace(const int64_t* n_per_level, int levels, int frames) {
+    if (!n_per_level || levels < 1 || levels > MAX_SETS || frames < 1) return -1;
+    int64_t b = 0;
+    for (int l = 0; l < levels; ++l) b += set_bytes(n_per_level[l], frames);
+    return b;
+}
+
+extern "C" int cofi_knn_pyramid(const float* const* points, const int64_t* n_per_level, int levels, int frames, int k,
+                                int mode, int64_t* const* neighbors, int64_t* const* subsampling,
+                                int64_t* const* upsampling, void* workspace, void* stream) {
+    COFI_REQUIRE(points && n_per_level && workspace && levels >= 1 && levels <= MAX_SETS && frames >= 1 && frames <= 65535,
+                 "cofi_knn_pyramid: bad argument");
+    COFI_REQUIRE(k >= 1 && k <= KB, "cofi_knn_pyramid: k must be in 1..128");
+    COFI_REQUIRE((mode & 0xff) == COFI_KNN_DIRECT || (mode & 0xff) == COFI_KNN_EXPANDED, "cofi_knn_pyramid: bad mode");
+    QueryParams Q;
+    char* w = (char*)workspace;
+    for (int l = 0; l < levels; ++l) {
+        COFI_REQUIRE(points[l] && n_per_level[l] >= 1 && n_per_level[l] <= (1 << 20),
+                     "cofi_knn_pyramid: level %d must hold 1..2^20 points per frame", l);
+        w = carve_set(Q.set[l], points[l], n_per_level[l], frames, w);
+    }
+    Q.njobs = 0;
+    Q.k = k;
+    Q.cull = (mode & COFI_KNN_NOCULL) ? 0 : 1;
+    auto add = [&](int src, int qry, int64_t* out) {
+        if (!out) return;
+        JobDesc& J = Q.job[Q.njobs++];
+        J.src = src;
+        J.qry = qry;
+        J.out = out;
+        J.block_begin = 0;
+        J.pad = 0;
+    };
+    for (int l = 0; l < levels; ++l) {
+        if (neighbors) add(l, l, neighbors[l]);
+        if (l + 1 < levels) {
+            if (subsampling) add(l, l + 1, subsampling[l]);  // level l+1 points look up level l
+            if (upsampling) add(l + 1, l, upsampling[l]);    // level l points look up level l+1
+        }
+    }
+    if (Q.njobs == 0) return COFI_OK;
+    return run(Q, levels, frames, mode, (cudaStream_t)stream);
+}
+
+extern "C" int64_t cofi_knn_table_workspace(int64_t ns, int64_t nq, int frames) {
+    if (ns < 1 || nq < 1 || frames < 1) return -1;
+    return set_bytes(ns, frames) + set_bytes(nq, frames);
+}
+
+extern "C" int cofi_knn_table(const float* src, int64_t ns, const float* qry, int64_t nq, int frames, int k, int mode,
+                              int64_t* out, void* workspace, void* stream) {
+    COFI_REQUIRE(src && qry && out && workspace && ns >= 1 && nq >= 1 && ns <= (1 << 20) && nq <= (1 << 20) &&
+                     frames >= 1 && frames <= 65535,
+                 "cofi_knn_table: bad argument");
+    COFI_REQUIRE(k >= 1 && k <= KB, "cofi_knn_table: k must be in 1..128");
+    COFI_REQUIRE((mode & 0xff) == COFI_KNN_DIRECT || (mode & 0xff) == COFI_KNN_EXPANDED, "cofi_knn_table: bad mode");
+    QueryParams Q;
+    char* w = carve_set(Q.set[0], src, ns, frames, (char*)workspace);
+    const bool same = (src == qry && ns == nq);
+    if (!same) carve_set(Q.set[1], qry, nq, frames, w);
+    Q.njobs = 1;
+    Q.k = k;
+    Q.cull = (mode & COFI_KNN_NOCULL) ? 0 : 1;
+    Q.job[0].src = 0;
+    Q.job[0].qry = same ? 0 : 1;
+    Q.job[0].out = out;
+    Q.job[0].block_begin = 0;
+    Q.job[0].pad = 0;
+    return run(Q, same ? 1 : 2, frames, mode, (cudaStream_t)stream);
+}

@@ -535,6 +535,56 @@ def select_matches(score, best_idx, frames: int, grid_h: int, grid_w: int, thres
     return cnt, oidx, oxy
 
 
+KNN_DIRECT, KNN_EXPANDED, KNN_NOCULL = 0, 1, 0x100
+
+
+def knn_pyramid(points, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT, want=("neighbors", "subsampling", "upsampling"),
+                workspace: Optional[torch.Tensor] = None):
+    """All KNN-k tables of a point pyramid in two launches (reference model/kpconv/preprocess_data.py:75-99,172-190).
+    points: list of [frames*n_l, 3] fp32 CUDA tensors -> dict(neighbors, subsampling, upsampling) of int64 tables with
+    frame-local indices, rows ascending in (distance, index)."""
+    pts = [_f32(p, "points").contiguous() for p in points]
+    L, dev = len(pts), pts[0].device
+    n = [p.shape[0] // frames for p in pts]
+    for p, nl in zip(pts, n):
+        if p.dim() != 2 or p.shape[1] != 3 or nl * frames != p.shape[0] or nl < 1:
+            raise RuntimeError(f"knn_pyramid: every level must be [frames*n, 3], got {tuple(p.shape)} for frames={frames}")
+    n_arr = (ctypes.c_int64 * L)(*n)
+    if workspace is None:
+        workspace = _ws(_lib.cofi_knn_pyramid_workspace(n_arr, L, frames), dev)
+    out = {"neighbors": [], "subsampling": [], "upsampling": []}
+    if "neighbors" in want:
+        out["neighbors"] = [torch.empty((frames * n[l], k), dtype=torch.int64, device=dev) for l in range(L)]
+    if "subsampling" in want:
+        out["subsampling"] = [torch.empty((frames * n[l + 1], k), dtype=torch.int64, device=dev) for l in range(L - 1)]
+    if "upsampling" in want:
+        out["upsampling"] = [torch.empty((frames * n[l], k), dtype=torch.int64, device=dev) for l in range(L - 1)]
+
+    def arr(ts):
+        return (ctypes.c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts]) if ts else None
+    pairs = sum(n[l] * n[l] for l in range(L)) * ("neighbors" in want) + \
+        sum(2 * n[l] * n[l + 1] for l in range(L - 1)) * (("subsampling" in want) + ("upsampling" in want)) / 2
+    nb = sum(t.numel() * 8 for v in out.values() for t in v) + sum(p.numel() * 4 for p in pts)
+    _meta(8.0 * pairs * frames, nb)
+    _call("cofi_knn_pyramid", arr(pts), n_arr, L, frames, k, mode, arr(out["neighbors"]), arr(out["subsampling"]),
+          arr(out["upsampling"]), _p(workspace), _st())
+    return out
+
+
+def knn_table(src, qry, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT):
+    """out[frames*nq, k]: the k nearest rows of src for every row of qry (`knn(nodes, points, k)`,
+    reference model/kpconv/preprocess_data.py:131-143)."""
+    src, qry = _f32(src, "src").contiguous(), _f32(qry, "qry").contiguous()
+    ns, nq = src.shape[0] // frames, qry.shape[0] // frames
+    if src.dim() != 2 or qry.dim() != 2 or src.shape[1] != 3 or qry.shape[1] != 3 or ns < 1 or nq < 1:
+        raise RuntimeError(f"knn_table: expected [frames*n, 3] clouds, got {tuple(src.shape)} and {tuple(qry.shape)}")
+    out = torch.empty((frames * nq, k), dtype=torch.int64, device=src.device)
+    ws = _ws(_lib.cofi_knn_table_workspace(ns, nq, frames), src.device)
+    _meta(8.0 * ns * nq * frames, out.numel() * 8 + (src.numel() + qry.numel()) * 4)
+    _call("cofi_knn_table", _p(src), ns, _p(qry), nq, frames, k, mode, _p(out), _p(ws), _st())
+    return out
+
+
 def nn_argmin(points, nodes):
     points, nodes = _f32(points, "points").contiguous(), _f32(nodes, "nodes").contiguous()
     n = points.shape[0]

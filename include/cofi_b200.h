@@ -100,6 +100,39 @@ int cofi_gather_rows(const float* x, int64_t ldx, int C, const int64_t* idx, int
                      int64_t Mq, int64_t Ns, int frames, float* out, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Pyramid index tables (the step immediately before the hot path)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* distance used for ranking */
+#define COFI_KNN_DIRECT 0   /* ((dx*dx + dy*dy) + dz*dz), rounded fp32 ops, no FMA: the true squared distance open3d's
+                               KNNSearch ranks by (model/kpconv/preprocess_data.py:75-99) */
+#define COFI_KNN_EXPANDED 1 /* ((-2 q.s + |q|^2) + |s|^2) clamped at 1e-12: `knn()` / `square_distance()` of
+                               model/kpconv/preprocess_data.py:110-143 (precompute_point_cloud_cuda) */
+#define COFI_KNN_NOCULL 0x100 /* OR-ed into `mode`: open every tile (brute force; same result, test/debug only) */
+
+/* Exact k-nearest-neighbour tables of a whole point pyramid, all frames and all tables in two launches
+ * (Morton sort + warp-per-query search).  Replaces the 13 KNNSearch / knn() calls of
+ * model/kpconv/preprocess_data.py:75-99 (stack mode) and :172-190 (cuda mode).
+ *   points[l]       device [frames*n[l], 3] fp32           (host array of `levels` device pointers)
+ *   neighbors[l]    device [frames*n[l],   k] int64: level l   looks up level l     (levels entries)
+ *   subsampling[l]  device [frames*n[l+1], k] int64: level l+1 looks up level l     (levels-1 entries)
+ *   upsampling[l]   device [frames*n[l],   k] int64: level l   looks up level l+1   (levels-1 entries)
+ * Rows are ascending in (distance, index): ties go to the lower index, the query itself comes first when it is in the
+ * source set.  Indices are frame-local; when a source level has fewer than k points the tail holds n (the shadow
+ * index of model/kpconv/kpconv.py:91).  Any of the three table arrays, or any entry, may be NULL (skipped).
+ * k <= 128, levels <= 8, n[l] <= 2^20.  workspace: cofi_knn_pyramid_workspace() bytes, 256-byte aligned. */
+int64_t cofi_knn_pyramid_workspace(const int64_t* n_per_level /* host */, int levels, int frames);
+int cofi_knn_pyramid(const float* const* points /* host array */, const int64_t* n_per_level /* host */, int levels,
+                     int frames, int k, int mode, int64_t* const* neighbors, int64_t* const* subsampling,
+                     int64_t* const* upsampling, void* workspace, void* stream);
+
+/* One table: out[frames*nq, k] = the k nearest of src[frames*ns,3] for every row of qry[frames*nq,3]
+ * (`knn(nodes, points, k)`, model/kpconv/preprocess_data.py:131-143; KNNSearch()(src, qry, k), :82). */
+int64_t cofi_knn_table_workspace(int64_t ns, int64_t nq, int frames);
+int cofi_knn_table(const float* src, int64_t ns, const float* qry, int64_t nq, int frames, int k, int mode,
+                   int64_t* out, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Dense contractions
  * ------------------------------------------------------------------------------------------------- */
 

@@ -6,7 +6,7 @@ import importlib
 import sys
 
 _SUBMODULES = ("network", "imagenet", "loss", "kpconv", "kpconv.kp_backbone", "kpconv.modules", "kpconv.kpconv",
-               "kpconv.functional", "kpconv.kernel_points", "transformer", "transformer.transformer",
+               "kpconv.functional", "kpconv.kernel_points", "kpconv.preprocess_data", "transformer", "transformer.transformer",
                "transformer.position_encoding", "transformer.linear_attention")
 
 _pkg = importlib.import_module("cofii2p_b200.model")

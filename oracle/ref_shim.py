@@ -119,6 +119,46 @@ def load_reference():
     return pkg, omod.Options_KITTI
 
 
+def load_reference_preprocess():
+    """The reference's model/kpconv/preprocess_data.py (its `knn`, `square_distance`, `precompute_point_cloud_*`).
+    That module imports `open3d.ml.torch.layers` (FixedRadiusSearch, KNNSearch: native, absent here); the stub
+    KNNSearch is an exact brute-force search (fp64 direct distances, ties to the lower index) so that the reference's own
+    stack-mode driver code -- the sampling and the which-cloud-queries-which wiring -- can run unmodified."""
+    import torch
+
+    load_reference()
+    if "open3d.ml" not in sys.modules:
+        ml = types.ModuleType("open3d.ml")
+        mlt = types.ModuleType("open3d.ml.torch")
+        layers = types.ModuleType("open3d.ml.torch.layers")
+
+        class _Result:
+            def __init__(self, idx):
+                self.neighbors_index = idx
+
+        class KNNSearch:
+            def __init__(self, return_distances=False, **kw):
+                pass
+
+            def __call__(self, points, queries, k):
+                p, q = points.double(), queries.double()
+                rows = []
+                for a in range(0, q.shape[0], 1024):
+                    d = ((q[a:a + 1024, None, :] - p[None, :, :]) ** 2).sum(-1)
+                    rows.append(torch.argsort(d, dim=1, stable=True)[:, :k])
+                return _Result(torch.cat(rows, 0).reshape(-1))
+
+        class FixedRadiusSearch:
+            def __init__(self, *a, **kw):
+                raise NotImplementedError("open3d stub")
+
+        layers.KNNSearch, layers.FixedRadiusSearch = KNNSearch, FixedRadiusSearch
+        ml.torch, mlt.layers = mlt, layers
+        sys.modules["open3d"].ml = ml
+        sys.modules["open3d.ml"], sys.modules["open3d.ml.torch"], sys.modules["open3d.ml.torch.layers"] = ml, mlt, layers
+    return importlib.import_module(ALIAS + ".kpconv.preprocess_data")
+
+
 def build_reference_model(seed: int = 0):
     """Seeded reference CoFiI2P (eval mode). Construction draws from both torch and numpy RNGs
     (reference `model/kpconv/kernel_points.py:426-453` uses np.random for the per-layer kernel rotation)."""

@@ -246,3 +246,86 @@ def test_top_level_model_alias_is_the_drop_in_surface():
     assert mn.CoFiI2P is fast.CoFiI2P and hasattr(ml, "fine_circle_loss") and KPConvFPN is not None
     for name in ("fine_process", "extract_patch", "point2node", "square_distance", "CoFiI2P_wrapper"):
         assert hasattr(mn, name)
+
+
+# ---------------------------------------------------------------------------------------------- KNN table builder (row f1)
+def _knn_golden_inputs():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import make_knn_golden as mk
+    return mk.knn_case(), mk.driver_case()
+
+
+def test_knn_oracle_vs_reference_golden():
+    """oracle/knn.py against outputs of the reference's own `knn()` and stack-mode driver frozen in
+    tests/golden/knn_ref.npz (oracle/make_knn_golden.py).  Integer-lattice inputs: every distance is exact, so the
+    distance rows must be identical and indices may differ only inside groups of equal distance."""
+    from oracle import knn as ok
+    z = np.load(os.path.join(GOLD, "knn_ref.npz"))
+    (src, qry), pts = _knn_golden_inputs()
+    ref = z["knn_idx"].astype(np.int64)
+    mine = ok.knn_table(src, qry, 128, ok.EXPANDED)
+    d = ok.distances(src, qry, ok.EXPANDED)
+    dr, dm = np.take_along_axis(d, ref, 1), np.take_along_axis(d, mine, 1)
+    assert np.array_equal(dr, dm)                       # same distances in the same (ascending) order
+    strict = dm < dm[:, -1:]                            # below the k-th distance the index SETS must agree
+    for r in range(ref.shape[0]):
+        assert set(ref[r][strict[r]]) == set(mine[r][strict[r]])
+    assert (ref == mine).mean() > 0.95
+    # driver: seeded half-sampling + which level queries which (the shim's KNNSearch stand-in breaks ties like the oracle)
+    np.random.seed(7)
+    levels = ok.half_sample_pyramid(pts, 5)
+    for i, l in enumerate(levels):
+        assert np.array_equal(l, z[f"points{i}"])
+    tabs = ok.pyramid_tables(levels, 128, ok.DIRECT)
+    for name in ("neighbors", "subsampling", "upsampling"):
+        for i, t in enumerate(tabs[name]):
+            assert np.array_equal(t, z[f"{name}{i}"].astype(np.int64)), (name, i)
+    assert list(z["lengths"]) == [2048, 1024, 512, 256, 128]
+
+
+def test_knn_oracle_vs_reference_when_available():
+    from oracle.ref_shim import reference_available, load_reference_preprocess
+    if not reference_available():
+        pytest.skip("/root/reference not present (GPU box): pinned through tests/golden/knn_ref.npz instead")
+    from oracle import knn as ok
+    pp = load_reference_preprocess()
+    rng = np.random.default_rng(3)
+    src = (rng.normal(size=(1500, 3)) * 20).astype(np.float32)   # float cloud: BLAS may fuse the 3-term dot product,
+    qry = src[:200]                                              # so only near-ties may differ from the oracle
+    ref = pp.knn(torch.from_numpy(src), torch.from_numpy(qry), 128).numpy()
+    mine = ok.knn_table(src, qry, 128, ok.EXPANDED)
+    assert (ref == mine).mean() > 0.999
+    d = ok.distances(src, qry, ok.EXPANDED)
+    assert np.allclose(np.take_along_axis(d, ref, 1), np.take_along_axis(d, mine, 1), rtol=0, atol=2e-3)
+
+
+def test_knn_oracle_matches_frame_generator():
+    """The synthetic frames' tables (frames._knn_table, exact integer arithmetic) are what the oracle yields on the
+    lattice, shadow tail included."""
+    from cofii2p_b200.frames import _knn_table
+    from oracle import knn as ok
+    rng = np.random.default_rng(5)
+    lat = np.unique(rng.integers(-40, 40, (700, 3)), axis=0).astype(np.int32)
+    sub = lat[rng.permutation(lat.shape[0])[:100]]
+    for s, q, k in ((lat, lat, 128), (lat, sub, 128), (sub, lat, 128), (sub, sub, 16)):
+        a = _knn_table(torch.from_numpy(s), torch.from_numpy(q), k).numpy()
+        b = ok.knn_table(s.astype(np.float32), q.astype(np.float32), k, ok.DIRECT)
+        assert np.array_equal(a, b)
+    assert (ok.knn_table(sub.astype(np.float32), lat.astype(np.float32), 128)[:, 100:] == 100).all()
+
+
+def test_preprocess_surface_without_gpu():
+    """Drop-in names exist under `model.kpconv.preprocess_data` (reference data/kitti.py:18) and fail loudly off-GPU."""
+    import model.kpconv.preprocess_data as pp
+    for name in ("precompute_point_cloud_stack_mode", "precompute_point_cloud_cuda", "knn", "square_distance"):
+        assert callable(getattr(pp, name))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            pp.precompute_point_cloud_stack_mode(np.zeros((3, 256), np.float32), None, None, 256, 2)
+    np.random.seed(7)
+    from oracle import knn as ok
+    pts = _knn_golden_inputs()[1]
+    a = pp.half_sample(pts, 5)
+    np.random.seed(7)
+    b = ok.half_sample_pyramid(pts, 5)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))

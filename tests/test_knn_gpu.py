@@ -1,0 +1,178 @@
+"""GPU parity of the pyramid / KNN table builder (csrc/knn.cu), through the C ABI.
+
+Checker = oracle/knn.py (numpy restatement of reference model/kpconv/preprocess_data.py) at sizes it finishes in
+seconds, the frozen outputs of the reference's own `knn()` / stack-mode driver (tests/golden/knn_ref.npz), and at the
+full 20480-point size a same-arithmetic torch brute force plus size-independent properties (sorted rows, self first,
+nothing outside the row is closer than its last entry).  Index work: bit-exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def _clouds(kind, rng, n):
+    if kind == "lattice":          # exact distances, many ties
+        p = rng.integers(-50, 50, (n, 3)).astype(np.float32)
+        p[:, 1] = np.round(p[:, 1] / 8)
+    elif kind == "float":
+        p = (rng.normal(size=(n, 3)) * np.array([20, 2, 20])).astype(np.float32)
+    elif kind == "far":            # 80 m from the origin: the expanded form's cancellation noise is ~1e-3 m^2
+        p = (rng.normal(size=(n, 3)) * np.array([6, 1, 6]) + np.array([80, 1, -75])).astype(np.float32)
+    else:                          # duplicates, as the reference's sampling WITH replacement produces
+        p = (rng.normal(size=(n // 2 + 1, 3)) * 10).astype(np.float32)
+        p = p[rng.integers(0, p.shape[0], n)]
+    return p
+
+
+@pytest.mark.parametrize("kind", ["lattice", "float", "far", "dups"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_knn_table_vs_oracle(kind, mode):
+    from cofii2p_b200 import ops
+    from oracle import knn as ok
+    rng = np.random.default_rng(["lattice", "float", "far", "dups"].index(kind) * 2 + mode)
+    for ns, nq, k in ((1500, 700, 128), (333, 1000, 128), (100, 37, 128), (1, 5, 128), (4096, 300, 16), (257, 257, 1)):
+        src, qry = _clouds(kind, rng, ns), _clouds(kind, rng, nq)
+        if nq <= ns and kind != "far":
+            qry[: nq // 2] = src[rng.permutation(ns)[: nq // 2]]     # half the queries are members of the source
+        want = ok.knn_table(src, qry, k, mode)
+        for flags in (0, ops.KNN_NOCULL):
+            got = ops.knn_table(_cuda(src), _cuda(qry), 1, k, mode | flags).cpu().numpy()
+            assert np.array_equal(got, want), (kind, mode, ns, nq, k, flags, int((got != want).sum()))
+
+
+def test_knn_table_self_and_frames():
+    """src is qry (same-level job), several stacked frames with frame-local indices."""
+    from cofii2p_b200 import ops
+    from oracle import knn as ok
+    rng = np.random.default_rng(2)
+    B, n = 3, 900
+    clouds = [_clouds("lattice" if b == 0 else "float", rng, n) for b in range(B)]
+    x = _cuda(np.concatenate(clouds, 0))
+    got = ops.knn_table(x, x, B, 128, 0).cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(got[b * n:(b + 1) * n], ok.knn_table(clouds[b], clouds[b], 128, 0)), b
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_knn_pyramid_vs_oracle(mode):
+    from cofii2p_b200 import ops
+    from oracle import knn as ok
+    rng = np.random.default_rng(4)
+    B, n0, L = 2, 2000, 4
+    per_frame = []
+    for b in range(B):
+        np.random.seed(20 + b)
+        per_frame.append(ok.half_sample_pyramid(_clouds("float" if b else "lattice", rng, n0).T, L))
+    levels = [_cuda(np.concatenate([per_frame[b][l] for b in range(B)], 0)) for l in range(L)]
+    got = ops.knn_pyramid(levels, frames=B, k=128, mode=mode)
+    for b in range(B):
+        want = ok.pyramid_tables(per_frame[b], 128, mode)
+        for name in ("neighbors", "subsampling", "upsampling"):
+            for l, t in enumerate(want[name]):
+                g = got[name][l].cpu().numpy()
+                rows = t.shape[0]
+                assert np.array_equal(g[b * rows:(b + 1) * rows], t), (name, l, b)
+    # a subset of the tables only
+    part = ops.knn_pyramid(levels, frames=B, k=128, mode=mode, want=("upsampling",))
+    assert part["neighbors"] == [] and torch.equal(part["upsampling"][1], got["upsampling"][1])
+
+
+def test_knn_vs_reference_golden():
+    """Outputs of the reference's own knn() / precompute_point_cloud_stack_mode (frozen by oracle/make_knn_golden.py)."""
+    from cofii2p_b200 import ops
+    from oracle import knn as ok
+    from oracle import make_knn_golden as mk
+    import model.kpconv.preprocess_data as pp
+    z = np.load(os.path.join(GOLD, "knn_ref.npz"))
+    src, qry = mk.knn_case()
+    got = pp.knn(torch.from_numpy(src), torch.from_numpy(qry), 128).numpy()
+    ref = z["knn_idx"].astype(np.int64)
+    d = ok.distances(src, qry, ok.EXPANDED)
+    dr, dg = np.take_along_axis(d, ref, 1), np.take_along_axis(d, got, 1)
+    assert np.array_equal(dr, dg)
+    strict = dg < dg[:, -1:]
+    for r in range(ref.shape[0]):
+        assert set(ref[r][strict[r]]) == set(got[r][strict[r]])
+    # the drop-in driver, seeded like the golden run: identical pyramid and identical tables
+    np.random.seed(7)
+    out = pp.precompute_point_cloud_stack_mode(mk.driver_case(), None, None, lengths=2048, num_stages=5)
+    assert out["lengths"] == list(z["lengths"])
+    for i, p in enumerate(out["points"]):
+        assert p.is_cuda and np.array_equal(p.cpu().numpy(), z[f"points{i}"])
+    for name in ("neighbors", "subsampling", "upsampling"):
+        for i, t in enumerate(out[name]):
+            assert t.dtype == torch.int64 and np.array_equal(t.cpu().numpy(), z[f"{name}{i}"].astype(np.int64)), (name, i)
+
+
+def _torch_direct_rows(src, qry, rows):
+    """same arithmetic as COFI_KNN_DIRECT with torch elementwise ops (each rounded to fp32), sorted by (d, index)."""
+    q = qry[rows]
+    dx, dy, dz = q[:, None, 0] - src[None, :, 0], q[:, None, 1] - src[None, :, 1], q[:, None, 2] - src[None, :, 2]
+    d = (dx * dx + dy * dy) + dz * dz
+    dv, di = torch.sort(d, dim=1, stable=True)
+    return dv, di
+
+
+def test_knn_full_size_frame():
+    """20480-point synthetic KITTI frame: all 13 tables; checked against the frame generator's exact-integer tables where
+    the geometry is still on the lattice, and against a same-arithmetic torch brute force on the posed (float) clouds."""
+    from cofii2p_b200 import ops
+    from cofii2p_b200.frames import make_frame
+    from conftest import FRAME_CACHE
+    f = make_frame(3, num_pc=20480, cache_dir=FRAME_CACHE, device="cuda")
+    d = f["pc_data_dict"]
+    levels = [p.cuda() for p in d["points"]]
+    got = ops.knn_pyramid(levels, frames=1, k=128, mode=0)
+    nocull = ops.knn_pyramid(levels, frames=1, k=128, mode=ops.KNN_NOCULL)
+    g = torch.Generator().manual_seed(0)
+    for name, pairs in (("neighbors", [(l, l) for l in range(5)]), ("subsampling", [(l, l + 1) for l in range(4)]),
+                        ("upsampling", [(l + 1, l) for l in range(4)])):
+        for i, (s, q) in enumerate(pairs):
+            t = got[name][i]
+            assert torch.equal(t, nocull[name][i]), (name, i)
+            rows = torch.randperm(levels[q].shape[0], generator=g)[:256].cuda()
+            dv, di = _torch_direct_rows(levels[s], levels[q], rows)
+            assert torch.equal(t[rows], di[:, :128]), (name, i)
+            # the posed cloud is a rigid motion of the lattice: the generator's exact tables differ only inside groups of (near-)equal distance, which the lattice is full of
+            assert (t.cpu() == d[name][i]).float().mean() > 0.8, (name, i)
+    assert torch.equal(got["neighbors"][0][:, 0].cpu(), torch.arange(20480))  # self first (no duplicate points)
+
+
+def test_knn_integer_cloud_equals_frame_generator():
+    """On integer-valued coordinates the kernel reproduces frames._knn_table bit for bit, so a forward pass fed with
+    device-built tables is the forward pass of the committed goldens."""
+    from cofii2p_b200 import ops
+    from cofii2p_b200.frames import _knn_table
+    rng = np.random.default_rng(9)
+    lat = np.unique(rng.integers(-120, 120, (9000, 3)), axis=0).astype(np.int32)
+    lat[:, 1] //= 10
+    lat = np.unique(lat, axis=0)
+    rng.shuffle(lat, axis=0)
+    sub = lat[: lat.shape[0] // 2]
+    tl, ts = torch.from_numpy(lat).cuda(), torch.from_numpy(sub).cuda()
+    got = ops.knn_pyramid([tl.float(), ts.float()], frames=1, k=128, mode=0)
+    assert torch.equal(got["neighbors"][0], _knn_table(tl, tl, 128))
+    assert torch.equal(got["subsampling"][0], _knn_table(tl, ts, 128))
+    assert torch.equal(got["upsampling"][0], _knn_table(ts, tl, 128))
+
+
+def test_knn_bad_arguments():
+    from cofii2p_b200 import ops
+    x = torch.zeros((64, 3), device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.knn_table(x, x, 1, 129, 0)
+    with pytest.raises(RuntimeError):
+        ops.knn_table(x, x, 1, 16, 7)
+    with pytest.raises(RuntimeError):
+        ops.knn_table(x.cpu(), x, 1, 16, 0)
