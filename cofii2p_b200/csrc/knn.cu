@@ -6,9 +6,10 @@
 // 13 tables per frame (5 x neighbors, 4 x subsampling, 4 x upsampling), k = 128, about 1.1 G point pairs brute force.
 //
 // Design (no tensor cores: integer/selection work, ALU + L1/L2 bound):
-//   1. knn_sort_kernel: one CTA per (point set, frame).  Bounding box -> 30-bit Morton code -> bitonic sort of
-//      (code << 32 | index) keys (shared-memory chunks of 8192 keys, the few long-stride stages through L2) ->
-//      the set re-ordered as float4 (x, y, z, original index), the sorted codes, and one AABB per 32 consecutive points.
+//   1. knn_sort_chunks_kernel + knn_sort_kernel: bounding box -> 30-bit Morton code -> bitonic sort of
+//      (code << 32 | index) keys (4096-key chunks sorted by one CTA each in shared memory, then one CTA per set merges
+//      them: 8192-key shared-memory chunks, the few long-stride stages through L2) -> the set re-ordered as float4
+//      (x, y, z, original index), the sorted codes, one AABB per 32 consecutive points and one per 32 such tiles.
 //   2. knn_query_kernel: one warp per query, queries taken in their own Morton order so that the 8 warps of a CTA touch
 //      the same tiles.  The warp seeds its candidate list from the 4 tiles around the query's position in the source
 //      order, tightens it on the 8 tiles next to those, then sweeps all remaining tiles 32 AABBs at a time (one per
@@ -32,7 +33,8 @@ namespace {
 constexpr int KB = 128;  // capacity of the best list and of the candidate buffer (k <= 128)
 constexpr int QWARPS = 8;
 constexpr int SORT_THREADS = 1024;
-constexpr int SORT_CHUNK = 8192;
+constexpr int SORT_CHUNK = 8192;    // shared-memory chunk of the merge step
+constexpr int SORT_CHUNK_A = 4096;  // chunk sorted by one CTA in the first step
 constexpr int MAX_SETS = 8;
 constexpr int MAX_JOBS = 16;
 constexpr unsigned long long KMAX = ~0ull;
@@ -44,11 +46,15 @@ struct SetDesc {
     uint32_t* codes;           // [frames, npad]
     float4* tmin;              // [frames, npad/32]  (min x, min y, min z, max |s|^2)
     float4* tmax;              // [frames, npad/32]
+    float4* smin;              // [frames, nsup]  boxes of 32 consecutive tiles (1024 points), same layout
+    float4* smax;              // [frames, nsup]
     float4* info;              // [frames]  (bbox min xyz, cells per metre)
-    int n, npad, P;
+    int n, npad, P, nsup;
 };
 struct SortParams {
     SetDesc set[MAX_SETS];
+    int chunk_begin[MAX_SETS + 1];
+    int nsets;
 };
 struct JobDesc {
     int64_t* out;  // [frames*nq, k]
@@ -89,15 +95,20 @@ __device__ __forceinline__ void bitonic_stage_smem(unsigned long long* sm, int l
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) knn_sort_kernel(const __grid_constant__ SortParams P) {
-    extern __shared__ unsigned long long sm[];  // SORT_CHUNK keys
+// Step 1 of the sort, one CTA per (4096-key chunk, frame): bounding box of the whole set (recomputed by every chunk: a
+// few thousand loads), keys = (morton << 32 | index) padded with KMAX, full bitonic sort of the chunk in shared memory
+// (ascending or descending by chunk parity, as the global bitonic network wants it).
+__global__ void __launch_bounds__(SORT_THREADS) knn_sort_chunks_kernel(const __grid_constant__ SortParams P) {
+    __shared__ unsigned long long sm[SORT_CHUNK_A];
     __shared__ float red[6][32];
     __shared__ float4 s_info;
-    const SetDesc& S = P.set[blockIdx.x];
+    int si = 0;
+    while (si + 1 < P.nsets && (int)blockIdx.x >= P.chunk_begin[si + 1]) ++si;
+    const SetDesc& S = P.set[si];
+    const int chunk = blockIdx.x - P.chunk_begin[si];
     const int frame = blockIdx.y, n = S.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* pts = S.pts + (size_t)frame * n * 3;
 
-    // bounding box of the set
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = tid; i < n; i += SORT_THREADS) {
 #pragma unroll
@@ -132,37 +143,42 @@ __global__ void __launch_bounds__(SORT_THREADS) knn_sort_kernel(const __grid_con
         }
         const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
         s_info = make_float4(lo[0], lo[1], lo[2], ext > 0.0f ? 1023.5f / ext : 0.0f);
-        S.info[frame] = s_info;
+        if (chunk == 0) S.info[frame] = s_info;
     }
     __syncthreads();
     const float4 info = s_info;
 
-    // keys = (morton << 32 | index), padded to a power of two with KMAX
-    unsigned long long* keys = S.keys + (size_t)frame * S.P;
-    for (int i = tid; i < S.P; i += SORT_THREADS) {
+    const int CH = S.P < SORT_CHUNK_A ? S.P : SORT_CHUNK_A, base = chunk * CH;
+    for (int i = tid; i < CH; i += SORT_THREADS) {
         unsigned long long key = KMAX;
-        if (i < n) {
-            const float x = __ldg(pts + (size_t)i * 3), y = __ldg(pts + (size_t)i * 3 + 1), z = __ldg(pts + (size_t)i * 3 + 2);
-            key = ((unsigned long long)morton_code(x, y, z, info) << 32) | (unsigned)i;
+        const int g = base + i;
+        if (g < n) {
+            const float x = __ldg(pts + (size_t)g * 3), y = __ldg(pts + (size_t)g * 3 + 1), z = __ldg(pts + (size_t)g * 3 + 2);
+            key = ((unsigned long long)morton_code(x, y, z, info) << 32) | (unsigned)g;
         }
-        keys[i] = key;
+        sm[i] = key;
     }
     __syncthreads();
+    for (int k = 2; k <= CH; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            bitonic_stage_smem(sm, CH, base, k, j);
+            __syncthreads();
+        }
+    unsigned long long* keys = S.keys + (size_t)frame * S.P;
+    for (int i = tid; i < CH; i += SORT_THREADS) keys[base + i] = sm[i];
+}
 
-    // bitonic sort: all strides below the chunk size run in shared memory
+// Step 2, one CTA per (set, frame): the remaining bitonic merge levels (strides >= 8192 through L2, the rest in
+// 8192-key shared-memory chunks), then the re-ordered set, its codes and the tile / group boxes.
+__global__ void __launch_bounds__(SORT_THREADS) knn_sort_kernel(const __grid_constant__ SortParams P) {
+    extern __shared__ unsigned long long sm[];  // SORT_CHUNK keys
+    const SetDesc& S = P.set[blockIdx.x];
+    const int frame = blockIdx.y, n = S.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* pts = S.pts + (size_t)frame * n * 3;
+    unsigned long long* keys = S.keys + (size_t)frame * S.P;
+
     const int CH = S.P < SORT_CHUNK ? S.P : SORT_CHUNK;
-    for (int base = 0; base < S.P; base += CH) {
-        for (int i = tid; i < CH; i += SORT_THREADS) sm[i] = keys[base + i];
-        __syncthreads();
-        for (int k = 2; k <= CH; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                bitonic_stage_smem(sm, CH, base, k, j);
-                __syncthreads();
-            }
-        for (int i = tid; i < CH; i += SORT_THREADS) keys[base + i] = sm[i];
-        __syncthreads();
-    }
-    for (int k = CH << 1; k <= S.P; k <<= 1) {
+    for (int k = SORT_CHUNK_A << 1; k <= S.P; k <<= 1) {
         for (int j = k >> 1; j >= CH; j >>= 1) {
             for (int p = tid; p < (S.P >> 1); p += SORT_THREADS) {
                 const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
@@ -179,7 +195,7 @@ __global__ void __launch_bounds__(SORT_THREADS) knn_sort_kernel(const __grid_con
         for (int base = 0; base < S.P; base += CH) {
             for (int i = tid; i < CH; i += SORT_THREADS) sm[i] = keys[base + i];
             __syncthreads();
-            for (int j = CH >> 1; j > 0; j >>= 1) {
+            for (int j = (k >> 1) < (CH >> 1) ? (k >> 1) : (CH >> 1); j > 0; j >>= 1) {
                 bitonic_stage_smem(sm, CH, base, k, j);
                 __syncthreads();
             }
@@ -223,6 +239,31 @@ __global__ void __launch_bounds__(SORT_THREADS) knn_sort_kernel(const __grid_con
         if (lane == 0) {
             tmin[i >> 5] = make_float4(lx, ly, lz, ss);
             tmax[i >> 5] = make_float4(hx, hy, hz, 0.0f);
+        }
+    }
+    __syncthreads();
+    // boxes of 32 consecutive tiles: the sweep tests these first and skips whole groups
+    const int T = S.npad >> 5;
+    for (int g = warp; g < S.nsup; g += SORT_THREADS / 32) {
+        const int t = (g << 5) + lane;
+        float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
+        if (t < T) {
+            lo = tmin[t];
+            hi = tmax[t];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
+            lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+            lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+            lo.w = fmaxf(lo.w, __shfl_xor_sync(0xffffffffu, lo.w, o));
+            hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+            hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+            hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+        }
+        if (lane == 0) {
+            S.smin[(size_t)frame * S.nsup + g] = lo;
+            S.smax[(size_t)frame * S.nsup + g] = hi;
         }
     }
 }
@@ -405,49 +446,62 @@ __global__ void __launch_bounds__(QWARPS * 32) knn_query_kernel(const __grid_con
     const int s0 = max(0, min(ht - 1, T - 4)), s1 = min(T, s0 + 4);
     const int r0 = max(0, s0 - 4), r1 = min(T, s1 + 4);
 
-    // Four phases through ONE loop body (so that the unrolled merge network exists once in the code):
+    // Four phases through one loop body (the unrolled merge network exists twice in the code: overflow and phase end):
     //   0  seeds: the 4 tiles around the query's position in the source order, no culling
     //   1  the 8 tiles next to the seeds, culled against the seed threshold
-    //   2  sweep of every other tile, 32 boxes per step, restricted to the radius at which a uniform surface would hold
+    //   2  sweep of every other tile -- first the boxes of 32-tile groups, one per lane, then 32 tile boxes per step inside
+    //      the groups that pass -- restricted to the radius at which a uniform surface would hold
     //      k points (twice the radius of the current 32nd key, i.e. 4x its squared distance): after it the k-th key is
     //      close to final
     //   3  second sweep: whatever else the tightened k-th key still admits
     // Pending candidates are folded in when the buffer could overflow and at the end of every phase.
+    const float4* gmin = S.smin + (size_t)frame * S.nsup;
+    const float4* gmax = S.smax + (size_t)frame * S.nsup;
     float near_d = INFINITY;
     for (int phase = 0; phase < 4; ++phase) {
         if (phase == 2 && P.cull && w.thresh != KMAX)
             near_d = 4.0f * __uint_as_float((unsigned)(knn_best_at(w, min(31, w.k - 1)) >> 32));
         if (phase == 3 && near_d == INFINITY) break;  // the first sweep already covered every tile
-        const int rounds = phase < 2 ? 1 : (T + 31) >> 5;
-        for (int rd = 0; rd < rounds; ++rd) {
-            int t;
-            bool ok;
-            if (phase == 0) {
-                t = s0 + lane;
-                ok = t < s1;
-            } else if (phase == 1) {
-                t = lane < 4 ? s0 - 4 + lane : s1 + lane - 4;
-                ok = lane < 8 && t >= 0 && t < T;
-            } else {
-                t = (rd << 5) + lane;
-                ok = t < T && (t < r0 || t >= r1);
-            }
-            if (ok && phase > 0 && P.cull) {
+        const int rounds = phase < 2 ? 1 : S.nsup;
+        for (int gb = 0; gb < rounds; gb += 32) {
+            // which groups of 32 tiles can matter at all (one group box per lane)
+            bool gok = gb + lane < rounds;
+            if (gok && phase >= 2 && P.cull) {
                 float smax;
-                const float d = knn_box_dist(tmin, tmax, t, qx, qy, qz, smax);
-                ok = (phase == 1 || (phase == 2 ? d <= near_d : d > near_d)) && knn_box_pass<MODE>(w, d, qq, smax);
+                const float d = knn_box_dist(gmin, gmax, gb + lane, qx, qy, qz, smax);
+                gok = (phase == 3 || d <= near_d) && knn_box_pass<MODE>(w, d, qq, smax);
             }
-            unsigned m = __ballot_sync(0xffffffffu, ok);
-            for (;;) {
-                if (m) {
+            unsigned gm = __ballot_sync(0xffffffffu, gok);
+            while (gm) {
+                const int rd = gb + __ffs(gm) - 1;
+                gm &= gm - 1;
+                int t;
+                bool ok;
+                if (phase == 0) {
+                    t = s0 + lane;
+                    ok = t < s1;
+                } else if (phase == 1) {
+                    t = lane < 4 ? s0 - 4 + lane : s1 + lane - 4;
+                    ok = lane < 8 && t >= 0 && t < T;
+                } else {
+                    t = (rd << 5) + lane;
+                    ok = t < T && (t < r0 || t >= r1);
+                }
+                if (ok && phase > 0 && P.cull) {
+                    float smax;
+                    const float d = knn_box_dist(tmin, tmax, t, qx, qy, qz, smax);
+                    ok = (phase == 1 || (phase == 2 ? d <= near_d : d > near_d)) && knn_box_pass<MODE>(w, d, qq, smax);
+                }
+                unsigned m = __ballot_sync(0xffffffffu, ok);
+                while (m) {
                     const int b = __ffs(m) - 1;
                     m &= m - 1;
                     knn_open_tile<MODE>(w, ssort, __shfl_sync(0xffffffffu, t, b), qx, qy, qz, qq);
+                    if (w.cnt > KB - 32) knn_merge(w);
                 }
-                if (w.cnt > KB - 32 || (m == 0 && rd == rounds - 1 && w.cnt > 0)) knn_merge(w);
-                if (m == 0) break;
             }
         }
+        if (w.cnt) knn_merge(w);
     }
 
     int64_t* out = J.out + ((size_t)frame * Q.n + qi) * P.k;
@@ -467,8 +521,9 @@ inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
 
 int64_t set_bytes(int64_t n, int frames) {
     const int64_t P = next_pow2(n), npad = (n + 31) / 32 * 32;
+    const int64_t nsup = (npad / 32 + 31) / 32;
     return align256(frames * P * 8) + align256(frames * npad * 16) + align256(frames * npad * 4) +
-           2 * align256(frames * (npad / 32) * 16) + align256((int64_t)frames * 16);
+           2 * align256(frames * (npad / 32) * 16) + 2 * align256(frames * nsup * 16) + align256((int64_t)frames * 16);
 }
 
 char* carve_set(SetDesc& S, const float* pts, int64_t n, int frames, char* w) {
@@ -486,6 +541,11 @@ char* carve_set(SetDesc& S, const float* pts, int64_t n, int frames, char* w) {
     w += align256((int64_t)frames * (S.npad / 32) * 16);
     S.tmax = (float4*)w;
     w += align256((int64_t)frames * (S.npad / 32) * 16);
+    S.nsup = (S.npad / 32 + 31) / 32;
+    S.smin = (float4*)w;
+    w += align256((int64_t)frames * S.nsup * 16);
+    S.smax = (float4*)w;
+    w += align256((int64_t)frames * S.nsup * 16);
     S.info = (float4*)w;
     w += align256((int64_t)frames * 16);
     return w;
@@ -499,9 +559,19 @@ int run(QueryParams& Q, int nsets, int frames, int mode, cudaStream_t st) {
         attr_done = true;
     }
     SortParams SP;
-    for (int s = 0; s < nsets; ++s) SP.set[s] = Q.set[s];
+    SP.nsets = nsets;
+    int chunks = 0;
+    for (int s = 0; s < nsets; ++s) {
+        SP.set[s] = Q.set[s];
+        SP.chunk_begin[s] = chunks;
+        chunks += Q.set[s].P <= SORT_CHUNK_A ? 1 : Q.set[s].P / SORT_CHUNK_A;
+    }
+    SP.chunk_begin[nsets] = chunks;
+    knn_sort_chunks_kernel<<<dim3(chunks, frames), SORT_THREADS, 0, st>>>(SP);
+    int rc = check_launch("cofi_knn: chunk sort");
+    if (rc) return rc;
     knn_sort_kernel<<<dim3(nsets, frames), SORT_THREADS, smem, st>>>(SP);
-    int rc = check_launch("cofi_knn: sort");
+    rc = check_launch("cofi_knn: sort");
     if (rc) return rc;
     int blocks = 0;
     for (int j = 0; j < Q.njobs; ++j) {
