@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--engine", default=os.environ.get("COFI_ENGINE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-from-points", action="store_true", help="skip the leg that builds the KNN tables on the device")
     ap.add_argument("--cpu-frames", type=int, default=2, help="timed frames of the CPU baseline sample")
     return ap.parse_args()
 
@@ -238,6 +239,20 @@ def run_cofi(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def timed_on(st, fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(st):
+            e0.record(st)
+            for _ in range(steps):
+                fn()
+            e1.record(st)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
     # ---- device-resident throughput (inputs already in HBM) -------------------------------------------
     for _ in range(max(args.warmup, 3)):
         eng.run()
@@ -273,6 +288,43 @@ def run_cofi(args):
     ms_e2e = float(ms_e2e_t.item())
     e2e_value = frames_total / (ms_e2e / 1000.0)
     pipe.last_results()  # validates the err flag / keeps the API honest
+    del pipe
+
+    # ---- the same pipeline fed with the point pyramid only: the 13 KNN-128 tables are built on the device inside the
+    # graph (csrc/knn.cu) instead of being computed on the host and shipped over PCIe -------
+    from_points = None
+    if not args.no_from_points:
+        eng_p = InferenceEngine(model, batch, mode="val", use_graph=not args.no_graph, tables="device")
+        for _ in range(3):
+            eng_p.run()
+        ms_p = timed_on(eng_p.stream, eng_p.run, args.steps)
+        lp = eng_p.launches_per_step
+        del eng_p
+        pipe = PipelinedEngine(model, batch, depth=2, tables="device")
+        hosts_p = [pipe.engines[0].host_buffers(batch), pipe.engines[0].host_buffers(batch)]
+        for i in range(3):
+            pipe.step(hosts_p[i % 2])
+        pipe.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(pipe.h2d)
+        for i in range(args.steps):
+            pin, pout = pipe.step(hosts_p[i % 2])
+        pipe.compute.wait_stream(pipe.h2d)
+        pipe.d2h.wait_stream(pipe.compute)
+        e1.record(pipe.d2h)
+        pipe.synchronize()
+        barrier()
+        ms_pe = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms_pe, op=dist.ReduceOp.MAX)
+        from_points = {"value": frames_total / (ms_p / 1000.0), "e2e": frames_total / (float(ms_pe.item()) / 1000.0),
+                       "unit": UNIT, "h2d_bytes_per_step": pin, "d2h_bytes_per_step": pout, "launches_per_step": lp,
+                       "what": "same forward, inputs = point pyramid + image only; the KNN-128 index tables (neighbors, "
+                               "subsampling: 128 columns; upsampling: its single live column) are built by cofi_knn_pyramid "
+                               "inside the captured graph"}
+        pipe.last_results()
+        del pipe
 
     # ---- roofline of the dominant kernel family: eager pass bracketed by CUDA events per launch --------
     hbm, tf_burst, tf_sust, peaks_src = measured_peaks()
@@ -336,6 +388,8 @@ def run_cofi(args):
         "launches_per_step": eng.launches_per_step,
         "roofline": roof,
     }
+    if from_points is not None:
+        line["from_points"] = from_points
     if world == 1 and not args.no_cpu_baseline:
         cpu_sd = {k: v.detach().cpu() for k, v in sd.items()}
         cores, cands = pick_cpu_threads(cpu_sd)

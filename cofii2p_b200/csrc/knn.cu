@@ -58,12 +58,12 @@ struct SortParams {
 };
 struct JobDesc {
     int64_t* out;  // [frames*nq, k]
-    int src, qry, block_begin, pad;
+    int src, qry, block_begin, k;
 };
 struct QueryParams {
     SetDesc set[MAX_SETS];
     JobDesc job[MAX_JOBS];
-    int njobs, k, cull;
+    int njobs, cull;
 };
 
 __device__ __forceinline__ uint32_t spread10(uint32_t v) {
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(QWARPS * 32) knn_query_kernel(const __grid_con
     w.cand = s_cand[warp];
     w.thresh = KMAX;
     w.cnt = 0;
-    w.k = P.k;
+    w.k = J.k;
     w.lane = lane;
 #pragma unroll
     for (int r = 0; r < 4; ++r) w.best.v[r] = KMAX;
@@ -504,11 +504,11 @@ __global__ void __launch_bounds__(QWARPS * 32) knn_query_kernel(const __grid_con
         if (w.cnt) knn_merge(w);
     }
 
-    int64_t* out = J.out + ((size_t)frame * Q.n + qi) * P.k;
+    int64_t* out = J.out + ((size_t)frame * Q.n + qi) * J.k;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const u64 key = w.best.v[r];
-        if (lane * 4 + r < P.k) out[lane * 4 + r] = key == KMAX ? (int64_t)ns : (int64_t)(unsigned)key;  // shadow index
+        if (lane * 4 + r < J.k) out[lane * 4 + r] = key == KMAX ? (int64_t)ns : (int64_t)(unsigned)key;  // shadow index
     }
 }
 
@@ -598,11 +598,11 @@ extern "C" int64_t cofi_knn_pyramid_workspace(const int64_t* n_per_level, int le
 }
 
 extern "C" int cofi_knn_pyramid(const float* const* points, const int64_t* n_per_level, int levels, int frames, int k,
-                                int mode, int64_t* const* neighbors, int64_t* const* subsampling,
+                                int k_up, int mode, int64_t* const* neighbors, int64_t* const* subsampling,
                                 int64_t* const* upsampling, void* workspace, void* stream) {
     COFI_REQUIRE(points && n_per_level && workspace && levels >= 1 && levels <= MAX_SETS && frames >= 1 && frames <= 65535,
                  "cofi_knn_pyramid: bad argument");
-    COFI_REQUIRE(k >= 1 && k <= KB, "cofi_knn_pyramid: k must be in 1..128");
+    COFI_REQUIRE(k >= 1 && k <= KB && k_up >= 1 && k_up <= KB, "cofi_knn_pyramid: k and k_up must be in 1..128");
     COFI_REQUIRE((mode & 0xff) == COFI_KNN_DIRECT || (mode & 0xff) == COFI_KNN_EXPANDED, "cofi_knn_pyramid: bad mode");
     QueryParams Q;
     char* w = (char*)workspace;
@@ -612,22 +612,21 @@ extern "C" int cofi_knn_pyramid(const float* const* points, const int64_t* n_per
         w = carve_set(Q.set[l], points[l], n_per_level[l], frames, w);
     }
     Q.njobs = 0;
-    Q.k = k;
     Q.cull = (mode & COFI_KNN_NOCULL) ? 0 : 1;
-    auto add = [&](int src, int qry, int64_t* out) {
+    auto add = [&](int src, int qry, int64_t* out, int kk) {
         if (!out) return;
         JobDesc& J = Q.job[Q.njobs++];
         J.src = src;
         J.qry = qry;
         J.out = out;
         J.block_begin = 0;
-        J.pad = 0;
+        J.k = kk;
     };
     for (int l = 0; l < levels; ++l) {
-        if (neighbors) add(l, l, neighbors[l]);
+        if (neighbors) add(l, l, neighbors[l], k);
         if (l + 1 < levels) {
-            if (subsampling) add(l, l + 1, subsampling[l]);  // level l+1 points look up level l
-            if (upsampling) add(l + 1, l, upsampling[l]);    // level l points look up level l+1
+            if (subsampling) add(l, l + 1, subsampling[l], k);  // level l+1 points look up level l
+            if (upsampling) add(l + 1, l, upsampling[l], k_up);  // level l points look up level l+1
         }
     }
     if (Q.njobs == 0) return COFI_OK;
@@ -651,12 +650,11 @@ extern "C" int cofi_knn_table(const float* src, int64_t ns, const float* qry, in
     const bool same = (src == qry && ns == nq);
     if (!same) carve_set(Q.set[1], qry, nq, frames, w);
     Q.njobs = 1;
-    Q.k = k;
     Q.cull = (mode & COFI_KNN_NOCULL) ? 0 : 1;
     Q.job[0].src = 0;
     Q.job[0].qry = same ? 0 : 1;
     Q.job[0].out = out;
     Q.job[0].block_begin = 0;
-    Q.job[0].pad = 0;
+    Q.job[0].k = k;
     return run(Q, same ? 1 : 2, frames, mode, (cudaStream_t)stream);
 }

@@ -22,11 +22,15 @@ def _pin(t: torch.Tensor) -> torch.Tensor:
 
 
 class InferenceEngine:
-    def __init__(self, model, batch: Dict, mode: str = "val", use_graph: bool = True, stream=None):
+    def __init__(self, model, batch: Dict, mode: str = "val", use_graph: bool = True, stream=None, tables: str = "host"):
         """`batch`: output of frames.stack_frames (CPU or CUDA tensors) that fixes all shapes.
-        `stream`: compute stream shared by several engines (PipelinedEngine)."""
+        `stream`: compute stream shared by several engines (PipelinedEngine).
+        `tables`: "host" = the KNN index tables arrive with the batch, as the reference's data loader supplies them;
+        "device" = only the point pyramid arrives and the tables are built inside the captured graph by
+        ops.knn_pyramid (csrc/knn.cu; neighbours/subsampling k columns, upsampling its single live column)."""
         assert mode == "val", "the graph covers the static-shape val/train-style forward; test mode adds an eager tail"
-        self.model, self.mode, self.B = model, mode, batch["frames"]
+        assert tables in ("host", "device")
+        self.model, self.mode, self.B, self.tables = model, mode, batch["frames"], tables
         dev = next(model.parameters()).device
         self.device = dev
         d = batch["pc_data_dict"]
@@ -38,6 +42,11 @@ class InferenceEngine:
             "feats": d["feats"].to(dev).contiguous(),
             "lengths": d["lengths"],
         }
+        self.knn_k = int(d["neighbors"][0].shape[1])
+        if tables == "device":
+            n = [p.shape[0] // self.B for p in self.inp["points"]]
+            import ctypes
+            self.knn_ws = ops._ws(_libmod.load().cofi_knn_pyramid_workspace((ctypes.c_int64 * len(n))(*n), len(n), self.B), dev)
         self.img = batch["img"].to(dev).contiguous()
         self.kpt = torch.stack([k.to(torch.float32) for k in batch["fine_center_kpt_coors"]]).to(dev).contiguous()
         self.inline = torch.stack([k.to(torch.int64) for k in batch["fine_pc_inline_index"]]).to(dev).contiguous()
@@ -66,6 +75,8 @@ class InferenceEngine:
     # one forward over the static buffers; fills self.out
     def _step_eager(self):
         m, B = self.model, self.B
+        if self.tables == "device":
+            self.inp.update(ops.knn_pyramid(self.inp["points"], frames=B, k=self.knn_k, k_up=1, workspace=self.knn_ws))
         core = m.core(self.inp, self.img, B)
         n1 = core["pc_decode_3"].shape[0] // B
         hw = m.pe_H * m.pe_W
@@ -99,9 +110,12 @@ class InferenceEngine:
     def host_buffers(self, batch: Dict):
         """Pinned host copies of a batch (what a data loader would hand over)."""
         d = batch["pc_data_dict"]
+        dev_tables = self.tables == "device"
         return {
-            "points": [_pin(t) for t in d["points"]], "neighbors": [_pin(t) for t in d["neighbors"]],
-            "subsampling": [_pin(t) for t in d["subsampling"]], "upsampling": [_pin(t[:, :1]) for t in d["upsampling"]],
+            "points": [_pin(t) for t in d["points"]],
+            "neighbors": [] if dev_tables else [_pin(t) for t in d["neighbors"]],
+            "subsampling": [] if dev_tables else [_pin(t) for t in d["subsampling"]],
+            "upsampling": [] if dev_tables else [_pin(t[:, :1]) for t in d["upsampling"]],
             "feats": _pin(d["feats"]), "img": _pin(batch["img"]),
             "kpt": _pin(torch.stack([k.to(torch.float32) for k in batch["fine_center_kpt_coors"]])),
             "inline": _pin(torch.stack([k.to(torch.int64) for k in batch["fine_pc_inline_index"]])),
@@ -152,12 +166,12 @@ class PipelinedEngine:
     lands in buffer set (i+1)%2 on a copy stream and the D2H of batch i-1 drains on a third stream (PCIe is full
     duplex).  Steady-state step time = max(H2D, compute, D2H) instead of their sum."""
 
-    def __init__(self, model, batch: Dict, depth: int = 2):
+    def __init__(self, model, batch: Dict, depth: int = 2, tables: str = "host"):
         dev = next(model.parameters()).device
         self.compute = torch.cuda.Stream(device=dev)
         self.h2d = torch.cuda.Stream(device=dev)
         self.d2h = torch.cuda.Stream(device=dev)
-        self.engines = [InferenceEngine(model, batch, use_graph=True, stream=self.compute) for _ in range(depth)]
+        self.engines = [InferenceEngine(model, batch, use_graph=True, stream=self.compute, tables=tables) for _ in range(depth)]
         self.uploaded = [torch.cuda.Event() for _ in range(depth)]
         self.computed = [torch.cuda.Event() for _ in range(depth)]
         self.drained = [torch.cuda.Event() for _ in range(depth)]

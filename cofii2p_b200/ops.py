@@ -539,10 +539,12 @@ KNN_DIRECT, KNN_EXPANDED, KNN_NOCULL = 0, 1, 0x100
 
 
 def knn_pyramid(points, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT, want=("neighbors", "subsampling", "upsampling"),
-                workspace: Optional[torch.Tensor] = None):
+                workspace: Optional[torch.Tensor] = None, k_up: Optional[int] = None):
     """All KNN-k tables of a point pyramid in two launches (reference model/kpconv/preprocess_data.py:75-99,172-190).
     points: list of [frames*n_l, 3] fp32 CUDA tensors -> dict(neighbors, subsampling, upsampling) of int64 tables with
-    frame-local indices, rows ascending in (distance, index)."""
+    frame-local indices, rows ascending in (distance, index).  k_up: columns of the upsampling tables (default k; the
+    model only reads column 0, reference model/kpconv/functional.py:20, so the engine asks for 1)."""
+    k_up = k if k_up is None else k_up
     pts = [_f32(p, "points").contiguous() for p in points]
     L, dev = len(pts), pts[0].device
     n = [p.shape[0] // frames for p in pts]
@@ -558,7 +560,7 @@ def knn_pyramid(points, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT, w
     if "subsampling" in want:
         out["subsampling"] = [torch.empty((frames * n[l + 1], k), dtype=torch.int64, device=dev) for l in range(L - 1)]
     if "upsampling" in want:
-        out["upsampling"] = [torch.empty((frames * n[l], k), dtype=torch.int64, device=dev) for l in range(L - 1)]
+        out["upsampling"] = [torch.empty((frames * n[l], k_up), dtype=torch.int64, device=dev) for l in range(L - 1)]
 
     def arr(ts):
         return (ctypes.c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts]) if ts else None
@@ -566,7 +568,7 @@ def knn_pyramid(points, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT, w
         sum(2 * n[l] * n[l + 1] for l in range(L - 1)) * (("subsampling" in want) + ("upsampling" in want)) / 2
     nb = sum(t.numel() * 8 for v in out.values() for t in v) + sum(p.numel() * 4 for p in pts)
     _meta(8.0 * pairs * frames, nb)
-    _call("cofi_knn_pyramid", arr(pts), n_arr, L, frames, k, mode, arr(out["neighbors"]), arr(out["subsampling"]),
+    _call("cofi_knn_pyramid", arr(pts), n_arr, L, frames, k, k_up, mode, arr(out["neighbors"]), arr(out["subsampling"]),
           arr(out["upsampling"]), _p(workspace), _st())
     return out
 

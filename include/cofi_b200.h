@@ -116,15 +116,17 @@ int cofi_gather_rows(const float* x, int64_t ldx, int C, const int64_t* idx, int
  *   points[l]       device [frames*n[l], 3] fp32           (host array of `levels` device pointers)
  *   neighbors[l]    device [frames*n[l],   k] int64: level l   looks up level l     (levels entries)
  *   subsampling[l]  device [frames*n[l+1], k] int64: level l+1 looks up level l     (levels-1 entries)
- *   upsampling[l]   device [frames*n[l],   k] int64: level l   looks up level l+1   (levels-1 entries)
+ *   upsampling[l]   device [frames*n[l], k_up] int64: level l looks up level l+1   (levels-1 entries)
  * Rows are ascending in (distance, index): ties go to the lower index, the query itself comes first when it is in the
  * source set.  Indices are frame-local; when a source level has fewer than k points the tail holds n (the shadow
  * index of model/kpconv/kpconv.py:91).  Any of the three table arrays, or any entry, may be NULL (skipped).
  * k <= 128, levels <= 8, n[l] <= 2^20.  workspace: cofi_knn_pyramid_workspace() bytes, 256-byte aligned. */
 int64_t cofi_knn_pyramid_workspace(const int64_t* n_per_level /* host */, int levels, int frames);
 int cofi_knn_pyramid(const float* const* points /* host array */, const int64_t* n_per_level /* host */, int levels,
-                     int frames, int k, int mode, int64_t* const* neighbors, int64_t* const* subsampling,
-                     int64_t* const* upsampling, void* workspace, void* stream);
+                     int frames, int k, int k_up /* columns of the upsampling tables: the model reads only column 0
+                     (model/kpconv/functional.py:20), k_up = 1 builds just that; k_up = k gives the reference's tables */,
+                     int mode, int64_t* const* neighbors, int64_t* const* subsampling, int64_t* const* upsampling,
+                     void* workspace, void* stream);
 
 /* One table: out[frames*nq, k] = the k nearest of src[frames*ns,3] for every row of qry[frames*nq,3]
  * (`knn(nodes, points, k)`, model/kpconv/preprocess_data.py:131-143; KNNSearch()(src, qry, k), :82). */

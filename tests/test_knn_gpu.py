@@ -176,3 +176,35 @@ def test_knn_bad_arguments():
         ops.knn_table(x, x, 1, 16, 7)
     with pytest.raises(RuntimeError):
         ops.knn_table(x.cpu(), x, 1, 16, 0)
+
+
+def test_engine_builds_tables_on_device():
+    """InferenceEngine(tables='device'): the captured graph starts from the point pyramid alone and equals the engine that
+    is handed the same tables."""
+    from cofii2p_b200 import ops
+    from cofii2p_b200.engine import InferenceEngine
+    from cofii2p_b200.frames import make_frame, stack_frames
+    from cofii2p_b200.model.network import CoFiI2P
+    from cofii2p_b200.options import Options_KITTI
+    from cofii2p_b200.weights import seeded_state_dict
+    from conftest import FRAME_CACHE
+    m = CoFiI2P(Options_KITTI())
+    m.load_state_dict(seeded_state_dict(m, 0), strict=True)
+    m = m.cuda().eval()
+    ops.set_engine("fp32")
+    frames = [make_frame(s, num_pc=4096, cache_dir=FRAME_CACHE, device="cuda") for s in (0, 1)]
+    batch = stack_frames(frames)
+    pts = [p.cuda() for p in batch["pc_data_dict"]["points"]]
+    tabs = ops.knn_pyramid(pts, frames=2, k=128)
+    for name in ("neighbors", "subsampling", "upsampling"):
+        batch["pc_data_dict"][name] = tabs[name]
+    a = InferenceEngine(m, batch, tables="host")
+    b = InferenceEngine(m, batch, tables="device")
+    assert b.launches_per_step == a.launches_per_step + 3
+    for e in (a, b):
+        e.run()
+    for ra, rb in zip(a.results(), b.results()):
+        for x, y in zip(ra[:6], rb[:6]):
+            assert torch.equal(x, y)
+    hb = b.host_buffers(batch)
+    assert hb["neighbors"] == [] and b.upload(hb) < 2 * (4096 * 2 * 3 * 4 + 4096 * 16 + 3 * 160 * 512 * 4) + 4096
