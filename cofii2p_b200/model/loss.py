@@ -41,7 +41,7 @@ def fine_circle_loss(device, fine_img_feature, fine_pc_feature, relative_index, 
     sim = torch.cosine_similarity(patch.unsqueeze(-1), fine_pc_feature.unsqueeze(-1).unsqueeze(-2))
     sim = torch.squeeze(sim)
     pos = torch.zeros(num_kpt, 16, device=sim.device)
-    pos[torch.arange(num_kpt, device=sim.device), relative_index] = 1
+    pos.scatter_(1, relative_index.view(-1, 1), 1.0)   # pos[arange, relative_index] = 1 without a host-side scalar copy
     neg = 1 - pos
     sp, sn = sim * pos, sim * neg
     ap = torch.relu(-sp.detach() + pos + pos * m)

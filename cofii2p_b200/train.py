@@ -62,6 +62,8 @@ class TrainStep:
         self.step_count = 0
         self.live: Optional[List[torch.nn.Parameter]] = None
         self.flat_p = self.flat_g = self.m = self.v = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._static = self._g_loss = self._g_parts = self._g_err = None
 
     # -------------------------------------------------------------------------------------------------------------
     def _flatten(self, live: List[torch.nn.Parameter]) -> None:
@@ -87,10 +89,10 @@ class TrainStep:
             off += sz
         self.live = live
 
-    def loss(self, batch: Dict):
+    def loss(self, batch: Dict, check: bool = True):
         """Mean over the rank's frames of the reference's per-frame loss."""
         model, B = self.model, batch["frames"]
-        outs = model.forward_batch(batch, "train")
+        outs = model.forward_batch(batch, "train", check=check)
         n4 = batch["pc_data_dict"]["points"][-1].shape[0] // B
         total, parts = None, []
         for b in range(B):
@@ -115,8 +117,58 @@ class TrainStep:
             self._flatten([p for p in self.model.parameters() if p.requires_grad and p.grad is not None])
         return loss.detach(), parts
 
+    # -------------------------------------------------------------------------------------------------------------
+    def enable_cuda_graph(self, batch: Dict) -> None:
+        """Capture forward + losses + backward over `batch`'s device buffers into one CUDA graph (about 2,000 kernel
+        launches and the autograd bookkeeping between them leave the critical path).  Later steps copy their batch into
+        these buffers and replay.  The gradient all-reduce and the Adam kernel (whose bias correction takes the step
+        number as an argument) stay outside the graph.  Needs the flat buffers, i.e. at least one eager step."""
+        if self.live is None:
+            self.backward(batch)
+        self.model.train()
+        # the eager step created the AccumulateGrad nodes on the default stream; the capture runs on its own stream
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up on the capture-side stream (allocator, caches)
+            self.flat_g.zero_()
+            l, _ = self.loss(batch, check=False)
+            l.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.flat_g.zero_()
+            l, parts = self.loss(batch, check=False)
+            l.backward()
+            self._g_loss, self._g_parts, self._g_err = l.detach(), parts, self.model.last_err
+        self.graph, self._static = g, batch
+
+    def _load_static(self, batch: Dict) -> None:
+        def cp(dst, src):
+            if torch.is_tensor(dst):
+                dst.copy_(src, non_blocking=True)
+            elif isinstance(dst, list):
+                for d, s in zip(dst, src):
+                    cp(d, s)
+            elif isinstance(dst, dict):
+                for k in dst:
+                    cp(dst[k], src[k])
+        cp(self._static, batch)
+
+    def check_errors(self) -> None:
+        """Host-side check of the captured step's out-of-map flag (synchronises)."""
+        if self._g_err is not None and int(self._g_err.item()) != 0:
+            raise AssertionError("extract_patch: a 4x4 window falls outside the feature map")
+
     def step(self, batch: Dict):
-        loss, parts = self.backward(batch)
+        if self.graph is not None:
+            if batch is not self._static:
+                self._load_static(batch)
+            self.graph.replay()
+            loss, parts = self._g_loss, self._g_parts
+        else:
+            loss, parts = self.backward(batch)
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_g, group=self.group)                  # NCCL sum over NVLink
         self.step_count += 1

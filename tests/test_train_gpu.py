@@ -383,3 +383,29 @@ def test_first_adam_step_moves_by_lr(seeded_sd):
 
 def _offset(ts, p):
     return (p.data_ptr() - ts.flat_p.data_ptr()) // 4
+
+
+def test_captured_step_equals_eager_step(seeded_sd):
+    """TrainStep.enable_cuda_graph: the replayed forward + losses + backward gives the eager step's loss and gradient
+    (the backward's vector atomics reorder fp32 sums, hence a tolerance), also for a batch other than the captured one."""
+    from cofii2p_b200 import ops
+    from cofii2p_b200.frames import frame_to, stack_frames
+    from cofii2p_b200.train import TrainStep
+    ops.set_engine("fp32")
+    b0 = stack_frames([frame_to(get_frame(0, 4096), "cuda")])
+    b1 = stack_frames([frame_to(get_frame(1, 4096), "cuda")])
+    model, opt = _fresh_model(seeded_sd)
+    eager = TrainStep(model, opt)
+    ref = {}
+    for name, b in (("b0", b0), ("b1", b1)):
+        l, _ = eager.backward(b)
+        ref[name] = (float(l), eager.flat_g.clone())
+    model2, _ = _fresh_model(seeded_sd)
+    ts = TrainStep(model2, opt, lr=0.0)                       # lr 0: parameters stay put, steps are comparable
+    keep = stack_frames([frame_to(get_frame(0, 4096), "cuda")])
+    ts.enable_cuda_graph(keep)
+    for name, b in (("b0", keep), ("b1", b1), ("b0", b0)):
+        l, _ = ts.step(b)
+        ts.check_errors()
+        assert abs(float(l) - ref[name][0]) < 1e-4 * abs(ref[name][0]), name
+        assert float((ts.flat_g - ref[name][1]).norm() / ref[name][1].norm()) < 1e-4, name
