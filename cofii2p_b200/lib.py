@@ -82,6 +82,8 @@ SIGNATURES = {
     "cofi_conv2d_wgrad_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "cofi_attention_fwd_lse": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp]),
     "cofi_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "cofi_attention_bwd_tc_workspace": (_l, [_l, _l, _i, _i, _i]),
+    "cofi_attention_bwd_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cofi_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
 }
 

@@ -801,6 +801,13 @@ def attention_bwd(q, k, v, out, dout, lse, frames: int, heads: int, scale: float
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     dsum = torch.empty((q.shape[0], heads), dtype=torch.float32, device=q.device)
     _meta(10.0 * frames * L * S * q.shape[1], 4.0 * (4 * q.numel() + 4 * k.numel()))
+    D = q.shape[1] // heads
+    if _engine == ENGINE_TF32 and D == 32 and L % 4 == 0 and S % 4 == 0:
+        # tcgen05 backward (tf32 operands, fp32 accumulate); Q^T, dO^T, K^T copies live in the workspace
+        ws = _ws(_lib.cofi_attention_bwd_tc_workspace(L, S, frames, heads, D), q.device)
+        _call("cofi_attention_bwd_tc", _p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), L, S, frames, heads, D, float(scale),
+              _p(dq), _p(dk), _p(dv), _p(dsum), _p(ws), _st())
+        return dq, dk, dv
     _call("cofi_attention_bwd", _p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), L, S, frames, heads, q.shape[1] // heads,
           float(scale), _p(dq), _p(dk), _p(dv), _p(dsum), _st())
     return dq, dk, dv

@@ -357,6 +357,13 @@ int cofi_attention_fwd_lse(const float* q, const float* k, const float* v, int64
 int cofi_attention_bwd(const float* q, const float* k, const float* v, const float* out, const float* dout,
                        const float* lse, int64_t L, int64_t S, int frames, int heads, int D, float scale, float* dq,
                        float* dk, float* dv, float* dsum_work /* [frames*L*heads] */, void* stream);
+/* The same backward on tcgen05 (tf32 operands, fp32 accumulate in TMEM; D == 32, L and S multiples of 4): two launches of
+ * one kernel shaped like the forward -- dQ with the keys streamed, then dK/dV with the queries streamed; the [L,S]
+ * matrices never reach HBM.  tr_work: cofi_attention_bwd_tc_workspace() bytes for the Q^T, dO^T, K^T copies. */
+int64_t cofi_attention_bwd_tc_workspace(int64_t L, int64_t S, int frames, int heads, int D);
+int cofi_attention_bwd_tc(const float* q, const float* k, const float* v, const float* out, const float* dout,
+                          const float* lse, int64_t L, int64_t S, int frames, int heads, int D, float scale, float* dq,
+                          float* dk, float* dv, float* dsum_work, void* tr_work, void* stream);
 /* fused Adam step (torch.optim.Adam semantics, reference train.py:154); grad_scale folds the 1/world_size of the
  * data-parallel gradient average. */
 int cofi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

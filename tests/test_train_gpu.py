@@ -409,3 +409,37 @@ def test_captured_step_equals_eager_step(seeded_sd):
         ts.check_errors()
         assert abs(float(l) - ref[name][0]) < 1e-4 * abs(ref[name][0]), name
         assert float((ts.flat_g - ref[name][1]).norm() / ref[name][1].norm()) < 1e-4, name
+
+
+@pytest.mark.parametrize("L,S,frames", [(300, 260, 2), (1280, 1280, 1), (64, 132, 3)])
+def test_attention_backward_tcgen05(L, S, frames):
+    """cofi_attention_bwd_tc (tf32 operands) against torch autograd in fp32, ragged tiles and stacked frames included."""
+    from cofii2p_b200 import autograd as ad, ops
+    ops.set_engine("tf32")
+    try:
+        g = torch.Generator().manual_seed(L + S)
+        q, k, v = (torch.randn((frames * n, 128), generator=g) for n in (L, S, S))
+        go = torch.randn((frames * L, 128), generator=g)
+        qr, kr, vr = _leaf(q), _leaf(k), _leaf(v)
+        outs = []
+        for f in range(frames):
+            qq, kk, vv = (qr[f * L:(f + 1) * L].view(1, L, 4, 32), kr[f * S:(f + 1) * S].view(1, S, 4, 32),
+                          vr[f * S:(f + 1) * S].view(1, S, 4, 32))
+            a = torch.softmax(torch.einsum("nlhd,nshd->nlsh", qq, kk) / 32 ** 0.5, dim=2)
+            outs.append(torch.einsum("nlsh,nshd->nlhd", a, vv).reshape(L, 128))
+        y = torch.cat(outs)
+        y.backward(go)
+        qc, kc, vc = _cuda_leaf(q), _cuda_leaf(k), _cuda_leaf(v)
+        yc = ad.attention(qc, kc, vc, frames, 4, 1.0 / 32 ** 0.5)
+        yc.backward(go.cuda())
+        for name, got, ref in (("y", yc, y), ("dq", qc.grad, qr.grad), ("dk", kc.grad, kr.grad), ("dv", vc.grad, vr.grad)):
+            assert _nrm_err(got, ref) < 3e-3, (name, _nrm_err(got, ref))
+            assert rel_err(got, ref) < 2e-2, (name, rel_err(got, ref))
+        # and against the SIMT fp32 backward of the same library on the same inputs
+        ops.set_engine("fp32")
+        q2, k2, v2 = _cuda_leaf(q), _cuda_leaf(k), _cuda_leaf(v)
+        ad.attention(q2, k2, v2, frames, 4, 1.0 / 32 ** 0.5).backward(go.cuda())
+        for name, got, ref in (("dq", qc.grad, q2.grad), ("dk", kc.grad, k2.grad), ("dv", vc.grad, v2.grad)):
+            assert _nrm_err(got, ref) < 3e-3, (name, _nrm_err(got, ref))
+    finally:
+        ops.set_engine("fp32")
