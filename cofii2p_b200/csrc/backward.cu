@@ -332,7 +332,9 @@ scatter_add_rows_kernel(const float* __restrict__ dy, int64_t ldy, int C, const 
         if (src >= 0 && src < Ns) atomicAdd(dx + (frame * Ns + src) * C + c, __ldg(dy + m * ldy + c));
     }
 }
-// maxpool over neighbours backward: gradient goes to the FIRST neighbour attaining the maximum (torch.max semantics)
+// maxpool over neighbours backward: gradient goes to the FIRST neighbour attaining the maximum (torch.max semantics).
+// Same gather as the forward kernel (kpconv.cu): warp per query, the 128 neighbour ids held 4 per lane, float4 per lane
+// over the channels, four independent gathers in flight; the arg-max is tracked per channel.
 __global__ void __launch_bounds__(128)
 maxpool_rows_bwd_kernel(const float* __restrict__ x, int C, const int64_t* __restrict__ nbr, int H, int64_t Mq,
                         int64_t Ns, int64_t total_q, const float* __restrict__ dy, float* __restrict__ dx) {
@@ -341,18 +343,61 @@ maxpool_rows_bwd_kernel(const float* __restrict__ x, int C, const int64_t* __res
     if (m >= total_q) return;
     const int64_t frame = m / Mq;
     const float* xb = x + frame * Ns * C;
-    for (int c = lane; c < C; c += 32) {
-        float best = -INFINITY;
-        int64_t arg = -1;
-        for (int h = 0; h < H; ++h) {
-            const int64_t id = __ldg(nbr + m * H + h);
-            const float v = (id >= 0 && id < Ns) ? __ldg(xb + id * C + c) : 0.0f;
-            if (v > best) {
-                best = v;
-                arg = (id >= 0 && id < Ns) ? id : -1;
+    int idx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int h = j * 32 + lane;
+        int64_t id = (h < H) ? __ldg(nbr + m * H + h) : -2;  // -2: beyond H (ignored), -1: shadow (value 0, no gradient)
+        if (id >= Ns || id < 0) id = (h < H) ? -1 : -2;
+        idx[j] = (int)id;
+    }
+    const bool vec = (C % 4) == 0;
+    for (int c0 = 0; c0 < C; c0 += 128) {
+        const int c = c0 + lane * 4;
+        const bool act = c < C;
+        float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        int a0 = -1, a1 = -1, a2 = -1, a3 = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll 2
+            for (int l = 0; l < 32; l += 4) {
+                int id[4];
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, idx[j], l + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (id[u] >= 0 && act) {
+                        const float* r = xb + (int64_t)id[u] * C;
+                        if (vec) {
+                            v[u] = __ldg(reinterpret_cast<const float4*>(r + c));
+                        } else {
+                            v[u].x = r[c];
+                            if (c + 1 < C) v[u].y = r[c + 1];
+                            if (c + 2 < C) v[u].z = r[c + 2];
+                            if (c + 3 < C) v[u].w = r[c + 3];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (id[u] == -2) continue;  // beyond H: not a neighbour at all
+                    if (v[u].x > mx.x) { mx.x = v[u].x; a0 = id[u]; }
+                    if (v[u].y > mx.y) { mx.y = v[u].y; a1 = id[u]; }
+                    if (v[u].z > mx.z) { mx.z = v[u].z; a2 = id[u]; }
+                    if (v[u].w > mx.w) { mx.w = v[u].w; a3 = id[u]; }
+                }
             }
         }
-        if (arg >= 0) atomicAdd(dx + (frame * Ns + arg) * C + c, __ldg(dy + m * C + c));
+        if (act) {
+            const float* g = dy + m * C + c;
+            float* db = dx + frame * Ns * C + c;
+            if (a0 >= 0) atomicAdd(db + (int64_t)a0 * C, __ldg(g));
+            if (c + 1 < C && a1 >= 0) atomicAdd(db + (int64_t)a1 * C + 1, __ldg(g + 1));
+            if (c + 2 < C && a2 >= 0) atomicAdd(db + (int64_t)a2 * C + 2, __ldg(g + 2));
+            if (c + 3 < C && a3 >= 0) atomicAdd(db + (int64_t)a3 * C + 3, __ldg(g + 3));
+        }
     }
 }
 
@@ -965,7 +1010,7 @@ extern "C" int cofi_scatter_add_rows(const float* dy, int64_t ldy, int C, const 
 
 extern "C" int cofi_maxpool_rows_bwd(const float* x, int C, const int64_t* nbr, int H, int64_t Mq, int64_t Ns, int frames,
                                      const float* dy, float* dx, void* stream) {
-    COFI_REQUIRE(x && nbr && dy && dx && C > 0 && H > 0 && frames > 0, "cofi_maxpool_rows_bwd: bad argument");
+    COFI_REQUIRE(x && nbr && dy && dx && C > 0 && H > 0 && H <= 128 && frames > 0, "cofi_maxpool_rows_bwd: bad argument");
     const int64_t total = Mq * frames;
     if (total == 0) return COFI_OK;
     maxpool_rows_bwd_kernel<<<(unsigned)ceil_div(total, 4), 128, 0, ST>>>(x, C, nbr, H, Mq, Ns, total, dy, dx);
