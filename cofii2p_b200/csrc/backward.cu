@@ -144,6 +144,97 @@ norm_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ dy,
         o[1] = b;
     }
 }
+// float4 variants (C % 4 == 0): four channels per thread, 16-byte loads, fp32 partial sums over the <= 40 rows a thread
+// sees, promoted to double for the cross-thread reduction; 2-D indexing instead of a 64-bit division per element.
+__global__ void __launch_bounds__(256)
+norm_bwd_stats_v4_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+                         int64_t R, int C, int G, const float2* __restrict__ mean_rstd, int act,
+                         double* __restrict__ part /* [frames][chunks][C][2] */) {
+    const int frame = blockIdx.z, chunk = blockIdx.y;
+    const int cl = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + cl) * 4;
+    const int64_t per = (R + kBwdChunks - 1) / kBwdChunks;
+    const int64_t r0 = chunk * per, r1 = (r0 + per < R) ? r0 + per : R;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+        const int gs = C / G;
+        float mean[4], rstd[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 ms = __ldg(mean_rstd + (int64_t)frame * G + (c + e) / gs);
+            mean[e] = ms.x;
+            rstd[e] = ms.y;
+        }
+        const int64_t base = (int64_t)frame * R;
+        for (int64_t r = r0 + ty; r < r1; r += 8) {
+            const int64_t i = (base + r) * C + c;
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + i));
+            const float4 y4 = __ldg(reinterpret_cast<const float4*>(y + i));
+            const float4 x4 = __ldg(reinterpret_cast<const float4*>(x + i));
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float dz = act_grad(gv[e], yv[e], act);
+                a[e] += dz;
+                b[e] = fmaf(dz, (xv[e] - mean[e]) * rstd[e], b[e]);
+            }
+        }
+    }
+    __shared__ double sh[8][32][8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        sh[ty][cl][e] = (double)a[e];
+        sh[ty][cl][4 + e] = (double)b[e];
+    }
+    __syncthreads();
+    if (c < C) {  // thread (ty, cl) folds entry ty (0..3: sums of dz, 4..7: sums of dz*xh) of column group cl
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sh[k][cl][ty];
+        part[(((int64_t)frame * kBwdChunks + chunk) * C + c + (ty & 3)) * 2 + (ty >> 2)] = t;
+    }
+}
+__global__ void __launch_bounds__(256)
+norm_bwd_apply_v4_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+                         int64_t R, int C, int G, const float2* __restrict__ mean_rstd, const float2* __restrict__ s12,
+                         const float* __restrict__ gamma, int act, float* __restrict__ dx, float* __restrict__ dres) {
+    const int frame = blockIdx.z;
+    const int cl = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + cl) * 4;
+    if (c >= C) return;
+    const int gs = C / G;
+    const float inv_n = 1.0f / ((float)R * (float)gs);
+    float mean[4], rstd[4], k1[4], k2[4], gm[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int g = (c + e) / gs;
+        const float2 ms = __ldg(mean_rstd + (int64_t)frame * G + g);
+        const float2 sv = __ldg(s12 + (int64_t)frame * G + g);
+        mean[e] = ms.x;
+        rstd[e] = ms.y;
+        k1[e] = sv.x * inv_n;
+        k2[e] = sv.y * inv_n;
+        gm[e] = gamma ? __ldg(gamma + c + e) : 1.0f;
+    }
+    const int64_t per = (R + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = blockIdx.y * per, r1 = (r0 + per < R) ? r0 + per : R;
+    const int64_t base = (int64_t)frame * R;
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+        const int64_t i = (base + r) * C + c;
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + i));
+        const float4 y4 = __ldg(reinterpret_cast<const float4*>(y + i));
+        const float4 x4 = __ldg(reinterpret_cast<const float4*>(x + i));
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+        float o[4], z[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            z[e] = act_grad(gv[e], yv[e], act);
+            const float xh = (xv[e] - mean[e]) * rstd[e];
+            o[e] = rstd[e] * (z[e] * gm[e] - k1[e] - xh * k2[e]);
+        }
+        *reinterpret_cast<float4*>(dx + i) = make_float4(o[0], o[1], o[2], o[3]);
+        if (dres) *reinterpret_cast<float4*>(dres + i) = make_float4(z[0], z[1], z[2], z[3]);
+    }
+}
 // per (frame, channel): reduce chunks -> AB[frame][c][2] (double)
 __global__ void __launch_bounds__(128)
 norm_bwd_reduce_kernel(const double* __restrict__ part, int C, int total /* frames*C */, double* __restrict__ ab) {
@@ -946,8 +1037,15 @@ extern "C" int cofi_norm_rows_bwd(const float* x, const float* dy, const float* 
     double* ab = part + (int64_t)frames * kBwdChunks * C * 2;
     float2* s12 = (float2*)(ab + (int64_t)frames * C * 2);
     const float2* mr = (const float2*)mean_rstd;
-    dim3 g1((unsigned)ceil_div(C, 32), kBwdChunks, frames);
-    norm_bwd_stats_kernel<<<g1, 256, 0, ST>>>(x, dy, y, R, C, G, mr, act, part);
+    const bool v4 = C % 4 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
+                    ((uintptr_t)dx % 16) == 0 && (!dres || ((uintptr_t)dres % 16) == 0);
+    if (v4) {
+        dim3 g1((unsigned)ceil_div(C, 128), kBwdChunks, frames);
+        norm_bwd_stats_v4_kernel<<<g1, 256, 0, ST>>>(x, dy, y, R, C, G, mr, act, part);
+    } else {
+        dim3 g1((unsigned)ceil_div(C, 32), kBwdChunks, frames);
+        norm_bwd_stats_kernel<<<g1, 256, 0, ST>>>(x, dy, y, R, C, G, mr, act, part);
+    }
     int rc = check_launch("cofi_norm_rows_bwd(stats)");
     if (rc) return rc;
     norm_bwd_reduce_kernel<<<(unsigned)ceil_div((int64_t)frames * C, 128), 128, 0, ST>>>(part, C, frames * C, ab);
@@ -959,7 +1057,17 @@ extern "C" int cofi_norm_rows_bwd(const float* x, const float* dy, const float* 
     rc = check_launch("cofi_norm_rows_bwd(finalize)");
     if (rc) return rc;
     const int64_t rows = R * frames;
-    norm_bwd_apply_kernel<<<ew_blocks_b(rows * C, 256), 256, 0, ST>>>(x, dy, y, R, C, G, rows, mr, s12, gamma, act, dx, dres);
+    if (v4) {
+        // about 8 resident CTAs per SM over the whole grid, at least 8 rows per CTA
+        const int64_t cb = ceil_div(C, 128);
+        int64_t chunks = ceil_div((int64_t)148 * 8, cb * frames);
+        if (chunks > ceil_div(R, 8)) chunks = ceil_div(R, 8);
+        if (chunks < 1) chunks = 1;
+        dim3 g2((unsigned)cb, (unsigned)chunks, frames);
+        norm_bwd_apply_v4_kernel<<<g2, 256, 0, ST>>>(x, dy, y, R, C, G, mr, s12, gamma, act, dx, dres);
+    } else {
+        norm_bwd_apply_kernel<<<ew_blocks_b(rows * C, 256), 256, 0, ST>>>(x, dy, y, R, C, G, rows, mr, s12, gamma, act, dx, dres);
+    }
     return check_launch("cofi_norm_rows_bwd(apply)");
 }
 

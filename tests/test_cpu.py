@@ -329,3 +329,27 @@ def test_preprocess_surface_without_gpu():
     np.random.seed(7)
     b = ok.half_sample_pyramid(pts, 5)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+# ---------------------------------------------------------------------------------------------- pose step (row f2)
+def test_pose_step_on_reference_golden_outputs():
+    """oracle/evaluate.py (eval_all.py:99-105) + the shared cv2 / get_P_diff wrappers on the reference's frozen test-mode
+    outputs: deterministic pose, exact RTE/RRE arithmetic on a known transform."""
+    from cofii2p_b200 import evaluate as ev
+    from oracle import evaluate as oev
+    z = np.load(os.path.join(GOLD, "frame_s0_n4096.npz"))
+    ri, ro, idx = oev.correspondences(*[torch.from_numpy(z["test/" + k]) for k in
+                                        ("fine_img_feature_patch", "fine_pc_inline_feature", "fine_center_xy", "coarse_pc_points")])
+    assert ri.shape == (52, 2) and ro.shape == (52, 3) and int(idx.min()) >= 0 and int(idx.max()) <= 15
+    c = z["test/fine_center_xy"]
+    assert np.array_equal(ri[:, 0], c[0] - 2 + idx.numpy() // 4) and np.array_equal(ri[:, 1], c[1] - 2 + idx.numpy() % 4)
+    K = get_frame(0, 4096)["K_half"].numpy()
+    a, b = ev.solve_pose(K, ri, ro), ev.solve_pose(K, ri, ro)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    T = np.eye(4)
+    ang = np.deg2rad(10.0)
+    T[:3, :3] = [[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]
+    T[:3, 3] = [0.3, 0.0, 0.4]
+    rte, rre = ev.pose_error(np.eye(4), T)
+    assert abs(rte - 0.5) < 1e-12 and abs(rre - 10.0) < 1e-9
+    assert max(ev.pose_error(T, T)) < 1e-12

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import get_frame, rel_err
+from conftest import ROOT, get_frame, rel_err
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -234,3 +234,29 @@ def test_graph_cached_forward_matches_eager(cuda_model):
         assert len(cuda_model._graphs) == 1
     finally:
         cuda_model.enable_cuda_graph(False)
+
+
+@pytest.mark.parametrize("seed,n", [(0, 4096), (1, 4096), (0, 20480)])
+def test_pose_matches_reference_pipeline(cuda_model, seed, n):
+    """Row f2: forward(test) -> fine matching -> cv2.solvePnPRansac, against the same steps applied to the REAL
+    reference's frozen outputs (tests/golden): correspondences identical, RTE/RRE within 1e-3 (north star)."""
+    import numpy as np
+    from cofii2p_b200 import evaluate as ev, ops
+    from cofii2p_b200.frames import frame_to
+    from oracle import evaluate as oev
+    ops.set_engine("fp32")
+    f = get_frame(seed, n)
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"frame_s{seed}_n{n}.npz"))
+    K = f["K_half"].numpy()
+    T_gt = np.linalg.inv(f["P_cloud_from_cam"].numpy().astype(np.float64))
+    mine = ev.register(cuda_model, frame_to(f, "cuda"), K, T_gt)
+    ri, ro, ridx = oev.correspondences(*[torch.from_numpy(z["test/" + k]) for k in
+                                         ("fine_img_feature_patch", "fine_pc_inline_feature", "fine_center_xy", "coarse_pc_points")])
+    assert np.array_equal(mine["image_points"], ri) and np.array_equal(mine["object_points"], ro)
+    assert torch.equal(mine["fine_index"].cpu(), ridx)
+    ok, T_ref, _ = ev.solve_pose(K, ri, ro)
+    assert ok == mine["success"]
+    if ok:
+        rte_r, rre_r = ev.pose_error(T_ref, T_gt)
+        assert abs(mine["rte"] - rte_r) <= 1e-3 and abs(mine["rre"] - rre_r) <= 1e-3
+        assert np.allclose(mine["T"], T_ref, atol=1e-9)
