@@ -425,7 +425,15 @@ scatter_add_rows_kernel(const float* __restrict__ dy, int64_t ldy, int C, const 
 }
 // maxpool over neighbours backward: gradient goes to the FIRST neighbour attaining the maximum (torch.max semantics).
 // Same gather as the forward kernel (kpconv.cu): warp per query, the 128 neighbour ids held 4 per lane, float4 per lane
-// over the channels, four independent gathers in flight; the arg-max is tracked per channel.
+// over the channels, four independent gathers in flight, narrow rows walked by several lane groups on interleaved
+// neighbours.  The arg-max is tracked per channel as (value, neighbour position): positions order ties across groups.
+__device__ __forceinline__ void amax_take(float& bv, int& bh, int& bi, float v, int h, int id) {
+    if (v > bv || (v == bv && h < bh)) {
+        bv = v;
+        bh = h;
+        bi = id;
+    }
+}
 __global__ void __launch_bounds__(128)
 maxpool_rows_bwd_kernel(const float* __restrict__ x, int C, const int64_t* __restrict__ nbr, int H, int64_t Mq,
                         int64_t Ns, int64_t total_q, const float* __restrict__ dy, float* __restrict__ dx) {
@@ -438,24 +446,26 @@ maxpool_rows_bwd_kernel(const float* __restrict__ x, int C, const int64_t* __res
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int h = j * 32 + lane;
-        int64_t id = (h < H) ? __ldg(nbr + m * H + h) : -2;  // -2: beyond H (ignored), -1: shadow (value 0, no gradient)
+        int64_t id = (h < H) ? __ldcs(nbr + m * H + h) : -2;  // -2: beyond H (ignored), -1: shadow (value 0, no gradient)
         if (id >= Ns || id < 0) id = (h < H) ? -1 : -2;
         idx[j] = (int)id;
     }
     const bool vec = (C % 4) == 0;
+    const int rl = C >> 2;
+    const int lpr = (vec && (rl == 4 || rl == 8 || rl == 16)) ? rl : 32;
+    const int groups = 32 / lpr, grp = lane / lpr, gl = lane - grp * lpr;
     for (int c0 = 0; c0 < C; c0 += 128) {
-        const int c = c0 + lane * 4;
+        const int c = c0 + gl * 4;
         const bool act = c < C;
-        float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        int a0 = -1, a1 = -1, a2 = -1, a3 = -1;
+        float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int bh[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30}, bi[4] = {-1, -1, -1, -1};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-#pragma unroll 2
-            for (int l = 0; l < 32; l += 4) {
+            for (int l = 0; l < 32; l += 4 * groups) {
                 int id[4];
                 float4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, idx[j], l + u);
+                for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, idx[j], l + u * groups + grp);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -474,20 +484,30 @@ maxpool_rows_bwd_kernel(const float* __restrict__ x, int C, const int64_t* __res
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (id[u] == -2) continue;  // beyond H: not a neighbour at all
-                    if (v[u].x > mx.x) { mx.x = v[u].x; a0 = id[u]; }
-                    if (v[u].y > mx.y) { mx.y = v[u].y; a1 = id[u]; }
-                    if (v[u].z > mx.z) { mx.z = v[u].z; a2 = id[u]; }
-                    if (v[u].w > mx.w) { mx.w = v[u].w; a3 = id[u]; }
+                    const int h = j * 32 + l + u * groups + grp;
+                    amax_take(bv[0], bh[0], bi[0], v[u].x, h, id[u]);
+                    amax_take(bv[1], bh[1], bi[1], v[u].y, h, id[u]);
+                    amax_take(bv[2], bh[2], bi[2], v[u].z, h, id[u]);
+                    amax_take(bv[3], bh[3], bi[3], v[u].w, h, id[u]);
                 }
             }
         }
-        if (act) {
+        for (int off = lpr; off < 32; off <<= 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv[e], off);
+                const int oh = __shfl_xor_sync(0xffffffffu, bh[e], off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi[e], off);
+                amax_take(bv[e], bh[e], bi[e], ov, oh, oi);
+            }
+        }
+        if (act && grp == 0) {
             const float* g = dy + m * C + c;
             float* db = dx + frame * Ns * C + c;
-            if (a0 >= 0) atomicAdd(db + (int64_t)a0 * C, __ldg(g));
-            if (c + 1 < C && a1 >= 0) atomicAdd(db + (int64_t)a1 * C + 1, __ldg(g + 1));
-            if (c + 2 < C && a2 >= 0) atomicAdd(db + (int64_t)a2 * C + 2, __ldg(g + 2));
-            if (c + 3 < C && a3 >= 0) atomicAdd(db + (int64_t)a3 * C + 3, __ldg(g + 3));
+            if (bi[0] >= 0) atomicAdd(db + (int64_t)bi[0] * C, __ldg(g));
+            if (c + 1 < C && bi[1] >= 0) atomicAdd(db + (int64_t)bi[1] * C + 1, __ldg(g + 1));
+            if (c + 2 < C && bi[2] >= 0) atomicAdd(db + (int64_t)bi[2] * C + 2, __ldg(g + 2));
+            if (c + 3 < C && bi[3] >= 0) atomicAdd(db + (int64_t)bi[3] * C + 3, __ldg(g + 3));
         }
     }
 }
@@ -529,7 +549,7 @@ kpconv_aggregate_bwd_kernel(const float* __restrict__ dagg, int C, const float4*
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int h = j * 32 + lane;
-        const int64_t id = (h < H) ? __ldg(nbr + m * H + h) : Ns;
+        const int64_t id = (h < H) ? __ldcs(nbr + m * H + h) : Ns;
         bool is_near = false;
         float rx = 0.f, ry = 0.f, rz = 0.f;
         if (id >= 0 && id < Ns) {

@@ -84,7 +84,7 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int h = j * 32 + lane;
-        const int64_t id = (h < H) ? __ldg(nbr + m * H + h) : Ns;
+        const int64_t id = (h < H) ? __ldcs(nbr + m * H + h) : Ns;
         bool is_near = false;
         float rx = 0.f, ry = 0.f, rz = 0.f;
         if (id >= 0 && id < Ns) {
@@ -183,6 +183,8 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
 }
 
 // ------------------------------------------------------------------------------------------ maxpool_rows
+// 4 channels (16 B) per lane; rows narrower than a warp (C < 128) are walked by 32 / (C/4) lane groups on interleaved
+// neighbours and folded with shuffles (see the fp16 variant below).
 __global__ void __launch_bounds__(128)
 maxpool_rows_kernel(const float* __restrict__ x, int64_t ldx, int C, const int64_t* __restrict__ nbr, int H,
                     int64_t Mq, int64_t Ns, int64_t total_q, float* __restrict__ out, int64_t ldo) {
@@ -195,23 +197,25 @@ maxpool_rows_kernel(const float* __restrict__ x, int64_t ldx, int C, const int64
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int h = j * 32 + lane;
-        int64_t id = (h < H) ? __ldg(nbr + m * H + h) : -2;  // -2: beyond H (ignored), -1: shadow (value 0)
+        int64_t id = (h < H) ? __ldcs(nbr + m * H + h) : -2;  // -2: beyond H (ignored), -1: shadow (value 0)
         if (id >= Ns) id = -1;
         idx[j] = (int)id;
     }
     const bool vec = (C % 4) == 0;
+    const int rl = C >> 2;
+    const int lpr = (vec && (rl == 4 || rl == 8 || rl == 16)) ? rl : 32;
+    const int groups = 32 / lpr, grp = lane / lpr, gl = lane - grp * lpr;
     for (int c0 = 0; c0 < C; c0 += 128) {
-        const int c = c0 + lane * 4;
+        const int c = c0 + gl * 4;
         const bool act = c < C;
         float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-#pragma unroll 2
-            for (int l = 0; l < 32; l += 4) {  // four independent gathers in flight per lane
+            for (int l = 0; l < 32; l += 4 * groups) {  // four independent gathers in flight per lane
                 int id[4];
                 float4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, idx[j], l + u);
+                for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, idx[j], l + u * groups + grp);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -237,20 +241,30 @@ maxpool_rows_kernel(const float* __restrict__ x, int64_t ldx, int C, const int64
                 }
             }
         }
-        float* o = out + m * ldo;
-        if (act && vec) {
-            *reinterpret_cast<float4*>(o + c) = mx;
-        } else if (act) {
-            o[c] = mx.x;
-            if (c + 1 < C) o[c + 1] = mx.y;
-            if (c + 2 < C) o[c + 2] = mx.z;
-            if (c + 3 < C) o[c + 3] = mx.w;
+        for (int off = lpr; off < 32; off <<= 1) {
+            mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, off));
+            mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, off));
+            mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, off));
+            mx.w = fmaxf(mx.w, __shfl_xor_sync(0xffffffffu, mx.w, off));
+        }
+        if (act && grp == 0) {
+            float* o = out + m * ldo + c;
+            if (vec) {
+                *reinterpret_cast<float4*>(o) = mx;
+            } else {
+                o[0] = mx.x;
+                if (c + 1 < C) o[1] = mx.y;
+                if (c + 2 < C) o[2] = mx.z;
+                if (c + 3 < C) o[3] = mx.w;
+            }
         }
     }
 }
 
 // fp16-input variant (tf32 engine): rounding is monotonic, so max over fp16-rounded rows == fp16-rounded max; the
-// gather moves half the bytes (the kernel is L2-gather-bound: 128 rows per output row).  8 channels (16 B) per lane.
+// gather moves half the bytes.  8 channels (16 B) per lane; when a row needs fewer than 32 lanes (C < 256) the warp
+// splits into 32 / (C/8) groups that walk interleaved neighbours and are folded with shuffles at the end, so all lanes
+// gather (C = 64: four neighbours per step instead of one with 24 idle lanes).
 __global__ void __launch_bounds__(128)
 maxpool_rows_f16_kernel(const __half* __restrict__ x, int64_t ldx, int C, const int64_t* __restrict__ nbr, int H,
                         int64_t Mq, int64_t Ns, int64_t total_q, float* __restrict__ out, int64_t ldo) {
@@ -263,12 +277,15 @@ maxpool_rows_f16_kernel(const __half* __restrict__ x, int64_t ldx, int C, const 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int h = j * 32 + lane;
-        int64_t id = (h < H) ? __ldg(nbr + m * H + h) : -2;
+        int64_t id = (h < H) ? __ldcs(nbr + m * H + h) : -2;
         if (id >= Ns) id = -1;
         idx[j] = (int)id;
     }
+    const int rl = C >> 3;                                                       // lanes one row needs
+    const int lpr = (rl == 4 || rl == 8 || rl == 16) ? rl : 32;                  // lanes per row group
+    const int groups = 32 / lpr, grp = lane / lpr, gl = lane - grp * lpr;
     for (int c0 = 0; c0 < C; c0 += 256) {
-        const int c = c0 + lane * 8;
+        const int c = c0 + gl * 8;
         const bool act = c < C;
         __half2 mx[4];
 #pragma unroll
@@ -276,12 +293,11 @@ maxpool_rows_f16_kernel(const __half* __restrict__ x, int64_t ldx, int C, const 
         const __half2 zero2 = __float2half2_rn(0.0f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-#pragma unroll 2
-            for (int l = 0; l < 32; l += 4) {
+            for (int l = 0; l < 32; l += 4 * groups) {  // four independent gathers in flight per lane
                 int id[4];
                 uint4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, idx[j], l + u);
+                for (int u = 0; u < 4; ++u) id[u] = __shfl_sync(0xffffffffu, idx[j], l + u * groups + grp);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     v[u] = make_uint4(0u, 0u, 0u, 0u);  // shadow row = zeros
@@ -296,7 +312,14 @@ maxpool_rows_f16_kernel(const __half* __restrict__ x, int64_t ldx, int C, const 
                 }
             }
         }
-        if (act) {
+        for (int off = lpr; off < 32; off <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned o = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<unsigned*>(&mx[i]), off);
+                mx[i] = __hmax2(mx[i], *reinterpret_cast<const __half2*>(&o));
+            }
+        }
+        if (act && grp == 0) {
             float* o = out + m * ldo + c;
             const float2 a = __half22float2(mx[0]), b = __half22float2(mx[1]), cc = __half22float2(mx[2]), d = __half22float2(mx[3]);
             *reinterpret_cast<float4*>(o) = make_float4(a.x, a.y, b.x, b.y);
