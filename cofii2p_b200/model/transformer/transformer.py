@@ -24,8 +24,10 @@ class LoFTREncoderLayer(nn.Module):
         self.norm1, self.norm2 = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
 
     def forward(self, x, source, frames: int = 1):
-        """x [B*L,C], source [B*S,C] -> [B*L,C]."""
+        """x [B*L,C], source [B*S,C] (None = x itself) -> [B*L,C]."""
         C = x.shape[1]
+        if source is None:
+            source = x
         if ad.active(self):  # training: differentiable kernels, SIMT attention with saved log-sum-exp
             q = ad.colnorm(ad.linear(x, self.q_proj.weight), frames)
             k = ad.linear(source, self.k_proj.weight)
@@ -72,8 +74,15 @@ class LocalFeatureTransformer(nn.Module):
             assert feat0.shape[0] == 1 and feat1.shape[0] == 1
             feat0, feat1 = feat0[0], feat1[0]
         assert self.d_model == feat0.size(-1), "the feature number of src and transformer must be equal"
+        n0 = feat0.shape[0]
         for layer, name in zip(self.layers, self.layer_names):
-            if name == "self":
+            if name == "self" and n0 == feat1.shape[0]:
+                # both streams go through the SAME layer weights and a self layer never mixes them, so with equal token
+                # counts (1280 super-pixels, 1280 super-points) they are one call over 2*frames segments: every kernel
+                # of the layer sees twice the rows (the 80-CTA GEMMs fill the SMs) and the launch count halves
+                both = layer(torch.cat([feat0, feat1], 0), None, 2 * frames)
+                feat0, feat1 = both[:n0], both[n0:]
+            elif name == "self":
                 feat0 = layer(feat0, feat0, frames)
                 feat1 = layer(feat1, feat1, frames)
             elif name == "cross":
