@@ -57,6 +57,32 @@ class LoFTREncoderLayer(nn.Module):
         return ops.gemm_ln(h, self.mlp[2].weight, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=x)
 
 
+    def cross_pair(self, both, n: int, frames: int):
+        """Inference path of one 'cross' layer over both streams held in one buffer: both[:n] = image tokens,
+        both[n:] = point tokens.  Reference order (model/transformer/transformer.py:98-100): the image stream attends to
+        the old point stream, then the point stream attends to the UPDATED image stream.  Everything that depends only
+        on the layer input -- the query projection (+ its sequence-axis normalisation) and the x half of mlp[0] -- is one
+        call over both streams; the rest runs stream after stream, writing into the halves of the output buffer."""
+        C = both.shape[1]
+        scale = 1.0 / self.dim ** 0.5
+        tc = ops.engine_id() == ops.ENGINE_TF32 and n % 4 == 0
+        q = ops.colnorm_rows(ops.gemm(both, self.q_proj.weight), 2 * frames)
+        w1 = self.mlp[0].weight
+        h = ops.gemm(both, w1[:, :C])
+        out = torch.empty_like(both)
+        for lo, src in ((0, both[n:]), (n, out[:n])):
+            k = ops.gemm(src, self.k_proj.weight)
+            if tc:
+                msg = ops.attention_vt(q[lo:lo + n], k, ops.gemm(self.v_proj.weight, src), frames, self.nhead, scale)
+            else:
+                msg = self.attention(q[lo:lo + n], k, ops.gemm(src, self.v_proj.weight), frames, self.nhead)
+            m = ops.gemm_ln(msg, self.merge.weight, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            hh = ops.gemm(m, w1[:, C:], out=h[lo:lo + n], accumulate=True, act=ops.ACT_RELU)
+            ops.gemm_ln(hh, self.mlp[2].weight, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=both[lo:lo + n],
+                        out=out[lo:lo + n])
+        return out
+
+
 class LocalFeatureTransformer(nn.Module):
     def __init__(self, D_MODEL, NHEAD, LAYER_NAMES, ATTENTION):
         super().__init__()
@@ -75,6 +101,13 @@ class LocalFeatureTransformer(nn.Module):
             feat0, feat1 = feat0[0], feat1[0]
         assert self.d_model == feat0.size(-1), "the feature number of src and transformer must be equal"
         n0 = feat0.shape[0]
+        if n0 == feat1.shape[0] and not ad.active(self) and all(nm in ("self", "cross") for nm in self.layer_names):
+            # inference with equal token counts: both streams live in one [2n, C] buffer for the whole stack
+            both = torch.cat([feat0, feat1], 0)
+            for layer, name in zip(self.layers, self.layer_names):
+                both = layer(both, None, 2 * frames) if name == "self" else layer.cross_pair(both, n0, frames)
+            feat0, feat1 = both[:n0], both[n0:]
+            return (feat0.unsqueeze(0), feat1.unsqueeze(0)) if squeeze else (feat0, feat1)
         for layer, name in zip(self.layers, self.layer_names):
             if name == "self" and n0 == feat1.shape[0]:
                 # both streams go through the SAME layer weights and a self layer never mixes them, so with equal token

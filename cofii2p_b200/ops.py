@@ -302,13 +302,17 @@ def norm_rows_pre(x, stats, frames: int, groups: int, gamma, beta, eps: float = 
 
 
 def gemm_ln(a, w, gamma, beta, eps: float = 1e-5, bias=None, act: int = ACT_NONE, residual=None,
-            engine: Optional[int] = None):
-    """act(LayerNorm(a @ w.T + bias)) + residual, one kernel on the tensor-core engines when N <= 128."""
+            engine: Optional[int] = None, out: Optional[torch.Tensor] = None):
+    """act(LayerNorm(a @ w.T + bias)) + residual, one kernel on the tensor-core engines when N <= 128.
+    `out`: optional contiguous [M, N] destination (e.g. a row slice of a larger buffer)."""
     a, lda = _rows(a, "a")
     w, ldw = _rows(w, "w")
     M, K = a.shape
     N = w.shape[0]
-    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    elif tuple(out.shape) != (M, N) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise RuntimeError(f"gemm_ln: out must be a contiguous float32 [{M}, {N}] tensor")
     ldr = 0
     if residual is not None:
         residual, ldr = _rows(residual, "residual")
