@@ -154,6 +154,28 @@ def cpu_forward_baseline(sd, num_pc, n_frames, mode="val"):
     return times
 
 
+def torch_eager_gpu_baseline(sd, num_pc, n_frames, dev, mode="val"):
+    """Secondary baseline of the cpu_baseline leg: the same oracle port executed by stock PyTorch
+    on the B200 (ATen / cuDNN / cuBLAS eager kernels, one frame per forward as the reference runs) -- what the
+    reference's own code gets from this GPU without this library.  Returns seconds per frame."""
+    from cofii2p_b200.frames import frame_to, make_frame
+    from oracle import restate
+    gsd = {k: v.to(dev) for k, v in sd.items()}
+    frames = [frame_to(make_frame(100 + i, num_pc=num_pc, cache_dir="/tmp/cofi_frames", device=str(dev)), dev)
+              for i in range(2)]
+    times = []
+    with torch.no_grad():
+        for i in range(n_frames + 2):
+            f = frames[i % 2]
+            torch.cuda.synchronize(dev)
+            t = time.perf_counter()
+            restate.forward(gsd, *[f[k] for k in ARGS], mode, run_dead=True)
+            torch.cuda.synchronize(dev)
+            if i >= 2:  # two warm-ups (cuDNN autotune, allocator)
+                times.append(time.perf_counter() - t)
+    return times
+
+
 # ------------------------------------------------------------------------------------------------ arms
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -399,6 +421,14 @@ def run_cofi(args):
                                 "sample": f"{len(times)} frames (after 1 warm-up) of the same 20480-pt workload, "
                                           f"oracle/restate.py forward(val) incl. dead layer3/4; best of thread counts "
                                           f"{cands} on a {os.cpu_count()}-core host -> {cores} threads"}
+        try:
+            tg = torch_eager_gpu_baseline(cpu_sd, args.num_pc, 5, dev)
+            line["cpu_baseline"]["torch_eager_b200"] = {
+                "value": len(tg) / sum(tg), "unit": UNIT,
+                "sample": f"{len(tg)} frames after 2 warm-ups: the same oracle port run by stock PyTorch eager kernels "
+                          "(ATen/cuDNN/cuBLAS, fp32) on this B200, one frame per forward"}
+        except Exception as e:  # a baseline must never take the measurement down
+            line["cpu_baseline"]["torch_eager_b200"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -226,6 +226,24 @@ def run_train(args):
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "1 training iteration (forward train mode incl. dead layers + losses + autograd backward) of "
                                           "one 20480-pt frame, oracle/restate.py on the host"}
+        try:   # secondary baseline: the same iteration by stock PyTorch eager + autograd on this B200
+            from cofii2p_b200.frames import frame_to
+            gsd = {k: v.to(dev) for k, v in cpu_sd.items()}
+            gfr = frame_to(fr, dev)
+            ts = []
+            for i in range(5):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                cpu_train_step(gsd, gfr, opt, None)
+                torch.cuda.synchronize(dev)
+                if i >= 2:
+                    ts.append(time.perf_counter() - t0)
+            line["cpu_baseline"]["torch_eager_b200"] = {
+                "value": len(ts) / sum(ts), "unit": UNIT,
+                "sample": f"{len(ts)} iterations after 2 warm-ups: oracle forward + losses + torch autograd backward run by "
+                          "stock PyTorch eager kernels (fp32) on this B200, one frame per iteration, no optimizer step"}
+        except Exception as e:
+            line["cpu_baseline"]["torch_eager_b200"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
