@@ -12,7 +12,8 @@
 //   warp 1     MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) four times
 //              per k-block on UMMA shared-memory descriptors; fp32 accumulator lives in TMEM (BN columns);
 //              tcgen05.commit releases ring slots and finally signals the epilogue.
-//   warps 2-5  epilogue: tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused rowdiv / per-channel
+//   warps 2-9  epilogue (two warps per TMEM lane quarter, alternating over the 32-column chunks; warps 2-5 only for
+//              3xTF32): tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused rowdiv / per-channel
 //              affine / bias / residual / accumulate / activation, 128-byte vector stores.
 //   warps 6-9  (TF32X3 only) operand splitters: rewrite each landed tile in place as hi = tf32-truncated value and
 //              write lo = x - hi into a second buffer; the issuer then runs hi*hi + lo*hi + hi*lo (3xTF32), which
@@ -173,7 +174,9 @@ struct Cfg {
     static constexpr int NS = (BN == 128) ? 3 : 4;
     static constexpr int RING = STAGE * NS * (X3 ? 2 : 1);
     static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */ + 12 * BN * 4 /* epilogue vectors + column statistics */;
-    static constexpr int THREADS = X3 ? 320 : 192;
+    static constexpr int EPI_SETS = X3 ? 1 : 2;  // epilogue warp sets (4 warps each, one per TMEM lane quarter); the sets
+                                                 // interleave over the 32-column chunks of the tile
+    static constexpr int THREADS = 320;          // 2 + 4 * EPI_SETS warps (+ 4 operand splitters for 3xTF32)
 };
 
 template <int BN, bool CONV, bool X3, bool HALF = false>
@@ -279,10 +282,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_commit(tmem_full);
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + 4 * C::EPI_SETS) {
         // ================================ epilogue ====================================
+        // The K <= 128 contractions of the path are epilogue-bound (tcgen05.ld -> math -> staged stores is one dependent
+        // chain per warp), so two warps share every TMEM lane quarter and alternate over the column chunks.
+        const int set = (warp - 2) >> 2;
         {   // stage the per-column epilogue vectors while the main loop runs
-            const int t = threadIdx.x - 64;  // 0..127
+            const int t = threadIdx.x - 64;  // 0 .. 128 * EPI_SETS - 1
             if (t < BN) {
                 const int n = n0 + t;
                 float sc = 1.0f, sh = 0.0f;
@@ -298,7 +304,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 s_gamma[t] = (p.ep.ln_gamma && n < p.N) ? __ldg(p.ep.ln_gamma + n) : 0.0f;
                 s_beta[t] = (p.ep.ln_gamma && n < p.N) ? __ldg(p.ep.ln_beta + n) : 0.0f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (C::EPI_SETS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+            else asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         if (!(p.dbg & 2)) mbar_wait(tmem_full, 0);
         tc_fence_after();
@@ -320,11 +327,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* crow = p.C + grow * p.ldc;
         const float* rrow = has_res ? ep.residual + grow * ep.ldres : nullptr;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-        float* stage = reinterpret_cast<float*>(smem) + q * (32 * 36);  // ring is idle once tmem_full fired
+        float* stage = reinterpret_cast<float*>(smem) + (set * 4 + q) * (32 * 36);  // ring is idle once tmem_full fired
         const bool rvec_ok = has_res && ((ep.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
         const bool has_ln = ep.ln_gamma != nullptr;  // host guarantees gridDim.y == 1 and N <= BN
         float ln_mean = 0.0f, ln_rstd = 1.0f;
-        if (has_ln) {
+        const bool ln_idle = has_ln && set != 0;  // a fused LayerNorm needs the whole row in one thread: set 0 does it alone
+        if (has_ln && !ln_idle) {
             float sum = 0.0f;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -351,8 +359,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             ln_rstd = rsqrtf(ssq / (float)p.N + ep.ln_eps);
         }
+        const int c_begin = ln_idle ? BN : (has_ln ? 0 : set * 32), c_step = has_ln ? 32 : 32 * C::EPI_SETS;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_begin; c0 < BN; c0 += c_step) {
             uint32_t acc[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
             tmem_ld_wait();
@@ -483,7 +492,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next chunk
         }
         if (p.stat_out) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (C::EPI_SETS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+            else asm volatile("bar.sync 1, 128;" ::: "memory");
             const int t = threadIdx.x - 64;
             if (t < BN && n0 + t < p.N) {
                 float cs = 0.0f, cq = 0.0f;
