@@ -462,23 +462,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // store instruction writes four full 128-byte lines (the per-thread-row layout would scatter 16-byte pieces)
             if (nb < p.N && !(p.dbg & 5)) {
                 const bool full = nb + 32 <= p.N;
+                const int cc = (lane & 7) * 4;
+                // dense case: row (q*32 + lane/8 + 4*it) of the tile -> one running pointer, no per-store address arithmetic
+                float* drow = CONV ? nullptr : p.C + (m0 + q * 32 + (lane >> 3)) * p.ldc + nb + cc;
+                const int64_t rows_left = CONV ? 0 : p.M - (m0 + q * 32 + (lane >> 3));
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
-                    const int rr = it * 4 + (lane >> 3), cc = (lane & 7) * 4;
-                    const int rt = q * 32 + rr;  // row inside the 128-row tile
-                    int64_t g2;
-                    bool ok2;
+                    const int rr = it * 4 + (lane >> 3);
+                    float* dst;
                     if (CONV) {
+                        const int rt = q * 32 + rr;  // row inside the 128-row tile
                         const int hl = rt / CONV_TW, wl = rt - hl * CONV_TW;
-                        g2 = ((int64_t)cb * p.Ho + ch0 + hl) * p.Wo + cw0 + wl;
-                        ok2 = true;
+                        dst = p.C + (((int64_t)cb * p.Ho + ch0 + hl) * p.Wo + cw0 + wl) * p.ldc + nb + cc;
                     } else {
-                        g2 = m0 + rt;
-                        ok2 = g2 < p.M;
+                        if (it * 4 >= rows_left) break;  // rows beyond M (rows grow with it)
+                        dst = drow + (int64_t)it * 4 * p.ldc;
                     }
-                    if (!ok2) continue;
                     const float4 val = *reinterpret_cast<const float4*>(stage + rr * 36 + cc);
-                    float* dst = p.C + g2 * p.ldc + nb + cc;
                     if (vec_ok && full) {
                         *reinterpret_cast<float4*>(dst) = val;
                     } else {
