@@ -87,13 +87,26 @@ colsum_partial_v4_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows,
         part[(int64_t)blockIdx.y * C + c + ty] = s;
     }
 }
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 colsum_final_kernel(const double* __restrict__ part, int chunks, int C, float* __restrict__ out, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    // 32 columns per block, 8 row-lanes: lane ty folds chunks ty, ty+8, ... (independent loads in flight instead of one
+    // serial chain of `chunks` L2 round trips), then a fixed-order fold over the 8 partials -- deterministic
+    __shared__ double sh[8][33];
+    const int cl = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     double s = 0.0;
-    for (int k = 0; k < chunks; ++k) s += part[(int64_t)k * C + c];
-    out[c] = (accumulate ? out[c] : 0.0f) + (float)s;
+    if (c < C) {
+#pragma unroll 4
+        for (int k = ty; k < chunks; k += 8) s += part[(int64_t)k * C + c];
+    }
+    sh[ty][cl] = s;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][cl];
+        out[c] = (accumulate ? out[c] : 0.0f) + (float)t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ norm_rows backward
@@ -242,6 +255,7 @@ norm_bwd_reduce_kernel(const double* __restrict__ part, int C, int total /* fram
     if (t >= total) return;
     const int frame = t / C, c = t - frame * C;
     double a = 0.0, b = 0.0;
+#pragma unroll 8
     for (int k = 0; k < kBwdChunks; ++k) {
         const double* o = part + (((int64_t)frame * kBwdChunks + k) * C + c) * 2;
         a += o[0];
@@ -818,6 +832,7 @@ __global__ void __launch_bounds__(256)
 split_sum_kernel(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out, int accumulate) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
+#pragma unroll 8
         for (int k = 0; k < splits; ++k) s += (double)part[(int64_t)k * n + i];
         out[i] = (accumulate ? out[i] : 0.0f) + (float)s;
     }
@@ -1038,7 +1053,7 @@ extern "C" int cofi_colsum(const float* x, int64_t ldx, int64_t rows, int C, flo
     }
     int rc = check_launch("cofi_colsum(partial)");
     if (rc) return rc;
-    colsum_final_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, ST>>>((const double*)work, chunks, C, out, accumulate);
+    colsum_final_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, ST>>>((const double*)work, chunks, C, out, accumulate);
     return check_launch("cofi_colsum(final)");
 }
 

@@ -555,7 +555,11 @@ int run(QueryParams& Q, int nsets, int frames, int mode, cudaStream_t st) {
     static bool attr_done = false;
     const int smem = SORT_CHUNK * 8;
     if (!attr_done) {
-        cudaFuncSetAttribute(knn_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(knn_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("cofi_knn: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+            return COFI_ECUDA;
+        }
         attr_done = true;
     }
     SortParams SP;
