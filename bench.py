@@ -357,19 +357,24 @@ def run_cofi(args):
         ops.profile_start()
         for _ in range(2):
             eng._step_eager()
-        prof = ops.profile_stop()
+        # contractions are split per call at the ridge of the tf32 tensor roof (half the measured bf16 rate) and the HBM roof
+        prof = ops.profile_stop(ridge=0.5 * tf_sust * 1e12 / (hbm * 1e9))
     model.fork_image_stream = True
     # kernel families: every tcgen05 GEMM entry point (plain / +column statistics / fp16 operands / +LayerNorm) is the
     # same kernel template (gemm_tc_kernel); the two KPConv aggregate variants likewise
     fam = {}
     for name, d in prof.items():
-        key = "cofi_gemm*" if name.startswith("cofi_gemm") else ("cofi_kpconv_aggregate*" if name.startswith("cofi_kpconv_aggregate") else name)
+        base, _, bound = name.partition("|")
+        key = "cofi_gemm*" if base.startswith("cofi_gemm") else ("cofi_kpconv_aggregate*" if base.startswith("cofi_kpconv_aggregate") else base)
+        if bound:
+            key += " [" + bound + "-bound calls]"
         f = fam.setdefault(key, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
         for k in f:
             f[k] += d[k]
     tot_ms = sum(d["ms"] for d in fam.values())
     name, d = max(fam.items(), key=lambda kv: kv[1]["ms"])
-    tensor_ops = ("cofi_gemm*", "cofi_conv2d_nhwc", "cofi_attention_vt", "cofi_attention", "cofi_sim_argmin")
+    tensor_ops = ("cofi_gemm* [tensor-bound calls]", "cofi_conv2d_nhwc [tensor-bound calls]", "cofi_attention_vt", "cofi_attention",
+                  "cofi_sim_argmin")
     if name in tensor_ops:
         ach = d["flops"] / (d["ms"] / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust}
@@ -382,7 +387,7 @@ def run_cofi(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(name)
+            traffic = json.load(f).get(name.split(" [")[0])   # ncu average over ALL launches of the kernel family
     roof.update({"traffic": traffic, "kernel": name, "launches_profiled": d["calls"],
                  "avg_launch_us": 1000.0 * d["ms"] / d["calls"], "share_of_step": d["ms"] / tot_ms,
                  "peak_source": peaks_src + (" (bf16 dense sustained; the family runs tf32 (nominal peak = half of bf16) and "

@@ -49,13 +49,18 @@ def profile_start() -> None:
     _prof = []
 
 
-def profile_stop():
-    """-> {op: dict(calls, ms, flops, bytes)} (synchronises)."""
+def profile_stop(ridge: Optional[float] = None):
+    """-> {op: dict(calls, ms, flops, bytes)} (synchronises).  With `ridge` (flop per byte at which the tensor roof meets the
+    HBM roof) the contraction entry points are split per call into "<op>|tensor" (arithmetic intensity above the ridge) and
+    "<op>|hbm": one entry point serves both the K <= 128 streaming contractions and the large-K ones, and a single
+    roofline for the mix would describe neither."""
     global _prof
     rec, _prof = _prof, None
     torch.cuda.synchronize()
     out = {}
     for name, e0, e1, fl, by in rec:
+        if ridge is not None and (name.startswith("cofi_gemm") or name.startswith("cofi_conv2d")) and by > 0:
+            name = name + ("|tensor" if fl / by > ridge else "|hbm")
         d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
         d["calls"] += 1
         d["ms"] += e0.elapsed_time(e1)

@@ -208,3 +208,25 @@ def test_engine_builds_tables_on_device():
             assert torch.equal(x, y)
     hb = b.host_buffers(batch)
     assert hb["neighbors"] == [] and b.upload(hb) < 2 * (4096 * 2 * 3 * 4 + 4096 * 16 + 3 * 160 * 512 * 4) + 4096
+
+
+def test_precompute_point_cloud_cuda_surface():
+    """The reference's second builder (model/kpconv/preprocess_data.py:145-203): half-sampling without replacement and the
+    expanded-form `knn()` ranking.  open3d's private RNG cannot be reproduced, so the check is on the returned pyramid:
+    every level is a subset of the previous one without duplicates, and the 13 tables are the oracle's for those levels."""
+    import model.kpconv.preprocess_data as pp
+    from oracle import knn as ok
+    rng = np.random.default_rng(21)
+    pts = (rng.normal(size=(3, 2048)) * np.array([[15.0], [1.5], [15.0]])).astype(np.float32)
+    np.random.seed(3)
+    out = pp.precompute_point_cloud_cuda(pts, None, None, lengths=2048, num_stages=5, device="cpu")
+    assert out["lengths"] == [2048, 1024, 512, 256, 128]
+    levels = [p.numpy() for p in out["points"]]
+    assert not out["points"][0].is_cuda and np.array_equal(levels[0], pts.T)
+    for a, b in zip(levels[:-1], levels[1:]):
+        assert b.shape[0] == a.shape[0] // 2 and np.unique(b, axis=0).shape[0] == b.shape[0]
+        assert set(map(tuple, b.tolist())) <= set(map(tuple, a.tolist()))
+    want = ok.pyramid_tables(levels, 128, ok.EXPANDED)
+    for name in ("neighbors", "subsampling", "upsampling"):
+        for i, t in enumerate(want[name]):
+            assert np.array_equal(out[name][i].numpy(), t), (name, i)
