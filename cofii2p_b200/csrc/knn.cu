@@ -445,6 +445,54 @@ __global__ void __launch_bounds__(QWARPS * 32) knn_query_kernel(const __grid_con
     const int ht = min(home >> 5, T - 1);
     const int s0 = max(0, min(ht - 1, T - 4)), s1 = min(T, s0 + 4);
     const int r0 = max(0, s0 - 4), r1 = min(T, s1 + 4);
+    const float4* gmin = S.smin + (size_t)frame * S.nsup;
+    const float4* gmax = S.smax + (size_t)frame * S.nsup;
+
+    if (J.k == 1) {
+        // Nearest neighbour only (the up-sampling tables of the engine: the model reads column 0, reference
+        // model/kpconv/functional.py:20): no candidate buffer, no sorting network -- the running best key is a warp-wide
+        // minimum (two redux.sync per tile), the seeds give the first bound, one culled sweep does the rest.
+        auto open1 = [&](int t) {
+            const float4 s = __ldg(ssort + ((size_t)t << 5) + lane);
+            const int si = __float_as_int(s.w);
+            const float d = dist2<MODE>(qx, qy, qz, qq, s);
+            const unsigned hi = si >= 0 ? __float_as_uint(d) : 0xffffffffu;
+            const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+            const unsigned ml = __reduce_min_sync(0xffffffffu, (hi == mh && si >= 0) ? (unsigned)si : 0xffffffffu);
+            const u64 m = ((u64)mh << 32) | ml;
+            if (m < w.thresh) w.thresh = m;
+        };
+        for (int t = s0; t < s1; ++t) open1(t);
+        for (int gb = 0; gb < S.nsup; gb += 32) {
+            bool gok = gb + lane < S.nsup;
+            if (gok && P.cull) {
+                float smax;
+                const float d = knn_box_dist(gmin, gmax, gb + lane, qx, qy, qz, smax);
+                gok = knn_box_pass<MODE>(w, d, qq, smax);
+            }
+            unsigned gm = __ballot_sync(0xffffffffu, gok);
+            while (gm) {
+                const int rd = gb + __ffs(gm) - 1;
+                gm &= gm - 1;
+                const int t = (rd << 5) + lane;
+                bool ok = t < T && (t < s0 || t >= s1);
+                if (ok && P.cull) {
+                    float smax;
+                    const float d = knn_box_dist(tmin, tmax, t, qx, qy, qz, smax);
+                    ok = knn_box_pass<MODE>(w, d, qq, smax);
+                }
+                unsigned m = __ballot_sync(0xffffffffu, ok);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    open1((rd << 5) + b);
+                }
+            }
+        }
+        if (lane == 0)
+            J.out[(size_t)frame * Q.n + qi] = w.thresh == KMAX ? (int64_t)ns : (int64_t)(unsigned)w.thresh;
+        return;
+    }
 
     // Four phases through one loop body (the unrolled merge network exists twice in the code: overflow and phase end):
     //   0  seeds: the 4 tiles around the query's position in the source order, no culling
@@ -455,8 +503,6 @@ __global__ void __launch_bounds__(QWARPS * 32) knn_query_kernel(const __grid_con
     //      close to final
     //   3  second sweep: whatever else the tightened k-th key still admits
     // Pending candidates are folded in when the buffer could overflow and at the end of every phase.
-    const float4* gmin = S.smin + (size_t)frame * S.nsup;
-    const float4* gmax = S.smax + (size_t)frame * S.nsup;
     float near_d = INFINITY;
     for (int phase = 0; phase < 4; ++phase) {
         if (phase == 2 && P.cull && w.thresh != KMAX)
