@@ -157,6 +157,7 @@ struct Params {
     Epilogue ep;
     // convolution geometry (CONV only)
     int Ho, Wo, Cin, cpt /* 32-channel chunks per tap */, KW, pad, tiles_w, tiles_per_img;
+    int tma_store;    // dense output with 16-byte aligned rows: tiles leave through TMA stores (tmC), else per-thread stores
     float* stat_out;  // optional [row tiles][N][2] per-tile column (sum, sum of squares) of the stored output
     int dbg;  // COFI_TC_DEBUG bits (perf triage only): 1 = skip global stores, 2 = skip TMA+MMA
 };
@@ -181,7 +182,8 @@ struct Cfg {
 
 template <int BN, bool CONV, bool X3, bool HALF = false>
 __global__ void __launch_bounds__(Cfg<BN, X3>::THREADS)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const Params p) {
     using C = Cfg<BN, X3>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -328,6 +330,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float* rrow = has_res ? ep.residual + grow * ep.ldres : nullptr;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         float* stage = reinterpret_cast<float*>(smem) + (set * 4 + q) * (32 * 36);  // ring is idle once tmem_full fired
+        // TMA-store path: two [32 rows][128 B] SWIZZLE_128B buffers per warp (1024-byte aligned), alternating per chunk
+        float* tstage = reinterpret_cast<float*>(smem) + (set * 4 + q) * 2048;
+        const bool tma_st = !CONV && p.tma_store != 0;
+        int tbuf = 0;
         const bool rvec_ok = has_res && ((ep.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
         const bool has_ln = ep.ln_gamma != nullptr;  // host guarantees gridDim.y == 1 and N <= BN
         float ln_mean = 0.0f, ln_rstd = 1.0f;
@@ -366,6 +372,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
             tmem_ld_wait();
             const int nb = n0 + c0;
+            float* tb = tstage + tbuf * 1024;
+            if (tma_st) {  // the store issued from this buffer two chunks ago must have read it
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+            }
             if (row_ok && nb < p.N && !(p.dbg & 4)) {
                 const bool full = nb + 32 <= p.N;
                 float v[32];
@@ -437,11 +448,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
                 }
                 // fallthrough to the staged store below
-                float* st = stage + lane * 36;
+                if (tma_st) {
+                    float* trow = tb + lane * 32;  // row `lane` of the box; 16-byte chunk j lands at j ^ (row & 7)
+                    const int swz = lane & 7;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(st + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(trow + ((j ^ swz) << 2)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+                    float* st = stage + lane * 36;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(st + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
             }
+            if (tma_st) fence_proxy_async_smem();  // staged rows -> visible to the TMA engine
             __syncwarp();
             if (p.stat_out) {
                 // per-tile column statistics for the GroupNorm that follows (host guarantees M % 128 == 0, act none):
@@ -450,7 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (nb + lane < p.N) {
 #pragma unroll 8
                     for (int rr = 0; rr < 32; ++rr) {
-                        const float x = stage[rr * 36 + lane];
+                        const float x = tma_st ? tb[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))] : stage[rr * 36 + lane];
                         cs += x;
                         cq = fmaf(x, x, cq);
                     }
@@ -460,7 +481,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             // transposed write-out: 8 lanes cover the 32 columns (128 B) of one row, 4 rows per instruction, so every
             // store instruction writes four full 128-byte lines (the per-thread-row layout would scatter 16-byte pieces)
-            if (nb < p.N && !(p.dbg & 5)) {
+            if (tma_st) {
+                // one bulk tensor store per 32 x 32 chunk: rows past M and columns past N are clipped by the TMA unit
+                if (nb < p.N && !(p.dbg & 5) && lane == 0) {
+                    tma_store_2d(&tmC, tb, nb, (int)m0 + q * 32);
+                    bulk_commit();
+                }
+                tbuf ^= 1;
+            } else if (nb < p.N && !(p.dbg & 5)) {
                 const bool full = nb + 32 <= p.N;
                 const int cc = (lane & 7) * 4;
                 // dense case: row (q*32 + lane/8 + 4*it) of the tile -> one running pointer, no per-store address arithmetic
@@ -507,6 +535,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 o[1] = cq;
             }
         }
+        if (tma_st) {  // shared memory must outlive the reads of the last stores
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+        }
         tc_fence_before();
     } else if (X3) {
         // ================================ operand splitters (3xTF32) ==================
@@ -547,7 +579,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, bool CONV, bool X3, bool HALF = false>
-static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const Params& p, dim3 grid, cudaStream_t st) {
+static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p_in, dim3 grid,
+                      cudaStream_t st) {
+    Params p = p_in;
+    p.tma_store = (c != nullptr && !CONV) ? 1 : 0;
+    if (!c) c = a;  // placeholder, never dereferenced by the kernel
     using C = Cfg<BN, X3>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -559,21 +595,21 @@ static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const Params& 
         }
         attr_done = true;
     }
-    gemm_tc_kernel<BN, CONV, X3, HALF><<<grid, C::THREADS, C::SMEM, st>>>(*a, *b, p);
+    gemm_tc_kernel<BN, CONV, X3, HALF><<<grid, C::THREADS, C::SMEM, st>>>(*a, *b, *c, p);
     return check_launch(CONV ? "cofi_conv2d_nhwc(tcgen05)" : "cofi_gemm(tcgen05)");
 }
 
 template <bool CONV>
-static int dispatch(const CUtensorMap* a, const CUtensorMap* b, const Params& p, int bn, bool x3, dim3 grid,
-                    cudaStream_t st) {
+static int dispatch(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p, int bn, bool x3,
+                    dim3 grid, cudaStream_t st) {
     if (x3) {
-        if (bn == 32) return launch_one<32, CONV, true>(a, b, p, grid, st);
-        if (bn == 64) return launch_one<64, CONV, true>(a, b, p, grid, st);
-        return launch_one<128, CONV, true>(a, b, p, grid, st);
+        if (bn == 32) return launch_one<32, CONV, true>(a, b, c, p, grid, st);
+        if (bn == 64) return launch_one<64, CONV, true>(a, b, c, p, grid, st);
+        return launch_one<128, CONV, true>(a, b, c, p, grid, st);
     }
-    if (bn == 32) return launch_one<32, CONV, false>(a, b, p, grid, st);
-    if (bn == 64) return launch_one<64, CONV, false>(a, b, p, grid, st);
-    return launch_one<128, CONV, false>(a, b, p, grid, st);
+    if (bn == 32) return launch_one<32, CONV, false>(a, b, c, p, grid, st);
+    if (bn == 64) return launch_one<64, CONV, false>(a, b, c, p, grid, st);
+    return launch_one<128, CONV, false>(a, b, c, p, grid, st);
 }
 
 static int tc_debug() {
@@ -608,6 +644,20 @@ bool gemm_tc_supported(int64_t lda, int64_t ldw, int64_t ldc, int64_t M, int N, 
     return tc::encode_fn() != nullptr;
 }
 
+// Output tensor map for the TMA-store epilogue: [M, N] fp32 with row pitch ldc, 32 x 32 boxes, SWIZZLE_128B.  nullptr when
+// the rows are not 16-byte aligned (the kernel then stores from registers through its transposing staging area) or when
+// COFI_TMA_STORE=0.
+static const CUtensorMap* c_tmap(const float* C, int64_t ldc, int64_t M, int N) {
+    static const bool on = [] {
+        const char* e = getenv("COFI_TMA_STORE");
+        return !(e && e[0] == '0');
+    }();
+    if (!on || (ldc & 3) || ((uintptr_t)C & 15) || ldc < N) return nullptr;
+    uint64_t d[2] = {(uint64_t)N, (uint64_t)M}, s[1] = {(uint64_t)ldc * 4};
+    uint32_t b[2] = {32, 32};
+    return tc::get_tmap_f32(C, 2, d, s, b);
+}
+
 int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
                    int K, const Epilogue& ep, int engine, cudaStream_t st, float* stat_out) {
     using namespace tc;
@@ -629,7 +679,7 @@ int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, flo
     p.stat_out = stat_out;
     p.dbg = tc_debug();
     dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
-    return dispatch<false>(ta, tb, p, bn, engine == COFI_GEMM_TF32X3, grid, st);
+    return dispatch<false>(ta, tb, c_tmap(C, ldc, M, N), p, bn, engine == COFI_GEMM_TF32X3, grid, st);
 }
 
 // fp16-operand GEMM (A [M,K] half, W [N,K] half, fp32 accumulate/output): KPConv weight-apply on the tf32 engine.
@@ -655,9 +705,10 @@ int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, f
     p.stat_out = stat_out;
     p.dbg = tc_debug();
     dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
-    if (bn == 32) return launch_one<32, false, false, true>(ta, tb, p, grid, st);
-    if (bn == 64) return launch_one<64, false, false, true>(ta, tb, p, grid, st);
-    return launch_one<128, false, false, true>(ta, tb, p, grid, st);
+    const CUtensorMap* tc_map = c_tmap(C, ldc, M, N);
+    if (bn == 32) return launch_one<32, false, false, true>(ta, tb, tc_map, p, grid, st);
+    if (bn == 64) return launch_one<64, false, false, true>(ta, tb, tc_map, p, grid, st);
+    return launch_one<128, false, false, true>(ta, tb, tc_map, p, grid, st);
 }
 
 // ---------------------------------------------------------------------------------------------- conv entry
@@ -700,7 +751,7 @@ int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w,
     p.tiles_w = Wo / CONV_TW;
     p.tiles_per_img = p.tiles_w * (Ho / CONV_TH);
     dim3 grid((unsigned)(B * p.tiles_per_img), (unsigned)ceil_div(Cout, bn));
-    return dispatch<true>(ta, tb, p, bn, engine == COFI_GEMM_TF32X3, grid, st);
+    return dispatch<true>(ta, tb, nullptr, p, bn, engine == COFI_GEMM_TF32X3, grid, st);
 }
 
 }  // namespace cofi
