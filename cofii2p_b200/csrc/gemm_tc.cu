@@ -102,7 +102,12 @@ static const CUtensorMap* get_tmap_any(const void* base, int rank, const uint64_
         return nullptr;
     }
     if (cache.size() > 8192) {  // pointers churn only outside CUDA graphs; bound the cache
-        for (auto& kv : cache) delete kv.second;
+        // descriptors handed out a moment ago (the A/W maps of the launch being assembled) must stay valid: retired maps
+        // are freed one generation later
+        static std::vector<CUtensorMap*> retired;
+        for (CUtensorMap* m : retired) delete m;
+        retired.clear();
+        for (auto& kv : cache) retired.push_back(kv.second);
         cache.clear();
     }
     CUtensorMap* m = new CUtensorMap;
