@@ -68,21 +68,46 @@ def linear(x, w, b=None, act: int = ACT_NONE):
     return _Linear.apply(x.contiguous(), w, b, act)
 
 
+class _LinearStats(torch.autograd.Function):
+    """Linear whose GEMM epilogue also emits the per-128-row-tile column statistics of the output (tf32 engine): the
+    GroupNorm that follows (norm_rows_pre) needs no statistics pass over the activation.  Backward = _Linear's."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        y, st = ops.gemm_colstats(x, w, bias=b)
+        ctx.act = ACT_NONE
+        ctx.save_for_backward(x, w, None)
+        ctx.has_bias = b is not None
+        ctx.mark_non_differentiable(st)
+        return y, st
+
+    @staticmethod
+    def backward(ctx, dy, _dst):
+        return _Linear.backward(ctx, dy)[:3]
+
+
+def linear_stats(x, w, b=None):
+    return _LinearStats.apply(x.contiguous(), w, b)
+
+
 # ------------------------------------------------------------------------------------------------ KPConv
 class _KPConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, weights, bias, q_points, s_points, nbr, kernel_points, sigma, frames, kp_reach):
+    def forward(ctx, feats, weights, bias, q_points, s_points, nbr, kernel_points, sigma, frames, kp_reach, want_stats=False):
         K, C, Co = weights.shape
         packed = ops.pack_points(s_points, feats)
         agg, cnt = ops.kpconv_aggregate(feats, packed, q_points, nbr, kernel_points, sigma, frames, kp_reach)
         wt = ops.transpose2d(weights.reshape(K * C, Co))
-        y = ops.gemm(agg, wt, bias=bias, rowdiv=cnt)
         ctx.save_for_backward(feats, weights, q_points, s_points, nbr, kernel_points, cnt)
         ctx.meta = (float(sigma), int(frames), float(kp_reach), bias is not None)
-        return y
+        if want_stats:  # the weight-apply GEMM's epilogue feeds the GroupNorm that follows
+            y, st = ops.gemm_colstats(agg, wt, bias=bias, rowdiv=cnt)
+            ctx.mark_non_differentiable(st)
+            return y, st
+        return ops.gemm(agg, wt, bias=bias, rowdiv=cnt)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dst=None):
         feats, weights, q_points, s_points, nbr, kernel_points, cnt = ctx.saved_tensors
         sigma, frames, kp_reach, has_bias = ctx.meta
         K, C, Co = weights.shape
@@ -98,11 +123,13 @@ class _KPConv(torch.autograd.Function):
             dfeats = ops.kpconv_aggregate_bwd(dagg, C, packed, q_points, nbr, kernel_points, sigma, frames, kp_reach)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
-        return dfeats, dw, db, None, None, None, None, None, None, None
+        return dfeats, dw, db, None, None, None, None, None, None, None, None
 
 
-def kpconv(feats, weights, bias, q_points, s_points, nbr, kernel_points, sigma, frames, kp_reach):
-    return _KPConv.apply(feats.contiguous(), weights, bias, q_points, s_points, nbr, kernel_points, sigma, frames, kp_reach)
+def kpconv(feats, weights, bias, q_points, s_points, nbr, kernel_points, sigma, frames, kp_reach, want_stats=False):
+    """want_stats (tf32 engine, whole 128-row tiles per frame): returns (y, tile statistics) for norm_rows_pre."""
+    return _KPConv.apply(feats.contiguous(), weights, bias, q_points, s_points, nbr, kernel_points, sigma, frames, kp_reach,
+                         bool(want_stats))
 
 
 # ------------------------------------------------------------------------------------------------ normalisations
@@ -122,6 +149,29 @@ class _NormRows(torch.autograd.Function):
         frames, groups, eps, act, has_res = ctx.meta
         dx, dres, dgamma, dbeta = ops.norm_rows_bwd(x, dy.contiguous(), y, mr, frames, groups, gamma, act, has_res)
         return dx, dgamma, dbeta, dres, None, None, None, None
+
+
+class _NormRowsPre(torch.autograd.Function):
+    """GroupNorm on statistics that came out of the producing GEMM's epilogue; backward identical to _NormRows."""
+
+    @staticmethod
+    def forward(ctx, x, tile_stats, gamma, beta, residual, frames, groups, eps, act):
+        y, mr = ops.norm_rows_pre(x, tile_stats, frames, groups, gamma, beta, eps, residual=residual, act=act, return_mr=True)
+        ctx.save_for_backward(x, gamma, y, mr)
+        ctx.meta = (frames, groups, eps, act, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, y, mr = ctx.saved_tensors
+        frames, groups, eps, act, has_res = ctx.meta
+        dx, dres, dgamma, dbeta = ops.norm_rows_bwd(x, dy.contiguous(), y, mr, frames, groups, gamma, act, has_res)
+        return dx, None, dgamma, dbeta, dres, None, None, None, None
+
+
+def norm_rows_pre(x, tile_stats, frames, groups, gamma, beta, eps=1e-5, residual=None, act=ACT_NONE):
+    return _NormRowsPre.apply(x.contiguous(), tile_stats, gamma, beta, None if residual is None else residual.contiguous(),
+                              frames, groups, eps, act)
 
 
 def norm_rows(x, frames, groups, gamma=None, beta=None, eps=1e-5, residual=None, act=ACT_NONE, return_stats=False):

@@ -64,6 +64,9 @@ class KPConv(nn.Module):
     def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1, want_stats: bool = False):
         """s_feats [B*N,Cin], q_points [B*M,3], s_points [B*N,3], neighbor_indices [B*M,H] -> [B*M,Cout]."""
         if ad.active(self):  # training: differentiable kernels (fp32 aggregate, engine-selected GEMMs)
+            if want_stats and ops.colstats_ok(q_points.shape[0], frames, self.out_channels):
+                return ad.kpconv(s_feats, self.weights, self.bias, q_points, s_points, neighbor_indices, self.kernel_points,
+                                 self.sigma, frames, self.kp_reach(), want_stats=True)
             out = ad.kpconv(s_feats, self.weights, self.bias, q_points, s_points, neighbor_indices, self.kernel_points,
                             self.sigma, frames, self.kp_reach())
             return (out, None) if want_stats else out

@@ -23,6 +23,9 @@ class GroupNorm(nn.Module):
 
     def forward(self, x, frames: int = 1, act: int = ops.ACT_NONE, residual=None, tile_stats=None):
         if ad.active(self):
+            if tile_stats is not None:
+                return ad.norm_rows_pre(x, tile_stats, frames, self.num_groups, self.norm.weight, self.norm.bias, self.norm.eps,
+                                        residual, act)
             return ad.norm_rows(x, frames, self.num_groups, self.norm.weight, self.norm.bias, self.norm.eps, residual, act)
         if tile_stats is not None:  # statistics came out of the producing GEMM's epilogue
             return ops.norm_rows_pre(x, tile_stats, frames, self.num_groups, self.norm.weight, self.norm.bias, self.norm.eps,
@@ -51,6 +54,9 @@ class UnaryBlock(nn.Module):
         if final_act is not None:
             act = final_act
         if ad.active(self):
+            if ops.colstats_ok(x.shape[0], frames, self.out_channels):
+                y, st = ad.linear_stats(x, self.mlp.weight, self.mlp.bias)
+                return self.norm(y, frames, act=act, residual=residual, tile_stats=st)
             return self.norm(ad.linear(x, self.mlp.weight, self.mlp.bias), frames, act=act, residual=residual)
         if ops.colstats_ok(x.shape[0], frames, self.out_channels):
             y, st = ops.gemm_colstats(x, self.mlp.weight, bias=self.mlp.bias)

@@ -292,7 +292,10 @@ def colstats_ok(rows: int, frames: int, n: int) -> bool:
     return _engine == ENGINE_TF32 and rows % frames == 0 and (rows // frames) % 128 == 0 and n >= 16 and n % 4 == 0
 
 
-def norm_rows_pre(x, stats, frames: int, groups: int, gamma, beta, eps: float = 1e-5, residual=None, act: int = ACT_NONE):
+def norm_rows_pre(x, stats, frames: int, groups: int, gamma, beta, eps: float = 1e-5, residual=None, act: int = ACT_NONE,
+                  return_mr: bool = False):
+    """GroupNorm whose statistics come from the producing GEMM's epilogue (`stats` of gemm_colstats).  return_mr: also the
+    (mean, rstd) per (frame, group) [frames*groups, 2] the finalize kernel derived -- what cofi_norm_rows_bwd consumes."""
     x, ldx = _rows(x, "x")
     rows, C = x.shape
     y = torch.empty((rows, C), dtype=torch.float32, device=x.device)
@@ -303,7 +306,7 @@ def norm_rows_pre(x, stats, frames: int, groups: int, gamma, beta, eps: float = 
     _meta(4.0 * rows * C, 4.0 * rows * C * (2 + (residual is not None)))
     _call("cofi_norm_rows_pre", _p(x), ldx, rows // frames, C, frames, groups, _p(gamma), _p(beta), float(eps), _p(residual), ldr,
           act, _p(y), C, _p(stats), _p(ws), _st())
-    return y
+    return (y, ws.view(frames * groups, 2)) if return_mr else y
 
 
 def gemm_ln(a, w, gamma, beta, eps: float = 1e-5, bias=None, act: int = ACT_NONE, residual=None,
