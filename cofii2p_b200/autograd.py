@@ -98,7 +98,9 @@ class _KPConv(torch.autograd.Function):
         packed = ops.pack_points(s_points, feats)
         agg, cnt = ops.kpconv_aggregate(feats, packed, q_points, nbr, kernel_points, sigma, frames, kp_reach)
         wt = ops.transpose2d(weights.reshape(K * C, Co))
-        ctx.save_for_backward(feats, weights, q_points, s_points, nbr, kernel_points, cnt)
+        # the aggregate [M, K*C] and the packed points are kept for the backward instead of being recomputed: a few GB
+        # per step, nothing next to 180 GB of HBM, and no extra traffic (the tensors exist anyway)
+        ctx.save_for_backward(feats, weights, q_points, s_points, nbr, kernel_points, cnt, agg, packed)
         ctx.meta = (float(sigma), int(frames), float(kp_reach), bias is not None)
         if want_stats:  # the weight-apply GEMM's epilogue feeds the GroupNorm that follows
             y, st = ops.gemm_colstats(agg, wt, bias=bias, rowdiv=cnt)
@@ -108,15 +110,13 @@ class _KPConv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dst=None):
-        feats, weights, q_points, s_points, nbr, kernel_points, cnt = ctx.saved_tensors
+        feats, weights, q_points, s_points, nbr, kernel_points, cnt, agg, packed = ctx.saved_tensors
         sigma, frames, kp_reach, has_bias = ctx.meta
         K, C, Co = weights.shape
         dy = dy.contiguous()
         g = ops.rowscale(dy, cnt)                                   # d(acc) = dY / cnt
-        packed = ops.pack_points(s_points, feats)
         dfeats = dw = db = None
         if ctx.needs_input_grad[1]:
-            agg, _ = ops.kpconv_aggregate(feats, packed, q_points, nbr, kernel_points, sigma, frames, kp_reach)
             dw = ops.gemm_tn(agg, g).view(K, C, Co)                 # agg^T g = d weights.reshape(K*C, Co)
         if ctx.needs_input_grad[0]:
             dagg = ops.gemm(g, weights.reshape(K * C, Co))          # g W^T with W stored as [K*C, Co]
