@@ -382,3 +382,31 @@ def test_reorder_relabelling_is_consistent():
     x = torch.randn(d["points"][4].shape[0], 3)
     assert torch.equal(reorder.unpermute_rows(reorder._rows(x, perms[4]), perms[4]), x)
     assert torch.equal(d1["feats"], reorder._rows(d["feats"], perms[0]))
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines committed under profiles/ (written by bench.py on the B200) carry every key of the measurement
+    contract: metric/value/unit, e2e with host<->device byte counts, gpu_launches, roofline, cpu_baseline, clocks."""
+    for name, impl in (("r1_bench_infer_n1_final.json", None), ("r1_bench_train_n1_final.json", None),
+                       ("r1_bench_reference_arm.json", "reference")):
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            d = json.loads(f.readline())
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+            assert k in d, (name, k)
+        assert d["unit"] == "frames/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+        assert "workload" in d["config"] and d["data"] == "synthetic"
+        for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+            assert k in d["e2e"], (name, k)
+        for k in ("value", "unit", "cores", "kind", "sample"):
+            assert k in d["cpu_baseline"], (name, k)
+        if impl == "reference":
+            assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0
+            continue
+        assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+        r = d["roofline"]
+        for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+            assert k in r, (name, k)
+        assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
