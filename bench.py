@@ -5,10 +5,13 @@
     python bench.py --impl reference --gpus N --steps K ...   # CPU arm: oracle port of the reference forward
 
 A "step" is one pass of the hot path over one batch of B=8 synthetic KITTI-shaped frames per GPU
-(BASELINE.json configs[1]: 3x160x512 image + 20480-point cloud with 5-level KNN-128 tables), `val`-style
-forward (encoders + transformer + heads + decoder + patch/feature gathers).  Inference shards by frames: with N
-GPUs every rank runs its own B frames, no data-path collective ("replicas only", weak scaling).  One JSON line
-is printed by rank 0; see DESIGN.md section "Measurement" for every field.
+(BASELINE.json configs[1]: 3x160x512 image + 20480-point cloud with 5-level KNN-128 tables) in the mode the
+reference's evaluation runs, `test` (evaluation/eval_all.py:96): encoders + transformer + heads + decoder + the whole
+matching stage (fused similarity + arg-min on the tensor cores with exact re-rank, threshold loop, point2node, patch /
+feature gathers, 16-way fine match).  Inference shards by frames: with N GPUs every rank runs its own B frames, no
+data-path collective ("replicas only", weak scaling); the same line carries the data-parallel TRAINING step
+(BASELINE.json configs[4]: 4 frames per GPU, NCCL gradient all-reduce) as `train`.  One JSON line is printed by rank 0;
+see DESIGN.md section "Measurement" for every field.
 """
 from __future__ import annotations
 
@@ -42,7 +45,12 @@ def parse():
     ap.add_argument("--train-batch", type=int, default=4, help="training frames per GPU per step (configs[4])")
     ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
     ap.add_argument("--num-pc", type=int, default=20480)
-    ap.add_argument("--engine", default=os.environ.get("COFI_ENGINE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--engine", default=os.environ.get("COFI_ENGINE", "tf32"), choices=["fp32", "tf32", "tf32x3", "mixed"])
+    ap.add_argument("--mode", default="test", choices=["test", "val"], help="forward mode of the timed step")
+    ap.add_argument("--parity-engine", default="tf32x3", choices=["fp32", "tf32x3", "none"],
+                    help="second leg on the engine that meets the 1e-3 / exact-correspondence parity bar")
+    ap.add_argument("--no-train-leg", action="store_true", help="skip the data-parallel training leg (configs[4])")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip val-mode / host-table extra keys")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-from-points", action="store_true", help="skip the leg that builds the KNN tables on the device")
@@ -126,9 +134,9 @@ def pick_cpu_threads(sd):
     with torch.no_grad():
         for c in cands:
             torch.set_num_threads(c)
-            restate.forward(sd, *[f[k] for k in ARGS], "val", run_dead=True)
+            restate.forward(sd, *[f[k] for k in ARGS], "test", run_dead=True)
             t = time.perf_counter()
-            restate.forward(sd, *[f[k] for k in ARGS], "val", run_dead=True)
+            restate.forward(sd, *[f[k] for k in ARGS], "test", run_dead=True)
             dt = time.perf_counter() - t
             if dt < best_t:
                 best, best_t = c, dt
@@ -136,7 +144,7 @@ def pick_cpu_threads(sd):
     return best, cands
 
 
-def cpu_forward_baseline(sd, num_pc, n_frames, mode="val"):
+def cpu_forward_baseline(sd, num_pc, n_frames, mode="test"):
     """The reference forward (oracle port, incl. the dead layer3/layer4 work the reference executes) on the host
     cores at the best thread count: bounded sample of the same workload, one frame per forward as the reference runs."""
     from cofii2p_b200.frames import make_frame
@@ -154,7 +162,7 @@ def cpu_forward_baseline(sd, num_pc, n_frames, mode="val"):
     return times
 
 
-def torch_eager_gpu_baseline(sd, num_pc, n_frames, dev, mode="val"):
+def torch_eager_gpu_baseline(sd, num_pc, n_frames, dev, mode="test"):
     """Secondary baseline of the cpu_baseline leg: the same oracle port executed by stock PyTorch
     on the B200 (ATen / cuDNN / cuBLAS eager kernels, one frame per forward as the reference runs) -- what the
     reference's own code gets from this GPU without this library.  Returns seconds per frame."""
@@ -178,16 +186,19 @@ def torch_eager_gpu_baseline(sd, num_pc, n_frames, dev, mode="val"):
 
 # ------------------------------------------------------------------------------------------------ arms
 def run_reference(args):
+    """CPU arm: the oracle port of the reference forward in the SAME mode as the product arm (`test`), one 20480-point
+    frame per step, at the host's best thread count.  Nothing of the product library is loaded by this process."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from cofii2p_b200.model.network import CoFiI2P
+    from cofii2p_b200.model.network import CoFiI2P          # class definition only (state_dict keys): ops loads lazily
     from cofii2p_b200.options import Options_KITTI
     from cofii2p_b200.weights import seeded_state_dict
     from cofii2p_b200.frames import make_frame
     from oracle import restate
     m = CoFiI2P(Options_KITTI())
     sd = seeded_state_dict(m, 0)
+    del m
     cores, cands = pick_cpu_threads(sd)
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     frames = [make_frame(100 + i, num_pc=args.num_pc, cache_dir="/tmp/cofi_frames", device=dev)
@@ -195,27 +206,61 @@ def run_reference(args):
     with torch.no_grad():
         for i in range(args.warmup):
             f = frames[i % len(frames)]
-            restate.forward(sd, *[f[k] for k in ARGS], "val", run_dead=True)
+            restate.forward(sd, *[f[k] for k in ARGS], args.mode, run_dead=True)
         t0 = time.perf_counter()
         for i in range(args.steps):
             f = frames[(args.warmup + i) % len(frames)]
-            restate.forward(sd, *[f[k] for k in ARGS], "val", run_dead=True)
+            restate.forward(sd, *[f[k] for k in ARGS], args.mode, run_dead=True)
         dt = time.perf_counter() - t0
     fps = args.steps / dt
+    from cofii2p_b200 import lib as _l
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "reference CoFiI2P.forward(val) on CPU, one 20480-pt frame per step "
-                               "(bounded sample of configs[1])", "num_pc": args.num_pc, "frames_per_step": 1},
+        "config": {"workload": f"reference CoFiI2P.forward({args.mode}) on CPU, one 20480-pt frame per step "
+                               "(bounded sample of configs[1]; the product arm stacks 8 such frames per step -- frames/s "
+                               "is the common unit)", "num_pc": args.num_pc, "frames_per_step": 1, "mode": args.mode},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} frames, oracle/restate.py forward incl. dead layer3/4, "
+                         "sample": f"{args.steps} frames, oracle/restate.py forward({args.mode}) incl. dead layer3/4, "
                                    f"torch {torch.__version__} CPU, best of thread counts {cands} on a "
                                    f"{os.cpu_count()}-core host -> {torch.get_num_threads()} threads"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "product_library_loaded": _l._lib is not None,
     }
     print(json.dumps(line), flush=True)
+
+
+def golden_parity(model, dev):
+    """Measured parity of the CURRENT engine against the REAL reference's frozen outputs (tests/golden, 20480-point frame,
+    produced by oracle/make_golden.py from /root/reference): max relative error of the four dense outputs and of the
+    fine patches / point features, and whether the selected correspondences are identical."""
+    import numpy as np
+    from cofii2p_b200.frames import frame_to, make_frame
+    path = os.path.join(ROOT, "tests", "golden", "frame_s0_n20480.npz")
+    if not os.path.isfile(path):
+        return {"unavailable": "tests/golden/frame_s0_n20480.npz missing"}
+    z = np.load(path)
+    f = frame_to(make_frame(0, num_pc=20480, cache_dir="/tmp/cofi_frames", device=str(dev)), dev)
+    with torch.no_grad():
+        out = model(*[f[k] for k in ARGS], "test")
+    names = ["img_feature_norm", "pc_feature_norm", "coarse_img_score", "coarse_pc_score"]
+    rel = lambda a, b: float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+    errs = {nm: rel(out[i], torch.from_numpy(z["val/" + nm])) for i, nm in enumerate(names)}
+    gxy, gpts = torch.from_numpy(z["test/fine_center_xy"]), torch.from_numpy(z["test/coarse_pc_points"])
+    xy, pts = out[6].cpu(), out[7].cpu()
+    same = bool(xy.shape == gxy.shape and torch.equal(xy, gxy) and torch.equal(pts, gpts))
+    res = {"max_rel_err": max(errs.values()), "rel_err": errs, "correspondences_identical": same,
+           "matches": int(xy.shape[1]), "matches_reference": int(gxy.shape[1])}
+    if same:
+        for i, nm in ((4, "fine_img_feature_patch"), (5, "fine_pc_inline_feature")):
+            res["rel_err"][nm] = rel(out[i], torch.from_numpy(z["test/" + nm]))
+        res["max_rel_err"] = max(res["rel_err"].values())
+    else:  # agreement of the two correspondence sets (rows = (x, y, X, Y, Z))
+        a = {tuple(r) for r in torch.cat([xy.t(), pts], 1).tolist()}
+        b = {tuple(r) for r in torch.cat([gxy.t(), gpts], 1).tolist()}
+        res["correspondence_iou"] = len(a & b) / max(len(a | b), 1)
+    return res
 
 
 def run_cofi(args):
@@ -228,18 +273,16 @@ def run_cofi(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from cofii2p_b200 import lib, ops
-    from cofii2p_b200.engine import InferenceEngine
+    from cofii2p_b200.engine import InferenceEngine, PipelinedEngine
     from cofii2p_b200.frames import make_frame, stack_frames
 
     ops.set_engine(args.engine)
     model, sd = build_model(dev)
-    B = args.batch
+    B, mode = args.batch, args.mode
     frames = [make_frame(rank * B + i, num_pc=args.num_pc, cache_dir="/tmp/cofi_frames", device=f"cuda:{local}")
               for i in range(B)]
     batch = stack_frames(frames)
-    eng = InferenceEngine(model, batch, mode="val", use_graph=not args.no_graph)
-    host = eng.host_buffers(batch)
-    stream = eng.stream
+    frames_total = world * B * args.steps
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -247,19 +290,11 @@ def run_cofi(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(steps):
-                fn()
-            e1.record(stream)
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    def max_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def timed_on(st, fn, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -270,83 +305,93 @@ def run_cofi(args):
                 fn()
             e1.record(st)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return max_ranks(e0.elapsed_time(e1))
 
-    # ---- device-resident throughput (inputs already in HBM) -------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        eng.run()
-    clocks = ClockSampler(local)
-    ms_total = timed(eng.run, args.steps)
-    clk = clocks.stop()
-    frames_total = world * B * args.steps
-    value = frames_total / (ms_total / 1000.0)
+    def resident_fps(tables, md, warm=None):
+        """frames/s of graph replays with the step's inputs already resident in HBM -> (fps, ms/step, launches/step)"""
+        e = InferenceEngine(model, batch, mode=md, use_graph=not args.no_graph, tables=tables)
+        for _ in range(max(args.warmup, 3) if warm is None else warm):
+            e.run()
+        ms = timed_on(e.stream, e.run, args.steps)
+        lp = e.launches_per_step
+        stats = e.sim_stats.tolist() if md == "test" else None
+        del e
+        return frames_total / (ms / 1e3), ms / args.steps, lp, stats
 
-    # ---- end to end: pinned host buffers -> H2D -> forward -> D2H (double-buffered public API) ---------
-    from cofii2p_b200.engine import PipelinedEngine
-    pipe = PipelinedEngine(model, batch, depth=2)
-    hosts = [host, eng.host_buffers(batch)]  # two pinned staging copies, as a loader with prefetch would own
-    io = {"in": 0, "out": 0}
-    for i in range(3):
-        pipe.step(hosts[i % 2])
-    pipe.synchronize()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall = time.perf_counter()
-    e0.record(pipe.h2d)
-    for i in range(args.steps):
-        io["in"], io["out"] = pipe.step(hosts[i % 2])
-    pipe.compute.wait_stream(pipe.h2d)
-    pipe.d2h.wait_stream(pipe.compute)
-    e1.record(pipe.d2h)
-    pipe.synchronize()
-    wall_ms = (time.perf_counter() - t_wall) * 1e3
-    barrier()
-    ms_e2e_t = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_e2e_t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms_e2e_t.item())
-    e2e_value = frames_total / (ms_e2e / 1000.0)
-    pipe.last_results()  # validates the err flag / keeps the API honest
-    del pipe
-
-    # ---- the same pipeline fed with the point pyramid only: the 13 KNN-128 tables are built on the device inside the
-    # graph (csrc/knn.cu) instead of being computed on the host and shipped over PCIe -------
-    from_points = None
-    if not args.no_from_points:
-        eng_p = InferenceEngine(model, batch, mode="val", use_graph=not args.no_graph, tables="device")
-        for _ in range(3):
-            eng_p.run()
-        ms_p = timed_on(eng_p.stream, eng_p.run, args.steps)
-        lp = eng_p.launches_per_step
-        del eng_p
-        pipe = PipelinedEngine(model, batch, depth=2, tables="device")
-        hosts_p = [pipe.engines[0].host_buffers(batch), pipe.engines[0].host_buffers(batch)]
+    def pipelined_fps(tables, md):
+        """frames/s end to end through the public API: pinned host batch -> H2D || graph replay || D2H, double-buffered"""
+        pipe = PipelinedEngine(model, batch, depth=2, tables=tables, mode=md)
+        hosts = [pipe.engines[0].host_buffers(batch), pipe.engines[0].host_buffers(batch)]  # a prefetching loader's two slots
         for i in range(3):
-            pipe.step(hosts_p[i % 2])
+            pipe.step(hosts[i % 2])
         pipe.synchronize()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
         e0.record(pipe.h2d)
+        nin = nout = 0
         for i in range(args.steps):
-            pin, pout = pipe.step(hosts_p[i % 2])
+            nin, nout = pipe.step(hosts[i % 2])
         pipe.compute.wait_stream(pipe.h2d)
         pipe.d2h.wait_stream(pipe.compute)
         e1.record(pipe.d2h)
         pipe.synchronize()
+        wall_ms = (time.perf_counter() - t_wall) * 1e3
         barrier()
-        ms_pe = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms_pe, op=dist.ReduceOp.MAX)
-        from_points = {"value": frames_total / (ms_p / 1000.0), "e2e": frames_total / (float(ms_pe.item()) / 1000.0),
-                       "unit": UNIT, "h2d_bytes_per_step": pin, "d2h_bytes_per_step": pout, "launches_per_step": lp,
-                       "what": "same forward, inputs = point pyramid + image only; the KNN-128 index tables (neighbors, "
-                               "subsampling: 128 columns; upsampling: its single live column) are built by cofi_knn_pyramid "
-                               "inside the captured graph"}
-        pipe.last_results()
+        ms = max_ranks(max(e0.elapsed_time(e1), 0.0))
+        pipe.last_results()  # validates the err flag / match counts, keeps the API honest
         del pipe
+        return {"value": frames_total / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": nin, "d2h_bytes_per_step": nout,
+                "ms_per_step": ms / args.steps, "wall_ms_per_step": wall_ms / args.steps}
+
+    # ---- headline: device-resident throughput, test-mode step, index tables resident (what the reference arm is handed) --
+    eng = InferenceEngine(model, batch, mode=mode, use_graph=not args.no_graph)
+    for _ in range(max(args.warmup, 3)):
+        eng.run()
+    clocks = ClockSampler(local)
+    ms_total = timed_on(eng.stream, eng.run, args.steps)
+    clk = clocks.stop()
+    value = frames_total / (ms_total / 1000.0)
+    sim_stats = eng.sim_stats.tolist() if mode == "test" else None
+    runs = max(args.warmup, 3) + args.steps + 2   # + the two eager warm-ups of the capture
+    stream = eng.stream
+
+    # ---- end to end (the parsed e2e): point pyramid + image from pinned host memory, KNN tables built on the device in
+    # the graph (csrc/knn.cu, SURVEY.md section 8 row f1), results back to pinned host memory ----------------------------
+    e2e = pipelined_fps("device", mode)
+    e2e["api"] = ("cofii2p_b200.engine.PipelinedEngine(tables='device', mode='%s').step(pinned host batch): H2D of the point "
+                  "pyramid + features + image || graph replay (KNN-128 tables built on the device, forward, matching) || D2H of "
+                  "every output" % mode)
+    fp_value, fp_ms, fp_launches, _ = resident_fps("device", mode)
+    from_points = {"value": fp_value, "ms_per_step": fp_ms, "unit": UNIT, "launches_per_step": fp_launches,
+                   "what": "device-resident throughput of the e2e pipeline's graph: same step with the 13 KNN-128 index tables "
+                           "(neighbors, subsampling: 128 columns; upsampling: its single live column) built by cofi_knn_pyramid "
+                           "inside the captured graph from the point pyramid"}
+
+    extra = {}
+    if not args.no_extra_legs:
+        ht = pipelined_fps("host", mode)
+        ht["what"] = "end to end with the index tables computed on the host and shipped over PCIe every step (int64, as the " \
+                     "reference's data loader supplies them)"
+        extra["host_tables_e2e"] = ht
+        other = "val" if mode == "test" else "test"
+        v, ms_o, lp_o, _ = resident_fps("host", other)
+        extra[other + "_mode"] = {"value": v, "ms_per_step": ms_o, "unit": UNIT, "launches_per_step": lp_o,
+                                  "what": f"device-resident throughput of the {other}-mode step (round-1 headline was val)"}
+
+    # ---- parity, measured: this engine and the parity-grade engine against the real reference's golden outputs --------
+    parity = {"engine": args.engine, **golden_parity(model, dev),
+              "what": "forward(test) of this engine on the 20480-point golden frame vs outputs frozen from the real reference"}
+    parity_engine = None
+    if args.parity_engine != "none" and args.parity_engine != args.engine:
+        ops.set_engine(args.parity_engine)
+        pv, pms, plp, _ = resident_fps("host", mode)
+        pe2e = pipelined_fps("device", mode)
+        parity_engine = {"engine": args.parity_engine, "value": pv, "ms_per_step": pms, "unit": UNIT, "launches_per_step": plp,
+                         "e2e": pe2e["value"], "e2e_ms_per_step": pe2e["ms_per_step"], **golden_parity(model, dev),
+                         "what": "the same step on the engine that meets the north star's parity bar (<= 1e-3 relative, "
+                                 "correspondences bit-exact)"}
+        ops.set_engine(args.engine)
 
     # ---- roofline of the dominant kernel family: eager pass bracketed by CUDA events per launch --------
     hbm, tf_burst, tf_sust, peaks_src = measured_peaks()
@@ -360,6 +405,8 @@ def run_cofi(args):
         # contractions are split per call at the ridge of the tf32 tensor roof (half the measured bf16 rate) and the HBM roof
         prof = ops.profile_stop(ridge=0.5 * tf_sust * 1e12 / (hbm * 1e9))
     model.fork_image_stream = True
+    launches_per_step = eng.launches_per_step
+    del eng
     # kernel families: every tcgen05 GEMM entry point (plain / +column statistics / fp16 operands / +LayerNorm) is the
     # same kernel template (gemm_tc_kernel); the two KPConv aggregate variants likewise
     fam = {}
@@ -374,25 +421,51 @@ def run_cofi(args):
     tot_ms = sum(d["ms"] for d in fam.values())
     name, d = max(fam.items(), key=lambda kv: kv[1]["ms"])
     tensor_ops = ("cofi_gemm* [tensor-bound calls]", "cofi_conv2d_nhwc [tensor-bound calls]", "cofi_attention_vt", "cofi_attention",
-                  "cofi_sim_argmin")
+                  "cofi_sim_argmin", "cofi_sim_argmin_exact")
     if name in tensor_ops:
         ach = d["flops"] / (d["ms"] / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust}
     else:
         ach = d["bytes"] / (d["ms"] / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
-    # the family mixes tensor-bound (large K) and HBM-bound (K <= 128) launches: report the other roof too
     roof["hbm_gbs_same_family"] = d["bytes"] / (d["ms"] / 1e3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(name.split(" [")[0])   # ncu average over ALL launches of the kernel family
-    roof.update({"traffic": traffic, "kernel": name, "launches_profiled": d["calls"],
-                 "avg_launch_us": 1000.0 * d["ms"] / d["calls"], "share_of_step": d["ms"] / tot_ms,
+    # ncu DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), averaged over THE SAME launches the family
+    # above consists of: profiles/traffic.json is keyed by the family names used here (tools/ncu_traffic.py)
+    traffic, tsrc = None, None
+    for tname in ("r2_traffic.json", "traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj.get(name, tj.get(name.split(" [")[0]) if tname == "traffic.json" else None)
+            tsrc = "profiles/" + tname + ("" if name in tj else " (family average over all launches of the entry point)")
+            if traffic is not None:
+                break
+    roof.update({"traffic": traffic, "traffic_source": tsrc, "kernel": name, "launches_profiled": d["calls"],
+                 "algorithmic_bytes_per_launch": d["bytes"] / d["calls"], "avg_launch_us": 1000.0 * d["ms"] / d["calls"],
+                 "share_of_step": d["ms"] / tot_ms,
                  "peak_source": peaks_src + (" (bf16 dense sustained; the family runs tf32 (nominal peak = half of bf16) and "
                                              "fp16 operands)" if name in tensor_ops else " (copy bandwidth)"),
                  "by_kernel_ms_per_step": {k: round(v["ms"] / 2, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}})
+    sim = fam.get("cofi_sim_argmin_exact")
+    if sim is not None:  # the north star's fused similarity kernel, as it runs inside this step (launch-latency sized)
+        roof["similarity_kernel"] = {"calls_per_step": sim["calls"] // 2, "us_per_call": 1e3 * sim["ms"] / sim["calls"],
+                                     "tflops": sim["flops"] / (sim["ms"] / 1e3) / 1e12, "frac_of_bf16_burst": sim["flops"] / (sim["ms"] / 1e3) / 1e12 / tf_burst,
+                                     "what": "tcgen05 fp16 candidate pass + exact fp32 re-rank over 8 x 1280 x 1280 x 128; the "
+                                             "full-size sweep point (10240 x 20480 x 64) is in profiles/r2_sim_bench.jsonl"}
+
+    # ---- data-parallel training leg (BASELINE.json configs[4]) in the same line: what north_star splits across GPUs ------
+    train = None
+    if not args.no_train_leg:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_bench
+        torch.cuda.empty_cache()
+        try:
+            train = train_bench.train_leg(args, dev, world, rank, local)
+        except Exception as e:  # the training leg must never take the headline measurement down
+            train = {"unavailable": repr(e)[:300]}
+        ops.set_engine(args.engine)
+        model.eval()
 
     if rank != 0:
         if world > 1:
@@ -401,33 +474,42 @@ def run_cofi(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.engine], "data": "synthetic",
+        "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "mixed": "tf32+tf32x3"}[args.engine], "data": "synthetic",
         "config": {"workload": "configs[1]: single-GPU inference, batch=8 synthetic KITTI frames (3x160x512 img, "
-                               "20480x3 cloud, 5-level KNN-128 tables), val-style forward",
-                   "frames_per_gpu_per_step": B, "num_pc": args.num_pc, "engine": args.engine,
-                   "cuda_graph": not args.no_graph, "parallelism": f"replicas x{world}",
+                               f"20480x3 cloud, 5-level KNN-128 tables), {mode}-mode forward incl. the matching stage "
+                               "(evaluation/eval_all.py:96)",
+                   "frames_per_gpu_per_step": B, "num_pc": args.num_pc, "engine": args.engine, "policy": ops.get_policy(),
+                   "mode": mode, "cuda_graph": not args.no_graph, "parallelism": f"replicas x{world}",
                    "l2": "inputs larger than L2 (index tables 0.49 GB per step vs 126 MB L2)"},
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io["in"], "d2h_bytes_per_step": io["out"],
-                "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-                "api": "cofii2p_b200.engine.PipelinedEngine.step(pinned host batch): H2D || graph replay || D2H"},
-        "gpu_launches": eng.launches_per_step * args.steps,
-        "launches_per_step": eng.launches_per_step,
+        "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
         "roofline": roof,
+        "from_points": from_points,
+        "parity": parity,
     }
-    if from_points is not None:
-        line["from_points"] = from_points
+    if sim_stats is not None:
+        line["matching"] = {"reranked_candidates_per_point": sim_stats[0] / max(runs * B * (args.num_pc // 16), 1),
+                            "full_scan_rows": sim_stats[1],
+                            "what": "tcgen05 similarity pass -> exact fp32 re-rank: candidates evaluated per super-point, rows "
+                                    "whose candidate list overflowed (accumulated over every run of the headline engine)"}
+    if parity_engine is not None:
+        line["parity_engine"] = parity_engine
+    if train is not None:
+        line["train"] = train
+    line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
         cpu_sd = {k: v.detach().cpu() for k, v in sd.items()}
         cores, cands = pick_cpu_threads(cpu_sd)
-        times = cpu_forward_baseline(cpu_sd, args.num_pc, args.cpu_frames)
+        times = cpu_forward_baseline(cpu_sd, args.num_pc, args.cpu_frames, mode)
         fps = len(times) / sum(times)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{len(times)} frames (after 1 warm-up) of the same 20480-pt workload, "
-                                          f"oracle/restate.py forward(val) incl. dead layer3/4; best of thread counts "
+                                          f"oracle/restate.py forward({mode}) incl. dead layer3/4; best of thread counts "
                                           f"{cands} on a {os.cpu_count()}-core host -> {cores} threads"}
         try:
-            tg = torch_eager_gpu_baseline(cpu_sd, args.num_pc, 5, dev)
+            tg = torch_eager_gpu_baseline(cpu_sd, args.num_pc, 5, dev, mode)
             line["cpu_baseline"]["torch_eager_b200"] = {
                 "value": len(tg) / sum(tg), "unit": UNIT,
                 "sample": f"{len(tg)} frames after 2 warm-ups: the same oracle port run by stock PyTorch eager kernels "

@@ -127,6 +127,15 @@ sim_argmin_simt_kernel(const float* __restrict__ pt, int64_t ldpt, const float* 
 }
 
 // --------------------------------------------------------------------------------------- select_matches
+// reference model/network.py:145-151 (threshold loop 0.9, 0.88, ... until >= min_count matches survive) + :181-187
+// (score >= thr, border mask on the arg-min pixel, compaction in point order).  One CTA per frame, no host round trip:
+//   1. level(p) = first threshold index t with score[p] >= thr[t] (thresholds descend, so p passes every later one);
+//      histogram of the levels of the border-masked points, prefix sum -> first t whose count reaches min_count;
+//   2. ordered compaction (ballot + warp/block prefix) of the points passing thr[t];
+//   3. rows n..Npt-1 of the fixed-size outputs are padded with a valid dummy (index 0, centre (2,2)*xy_scale) so that the
+//      downstream fixed-shape kernels of a captured graph touch only valid memory; the count says how many rows are real.
+constexpr int SEL_MAXTHR = 128;
+
 __global__ void __launch_bounds__(1024)
 select_matches_kernel(const float* __restrict__ score, const int64_t* __restrict__ best_idx, int64_t Npt, int gridH,
                       int gridW, int xmax, int ymax, const float* __restrict__ thresholds, int nthr, int min_count,
@@ -135,45 +144,82 @@ select_matches_kernel(const float* __restrict__ score, const int64_t* __restrict
     const int frame = blockIdx.x;
     const float* sc = score + (int64_t)frame * Npt;
     const int64_t* bi = best_idx + (int64_t)frame * Npt;
-    __shared__ int s_sum;
-    int chosen = nthr - 1;
-    for (int t = 0; t < nthr; ++t) {
-        const float thr = thresholds[t];
-        int local = 0;
-        for (int64_t p = threadIdx.x; p < Npt; p += blockDim.x) {
-            const int x = (int)(bi[p] % gridW), y = (int)(bi[p] / gridW);
-            const bool m = (x >= 2) && (x <= xmax) && (y <= ymax) && (y >= 2);
-            local += (sc[p] >= thr && m) ? 1 : 0;
-        }
-        if (threadIdx.x == 0) s_sum = 0;
-        __syncthreads();
-        if (local) atomicAdd(&s_sum, local);
-        __syncthreads();
-        const int total = s_sum;  // block-uniform
-        __syncthreads();
-        if (total >= min_count) {
-            chosen = t;
-            break;
+    __shared__ float s_thr[SEL_MAXTHR];
+    __shared__ int s_hist[SEL_MAXTHR];
+    __shared__ int s_warp[32];
+    __shared__ int s_chosen, s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < nthr; t += blockDim.x) {
+        s_thr[t] = thresholds[t];
+        s_hist[t] = 0;
+    }
+    __syncthreads();
+    for (int64_t p = tid; p < Npt; p += blockDim.x) {
+        const int x = (int)(bi[p] % gridW), y = (int)(bi[p] / gridW);
+        const bool m = (x >= 2) && (x <= xmax) && (y <= ymax) && (y >= 2);
+        if (m) {
+            const float v = sc[p];
+            int t = 0;
+            while (t < nthr && !(v >= s_thr[t])) ++t;
+            if (t < nthr) atomicAdd(&s_hist[t], 1);
         }
     }
-    if (threadIdx.x == 0) {
-        const int s_thr = chosen;
-        const float thr = thresholds[s_thr];
-        int n = 0;
-        int64_t* oi = out_index + (int64_t)frame * Npt;
-        float* ox = out_xy + (int64_t)frame * 2 * Npt;
-        for (int64_t p = 0; p < Npt; ++p) {
-            const int x = (int)(bi[p] % gridW), y = (int)(bi[p] / gridW);
-            const bool m = (x >= 2) && (x <= xmax) && (y <= ymax) && (y >= 2);
-            if (sc[p] >= thr && m) {
-                oi[n] = p;
-                ox[n] = (float)x * xy_scale;
-                ox[Npt + n] = (float)y * xy_scale;
-                ++n;
+    __syncthreads();
+    if (tid == 0) {
+        int chosen = nthr - 1, acc = 0;
+        for (int t = 0; t < nthr; ++t) {
+            acc += s_hist[t];
+            if (acc >= min_count) {
+                chosen = t;
+                break;
             }
         }
+        s_chosen = chosen;
+        s_base = 0;
+    }
+    __syncthreads();
+    const int chosen = s_chosen;
+    const float thr = s_thr[chosen];
+    int64_t* oi = out_index + (int64_t)frame * Npt;
+    float* ox = out_xy + (int64_t)frame * 2 * Npt;
+    for (int64_t p0 = 0; p0 < Npt; p0 += blockDim.x) {
+        const int64_t p = p0 + tid;
+        bool keep = false;
+        int x = 0, y = 0;
+        if (p < Npt) {
+            x = (int)(bi[p] % gridW);
+            y = (int)(bi[p] / gridW);
+            const bool m = (x >= 2) && (x <= xmax) && (y <= ymax) && (y >= 2);
+            keep = m && (sc[p] >= thr);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (keep) {
+            const int n = before + __popc(bal & ((1u << lane) - 1u));
+            oi[n] = p;
+            ox[n] = (float)x * xy_scale;
+            ox[Npt + n] = (float)y * xy_scale;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_warp[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    const int n = s_base;
+    for (int64_t p = n + tid; p < Npt; p += blockDim.x) {
+        oi[p] = 0;
+        ox[p] = 2.0f * xy_scale;
+        ox[Npt + p] = 2.0f * xy_scale;
+    }
+    if (tid == 0) {
         out_count[frame * 2 + 0] = n;
-        out_count[frame * 2 + 1] = s_thr;
+        out_count[frame * 2 + 1] = chosen;
     }
 }
 
@@ -183,6 +229,9 @@ nn_argmin_kernel(const float* __restrict__ points, int64_t n, const float* __res
                  int64_t* __restrict__ idx) {
     const int64_t i = blockIdx.x;
     if (i >= n) return;
+    points += (int64_t)blockIdx.y * n * 3;   // frame-local clouds and indices
+    nodes += (int64_t)blockIdx.y * M * 3;
+    idx += (int64_t)blockIdx.y * n;
     const float px = points[i * 3], py = points[i * 3 + 1], pz = points[i * 3 + 2];
     const float sp = __fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz));
     float bv = INFINITY;
@@ -230,12 +279,20 @@ nn_argmin_kernel(const float* __restrict__ points, int64_t n, const float* __res
 // ------------------------------------------------------------------------------------------ extract_patch
 __global__ void __launch_bounds__(256)
 extract_patch_kernel(const float* __restrict__ map, int H, int W, int C, int b, const float* __restrict__ centers,
-                     int64_t n, float* __restrict__ out, int32_t* __restrict__ err_flag) {
-    const int64_t total = n * C * 16;
+                     int64_t n, float* __restrict__ out, int32_t* __restrict__ err_flag, int frames = 1) {
+    const int64_t per = n * C * 16, total = per * frames;
+    const float* centers0 = centers;
+    float* out0 = out;
+    const int b0 = b;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(t % C);            // channel fastest for coalesced NHWC reads
-        const int64_t r = t / C;
+        const int f = (int)(t / per);          // batched form: frame f reads centres [f,2,n], map image b0+f
+        const int64_t tf = t - (int64_t)f * per;
+        centers = centers0 + (int64_t)f * 2 * n;
+        out = out0 + (int64_t)f * per;
+        b = b0 + f;
+        const int c = (int)(tf % C);           // channel fastest for coalesced NHWC reads
+        const int64_t r = tf / C;
         const int pix = (int)(r % 16);
         const int64_t i = r / 16;
         const int dy = pix >> 2, dx = pix & 3;
@@ -332,7 +389,8 @@ extern "C" int cofi_select_matches(const float* score, const int64_t* best_idx, 
                                    int gridW, int xmax, int ymax, const float* thresholds, int nthr, int min_count,
                                    float xy_scale, int32_t* out_count, int64_t* out_index, float* out_xy, void* stream) {
     COFI_REQUIRE(score && best_idx && thresholds && out_count && out_index && out_xy, "cofi_select_matches: null pointer");
-    COFI_REQUIRE(Npt > 0 && frames > 0 && nthr > 0 && gridH > 4 && gridW > 4, "cofi_select_matches: bad shape");
+    COFI_REQUIRE(Npt > 0 && frames > 0 && nthr > 0 && nthr <= SEL_MAXTHR && gridH > 4 && gridW > 4,
+                 "cofi_select_matches: bad shape (at most %d thresholds)", SEL_MAXTHR);
     select_matches_kernel<<<frames, 1024, 0, (cudaStream_t)stream>>>(score, best_idx, Npt, gridH, gridW, xmax, ymax,
                                                                     thresholds, nthr, min_count, xy_scale, out_count, out_index,
                                                                     out_xy);
@@ -345,6 +403,24 @@ extern "C" int cofi_nn_argmin(const float* points, int64_t n, const float* nodes
     if (n == 0) return COFI_OK;
     nn_argmin_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(points, n, nodes, M, idx);
     return check_launch("cofi_nn_argmin");
+}
+
+extern "C" int cofi_nn_argmin_batched(const float* points, int64_t n, const float* nodes, int64_t M, int frames,
+                                      int64_t* idx, void* stream) {
+    COFI_REQUIRE(points && nodes && idx && n >= 0 && M > 0 && frames > 0 && frames < 65536, "cofi_nn_argmin_batched: bad argument");
+    if (n == 0) return COFI_OK;
+    nn_argmin_kernel<<<dim3((unsigned)n, (unsigned)frames), 256, 0, (cudaStream_t)stream>>>(points, n, nodes, M, idx);
+    return check_launch("cofi_nn_argmin_batched");
+}
+
+extern "C" int cofi_extract_patch_batched(const float* map, int H, int W, int C, int frames, const float* centers,
+                                          int64_t n, float* out, int32_t* err_flag, void* stream) {
+    COFI_REQUIRE(map && centers && out && H >= 4 && W >= 4 && C > 0 && frames > 0 && n >= 0,
+                 "cofi_extract_patch_batched: bad argument");
+    if (n == 0) return COFI_OK;
+    extract_patch_kernel<<<ew_blocks(n * C * 16 * frames, 256), 256, 0, (cudaStream_t)stream>>>(map, H, W, C, 0, centers, n,
+                                                                                               out, err_flag, frames);
+    return check_launch("cofi_extract_patch_batched");
 }
 
 extern "C" int cofi_extract_patch(const float* map, int H, int W, int C, int b, const float* centers, int64_t n,

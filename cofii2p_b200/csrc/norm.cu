@@ -6,6 +6,8 @@
 // passes (partials -> apply), no atomics.
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace cofi {
@@ -371,7 +373,7 @@ layer_norm_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, i
 
 __global__ void __launch_bounds__(128)
 l2norm_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C, const float* __restrict__ add,
-                   int64_t ldadd, float* __restrict__ y, int64_t ldy) {
+                   int64_t ldadd, float* __restrict__ y, int64_t ldy, __half* __restrict__ yh = nullptr, int64_t ldh = 0) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -388,6 +390,7 @@ l2norm_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C
         float v = __ldg(p + c) / denom;
         if (add) v += __ldg(add + row * ldadd + c);
         y[row * ldy + c] = v;
+        if (yh) yh[row * ldh + c] = __float2half_rn(v);
     }
 }
 
@@ -559,6 +562,16 @@ extern "C" int cofi_l2norm_rows(const float* x, int64_t ldx, int64_t rows, int C
     l2norm_rows_kernel<<<(unsigned)ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, add,
                                                                                             ldadd, y, ldy);
     return check_launch("cofi_l2norm_rows");
+}
+
+extern "C" int cofi_l2norm_rows_f16(const float* x, int64_t ldx, int64_t rows, int C, float* y, int64_t ldy, void* y_f16,
+                                    int64_t ldh, void* stream) {
+    COFI_REQUIRE(x && y && y_f16 && C > 0, "cofi_l2norm_rows_f16: bad argument");
+    if (rows == 0) return COFI_OK;
+    const int wpb = 4;
+    l2norm_rows_kernel<<<(unsigned)ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        x, ldx, rows, C, nullptr, 0, y, ldy, reinterpret_cast<__half*>(y_f16), ldh);
+    return check_launch("cofi_l2norm_rows_f16");
 }
 
 extern "C" int64_t cofi_colnorm_workspace(int frames, int C) {

@@ -22,6 +22,11 @@ constexpr int S16_MH = 128, S16_N = 128, S16_K = 64;       // fp16 elements per 
 constexpr int S16_SLOT = S16_N * 128;                      // 16 KB per k-block tile
 constexpr int S16_RING = 6, S16_MAXKB = 2;                 // C <= 128
 constexpr int S16_SMEM = 2 * S16_MAXKB * S16_SLOT + S16_RING * S16_SLOT + 1024 + 256;
+// exact mode: every epilogue thread (= one point row) keeps the pixels whose fp16 score lies within `margin` of its running
+// best -- the only pixels that can win the exact fp32 comparison -- in a shared-memory list of S16_CAP entries
+constexpr int S16_CAP = 16;
+constexpr int S16_ROWS = 2 * S16_MH;
+constexpr int S16_SMEM_CAND = S16_SMEM + S16_CAP * S16_ROWS * 8;
 
 struct Sim16Params {
     int64_t* best_idx;
@@ -31,8 +36,24 @@ struct Sim16Params {
     int num_tiles;       // pixel tiles in total
     int tiles_per_split; // pixel tiles handled by one CTA (blockIdx.z selects the range)
     int64_t split_stride; // rows of the output per split (frames * Npt) when partial results are written
+    // exact mode (CAND): per (split, row) candidate lists for sim_rerank_kernel
+    float margin;          // 2 * (bound of |fp16 score - exact fp32 score|) for unit-norm rows
+    const float* bound2;   // optional device [2]: max |pt row|^2, max |px row|^2 (scales the margin); null = rows have norm <= 1
+    int32_t* cand_idx;     // [nsplit, rows, S16_CAP]
+    float* cand_val;       // [nsplit, rows, S16_CAP]
+    int32_t* cand_cnt;     // [nsplit, rows]   (-1 = list overflowed: the re-rank scans the whole row exactly)
 };
 
+// margin = 2 x bound(|fp16-engine score - exact fp32 total|) + the resolution of d = fl(1 - total): for |total| < 0.5 the
+// subtraction quantises to 2^-24 (2^-23 above 1), so pixels whose totals differ by less than that can TIE in d, and the
+// exact engine then takes the lowest index -- they must all be candidates.
+__device__ __forceinline__ float sim_margin(float base, const float* bound2) {
+    float m = base;
+    if (bound2) m = base * sqrtf(bound2[0] * bound2[1]);
+    return m + 2.5e-7f;
+}
+
+template <bool CAND>
 __global__ void __launch_bounds__(320)
 sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const Sim16Params p) {
@@ -47,6 +68,8 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t* s_full = empty + S16_RING;   // [2]
     uint64_t* s_empty = s_full + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+    float* lv = reinterpret_cast<float*>(smem + S16_SMEM - 1024);   // [S16_CAP][S16_ROWS] (CAND only; past the 1 KB align slack)
+    int* li = reinterpret_cast<int*>(lv + S16_CAP * S16_ROWS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int frame = blockIdx.y;
@@ -126,6 +149,10 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         float best = -INFINITY;
         int bidx = 0;
+        const float margin = CAND ? sim_margin(p.margin, p.bound2) : 0.0f;
+        float thr = -INFINITY;   // best - margin
+        int cnt = 0;
+        bool ovf = false;
         for (int j = 0; j < ntl; ++j) {
             const int b = j & 1;
             mbar_wait(&s_full[b], (uint32_t)(j >> 1) & 1u);
@@ -149,7 +176,40 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 for (int i = 0; i < 8; ++i) m01[i] = fmaxf(m01[i], m01[i + 8]);
                 const float cm = fmaxf(fmaxf(fmaxf(m01[0], m01[1]), fmaxf(m01[2], m01[3])),
                                        fmaxf(fmaxf(m01[4], m01[5]), fmaxf(m01[6], m01[7])));
-                if (cm > best) {  // rare once the running best has warmed up; strict > keeps the lowest index on ties
+                if (CAND) {
+                    if (cm > thr) {  // some score of this chunk is within the margin of the running best
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float v = __uint_as_float(raw[i]);
+                            if (v > thr) {
+                                if (v > best) {
+                                    best = v;
+                                    bidx = base + c * 32 + i;
+                                    thr = best - margin;
+                                }
+                                if (cnt == S16_CAP) {  // compact: drop what fell out of the margin since it was appended
+                                    int k2 = 0;
+                                    for (int k = 0; k < S16_CAP; ++k) {
+                                        const float ov = lv[k * S16_ROWS + r];
+                                        if (ov > thr) {
+                                            lv[k2 * S16_ROWS + r] = ov;
+                                            li[k2 * S16_ROWS + r] = li[k * S16_ROWS + r];
+                                            ++k2;
+                                        }
+                                    }
+                                    cnt = k2;
+                                    if (cnt == S16_CAP) {
+                                        ovf = true;
+                                        cnt = S16_CAP - 1;
+                                    }
+                                }
+                                lv[cnt * S16_ROWS + r] = v;
+                                li[cnt * S16_ROWS + r] = base + c * 32 + i;
+                                ++cnt;
+                            }
+                        }
+                    }
+                } else if (cm > best) {  // rare once the running best has warmed up; strict > keeps the lowest index on ties
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float v = __uint_as_float(raw[i]);
@@ -168,7 +228,19 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (m0 + r < p.Npt) {
             const int64_t o = (int64_t)blockIdx.z * p.split_stride + (int64_t)frame * p.Npt + m0 + r;
             p.best_idx[o] = bidx;
-            p.best_val[o] = 1.0f - best;
+            p.best_val[o] = CAND ? best : 1.0f - best;   // CAND: the raw fp16-engine score (the re-rank thresholds on it)
+            if (CAND) {
+                int k2 = 0;
+                for (int k = 0; k < cnt; ++k) {
+                    const float ov = lv[k * S16_ROWS + r];
+                    if (ov > thr) {
+                        p.cand_val[o * S16_CAP + k2] = ov;
+                        p.cand_idx[o * S16_CAP + k2] = li[k * S16_ROWS + r];
+                        ++k2;
+                    }
+                }
+                p.cand_cnt[o] = ovf ? -1 : k2;
+            }
         }
     }
     __syncthreads();
@@ -209,6 +281,121 @@ cast_f16_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C, _
     }
 }
 
+// ---------------------------------------------------------------------------------------------- exact re-rank
+// The arithmetic of sim_argmin_simt_kernel (match.cu), i.e. of the reference's `1 - torch.sum(img * pc, dim=0)`
+// (model/network.py:174): rounded products, ATen's cascade sum over the channel axis (groups of 16, sequential inside and
+// across groups), d = 1 - total.  One warp per point row; lanes take the row's candidates (or, after a list overflow / an
+// empty list, every pixel) and the warp keeps the lexicographic minimum of (d, pixel index).
+__device__ __forceinline__ float sim_exact_d(const float* __restrict__ spt, const float* __restrict__ r, int C) {
+    float tot = 0.0f;
+    for (int c0 = 0; c0 < C; c0 += 16) {
+        float g = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(r + c0 + c));
+            g = __fadd_rn(g, __fmul_rn(a.x, spt[c0 + c + 0]));
+            g = __fadd_rn(g, __fmul_rn(a.y, spt[c0 + c + 1]));
+            g = __fadd_rn(g, __fmul_rn(a.z, spt[c0 + c + 2]));
+            g = __fadd_rn(g, __fmul_rn(a.w, spt[c0 + c + 3]));
+        }
+        tot = __fadd_rn(tot, g);
+    }
+    return __fsub_rn(1.0f, tot);
+}
+
+constexpr int RR_WARPS = 8, RR_MAXC = 128;
+
+__global__ void __launch_bounds__(RR_WARPS * 32)
+sim_rerank_kernel(const float* __restrict__ pt, int64_t ldpt, const float* __restrict__ px, int64_t ldpx, int64_t Npt,
+                  int64_t Npx, int C, int64_t rows, int nsplit, float margin_base, const float* __restrict__ bound2,
+                  const float* __restrict__ part_best, const int32_t* __restrict__ cand_idx,
+                  const float* __restrict__ cand_val, const int32_t* __restrict__ cand_cnt,
+                  int64_t* __restrict__ best_idx, float* __restrict__ best_val, int32_t* __restrict__ stats) {
+    __shared__ float spt_all[RR_WARPS][RR_MAXC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * RR_WARPS + warp;
+    if (row >= rows) return;
+    float* spt = spt_all[warp];
+    const int64_t frame = row / Npt;
+    const float* pxb = px + frame * Npx * ldpx;
+    for (int c = lane; c < C; c += 32) spt[c] = __ldg(pt + row * ldpt + c);
+    __syncwarp();
+    float gmax = -INFINITY;
+    bool ovf = false;
+    for (int s = 0; s < nsplit; ++s) {
+        gmax = fmaxf(gmax, part_best[(int64_t)s * rows + row]);
+        ovf |= cand_cnt[(int64_t)s * rows + row] < 0;
+    }
+    const float thr = gmax - sim_margin(margin_base, bound2);
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
+    int evaluated = 0;
+    if (!ovf) {
+        for (int slot = lane; slot < nsplit * S16_CAP; slot += 32) {
+            const int s = slot / S16_CAP, k = slot - s * S16_CAP;
+            const int64_t o = (int64_t)s * rows + row;
+            if (k < cand_cnt[o] && cand_val[o * S16_CAP + k] > thr) {
+                const int x = cand_idx[o * S16_CAP + k];
+                const float d = sim_exact_d(spt, pxb + (int64_t)x * ldpx, C);
+                ++evaluated;
+                if (d < bd || (d == bd && x < bi)) {
+                    bd = d;
+                    bi = x;
+                }
+            }
+        }
+    }
+    // nothing evaluated anywhere in the warp (non-finite scores) or an overflowed list: exact scan of the whole row
+    const bool scan = ovf || __ballot_sync(0xffffffffu, evaluated > 0) == 0u;
+    if (scan) {
+        for (int64_t x = lane; x < Npx; x += 32) {
+            const float d = sim_exact_d(spt, pxb + x * ldpx, C);
+            if (d < bd) {  // x ascending per lane: strict < keeps the lowest index
+                bd = d;
+                bi = (int)x;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bd || (ov == bd && oi < bi)) {
+            bd = ov;
+            bi = oi;
+        }
+    }
+    if (stats) {
+        const int ev = __reduce_add_sync(0xffffffffu, evaluated);
+        if (lane == 0) {
+            atomicAdd(stats + 0, scan ? 0 : ev);   // candidates re-ranked
+            atomicAdd(stats + 1, scan ? 1 : 0);    // rows that needed the full exact scan
+        }
+    }
+    if (lane == 0) {
+        best_idx[row] = bi;
+        best_val[row] = bd;
+    }
+}
+
+// fp32 -> fp16 rows plus the running maximum of the squared row norms (atomicMax on the float's bit pattern; norms are
+// non-negative so the unsigned order is the float order).  One warp per row.
+__global__ void __launch_bounds__(128)
+cast_f16_bound_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C, __half* __restrict__ y, int64_t ldy,
+                      float* __restrict__ bound2_slot) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float ss = 0.0f;
+    for (int c = lane * 2; c < C; c += 64) {
+        const float2 v = *reinterpret_cast<const float2*>(x + row * ldx + c);
+        ss += v.x * v.x + v.y * v.y;
+        *reinterpret_cast<__half2*>(y + row * ldy + c) = __floats2half2_rn(v.x, v.y);
+    }
+    ss = warp_sum(ss) * 1.0001f;
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(bound2_slot), __float_as_uint(ss));
+}
+
 }  // namespace tc
 }  // namespace cofi
 
@@ -222,6 +409,99 @@ extern "C" int cofi_cast_f16(const float* x, int64_t ldx, int64_t rows, int C, v
     if (blocks > 148 * 16) blocks = 148 * 16;
     tc::cast_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, reinterpret_cast<__half*>(y), ldy);
     return check_launch("cofi_cast_f16");
+}
+
+static int sim16_attrs() {
+    using namespace cofi::tc;
+    static bool attr_done = false;
+    if (attr_done) return COFI_OK;
+    cudaError_t e = cudaFuncSetAttribute(sim_argmin_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S16_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(sim_argmin_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S16_SMEM_CAND);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(sim16 smem=%d): %s", S16_SMEM_CAND, cudaGetErrorString(e));
+        return COFI_ECUDA;
+    }
+    attr_done = true;
+    return COFI_OK;
+}
+
+extern "C" int cofi_cast_f16_bound(const float* x, int64_t ldx, int64_t rows, int C, void* y, int64_t ldy, float* bound2_slot,
+                                   void* stream) {
+    COFI_REQUIRE(x && y && bound2_slot && rows >= 0 && C > 0 && C % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0,
+                 "cofi_cast_f16_bound: bad argument");
+    if (rows == 0) return COFI_OK;
+    tc::cast_f16_bound_kernel<<<(unsigned)ceil_div(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, ldx, rows, C,
+                                                                                           reinterpret_cast<__half*>(y), ldy, bound2_slot);
+    return check_launch("cofi_cast_f16_bound");
+}
+
+// pixel-range split of the tcgen05 pass: fill the machine when frames * Npt / 256 CTAs would not
+static int sim_exact_nsplit(int64_t Npt, int64_t Npx, int frames) {
+    using namespace cofi::tc;
+    const int64_t ctas = ceil_div(Npt, 2 * S16_MH) * frames;
+    const int64_t tiles = ceil_div(Npx, S16_N);
+    int64_t ns = 1;
+    if (ctas < 148) ns = (2 * 148 + ctas - 1) / ctas;
+    if (ns > tiles) ns = tiles;
+    if (ns < 1) ns = 1;
+    const int64_t tps = ceil_div(tiles, ns);
+    return (int)ceil_div(tiles, tps);
+}
+
+extern "C" int64_t cofi_sim_argmin_exact_workspace(int64_t Npt, int64_t Npx, int frames) {
+    using namespace cofi::tc;
+    if (Npt <= 0 || Npx <= 0 || frames <= 0) return 0;
+    const int64_t rows = Npt * frames, ns = sim_exact_nsplit(Npt, Npx, frames);
+    // per (split, row): best index (8) + best score (4) + count (4) + S16_CAP * (index 4 + score 4); + 2 stats counters
+    return ns * rows * (16 + S16_CAP * 8) + 64;
+}
+
+extern "C" int cofi_sim_argmin_exact(const float* pt, int64_t ldpt, const float* px, int64_t ldpx, const void* pt_h,
+                                     int64_t ldpth, const void* px_h, int64_t ldpxh, int64_t Npt, int64_t Npx, int C,
+                                     int frames, const float* bound2, int64_t* best_idx, float* best_val, void* work,
+                                     int32_t* stats, void* stream) {
+    using namespace cofi::tc;
+    COFI_REQUIRE(pt && px && pt_h && px_h && best_idx && best_val && work, "cofi_sim_argmin_exact: null pointer");
+    COFI_REQUIRE(Npt > 0 && Npx > 0 && frames > 0, "cofi_sim_argmin_exact: bad shape");
+    COFI_REQUIRE(C % 64 == 0 && C <= 64 * S16_MAXKB, "cofi_sim_argmin_exact: C=%d must be 64 or 128", C);
+    COFI_REQUIRE(ldpth % 8 == 0 && ldpxh % 8 == 0 && ((uintptr_t)pt_h % 16) == 0 && ((uintptr_t)px_h % 16) == 0,
+                 "cofi_sim_argmin_exact: fp16 rows must be 16-byte aligned");
+    COFI_REQUIRE(ldpx % 4 == 0 && ((uintptr_t)px % 16) == 0 && ((uintptr_t)work % 16) == 0,
+                 "cofi_sim_argmin_exact: px rows / workspace must be 16-byte aligned");
+    COFI_REQUIRE(Npx < (1ll << 31) && frames * Npt < (1ll << 31), "cofi_sim_argmin_exact: shape too large");
+    uint64_t dA[2] = {(uint64_t)C, (uint64_t)(frames * Npt)}, sA[1] = {(uint64_t)ldpth * 2};
+    uint32_t bA[2] = {S16_K, S16_MH};
+    uint64_t dB[2] = {(uint64_t)C, (uint64_t)(frames * Npx)}, sB[1] = {(uint64_t)ldpxh * 2};
+    uint32_t bB[2] = {S16_K, S16_N};
+    const CUtensorMap* ta = get_tmap_f16(pt_h, 2, dA, sA, bA);
+    const CUtensorMap* tb = get_tmap_f16(px_h, 2, dB, sB, bB);
+    if (!ta || !tb) return COFI_ECUDA;
+    if (int rc = sim16_attrs()) return rc;
+    const int num_tiles = (int)ceil_div(Npx, S16_N);
+    const int nsplit = sim_exact_nsplit(Npt, Npx, frames);
+    const int tps = (int)ceil_div(num_tiles, nsplit);
+    const int64_t rows = (int64_t)frames * Npt;
+    // workspace carve-up (all offsets 16-byte aligned: rows * nsplit * {8, 4, 4, 64, 64})
+    uint8_t* w = reinterpret_cast<uint8_t*>(work);
+    int64_t* part_idx = reinterpret_cast<int64_t*>(w);
+    w += (int64_t)nsplit * rows * 8;
+    int32_t* c_idx = reinterpret_cast<int32_t*>(w);
+    w += (int64_t)nsplit * rows * S16_CAP * 4;
+    float* c_val = reinterpret_cast<float*>(w);
+    w += (int64_t)nsplit * rows * S16_CAP * 4;
+    float* part_val = reinterpret_cast<float*>(w);
+    w += (int64_t)nsplit * rows * 4;
+    int32_t* c_cnt = reinterpret_cast<int32_t*>(w);
+    const float margin = 2.5e-3f;  // 2 x (2^-10 operand rounding + accumulation slack), see DESIGN.md
+    Sim16Params p{part_idx, part_val, Npt, Npx, C / S16_K, num_tiles, tps, rows, margin, bound2, c_idx, c_val, c_cnt};
+    dim3 grid((unsigned)ceil_div(Npt, 2 * S16_MH), frames, nsplit);
+    sim_argmin_f16_kernel<true><<<grid, 320, S16_SMEM_CAND, (cudaStream_t)stream>>>(*ta, *tb, p);
+    int rc = check_launch("cofi_sim_argmin_exact(tcgen05 pass)");
+    if (rc) return rc;
+    sim_rerank_kernel<<<(unsigned)ceil_div(rows, RR_WARPS), RR_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        pt, ldpt, px, ldpx, Npt, Npx, C, rows, nsplit, margin, bound2, part_val, c_idx, c_val, c_cnt, best_idx, best_val, stats);
+    return check_launch("cofi_sim_argmin_exact(re-rank)");
 }
 
 extern "C" int cofi_sim_argmin_f16(const void* pt, int64_t ldpt, const void* px, int64_t ldpx, int64_t Npt, int64_t Npx,
@@ -240,15 +520,7 @@ extern "C" int cofi_sim_argmin_f16(const void* pt, int64_t ldpt, const void* px,
     const CUtensorMap* ta = get_tmap_f16(pt, 2, dA, sA, bA);
     const CUtensorMap* tb = get_tmap_f16(px, 2, dB, sB, bB);
     if (!ta || !tb) return COFI_ECUDA;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(sim_argmin_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S16_SMEM);
-        if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(sim16 smem=%d): %s", S16_SMEM, cudaGetErrorString(e));
-            return COFI_ECUDA;
-        }
-        attr_done = true;
-    }
+    if (int rc = sim16_attrs()) return rc;
     const int num_tiles = (int)ceil_div(Npx, S16_N);
     if (nsplit < 1) nsplit = 1;
     if (nsplit > num_tiles) nsplit = num_tiles;
@@ -256,9 +528,10 @@ extern "C" int cofi_sim_argmin_f16(const void* pt, int64_t ldpt, const void* px,
     const int tps = (int)ceil_div(num_tiles, nsplit);
     nsplit = (int)ceil_div(num_tiles, tps);
     const int64_t rows = (int64_t)frames * Npt;
-    Sim16Params p{nsplit > 1 ? ws_idx : best_idx, nsplit > 1 ? ws_val : best_val, Npt, Npx, C / S16_K, num_tiles, tps, rows};
+    Sim16Params p{nsplit > 1 ? ws_idx : best_idx, nsplit > 1 ? ws_val : best_val, Npt, Npx, C / S16_K, num_tiles, tps, rows,
+                  0.0f, nullptr, nullptr, nullptr, nullptr};
     dim3 grid((unsigned)ceil_div(Npt, 2 * S16_MH), frames, nsplit);
-    sim_argmin_f16_kernel<<<grid, 320, S16_SMEM, (cudaStream_t)stream>>>(*ta, *tb, p);
+    sim_argmin_f16_kernel<false><<<grid, 320, S16_SMEM, (cudaStream_t)stream>>>(*ta, *tb, p);
     int rc = check_launch("cofi_sim_argmin_f16");
     if (rc || nsplit == 1) return rc;
     sim_merge_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(ws_idx, ws_val, nsplit, rows, best_idx,

@@ -1,4 +1,4 @@
-"""Batched inference engine: static device buffers + one CUDA graph for the whole `val`-mode forward.
+"""Batched inference engine: static device buffers + one CUDA graph for the whole forward, `val` or `test` mode.
 
 The reference runs one frame at a time through ~1,150 eager kernels and 256 host syncs.  Here B
 frames are stacked along the row axis (frame-local index tables), every kernel launch of the forward is
@@ -6,6 +6,12 @@ captured once into a CUDA graph, and a step is: (optional) async H2D copies from
 static input buffers -> graph replay -> (optional) async D2H of the outputs into pinned host memory.
 Only column 0 of the up-sampling tables is ever read by the model (reference model/kpconv/functional.py:20), so
 the engine keeps and uploads [N,1] columns instead of [N,128] tables.
+
+mode="test" is what the reference's evaluation runs (evaluation/eval_all.py:96): the whole matching stage -- fused
+similarity + arg-min over all B frames (tcgen05 candidate pass + exact fp32 re-rank), threshold loop + border mask +
+compaction, point2node, patch / feature gathers, and the caller's 16-way fine match (eval_all.py:99-102) -- is inside the
+captured graph with fixed shapes (N4 rows per frame, the upper bound on the matches) and the match counts in a device
+tensor; nothing synchronises with the host until results() trims the rows.
 """
 from __future__ import annotations
 
@@ -28,7 +34,7 @@ class InferenceEngine:
         `tables`: "host" = the KNN index tables arrive with the batch, as the reference's data loader supplies them;
         "device" = only the point pyramid arrives and the tables are built inside the captured graph by
         ops.knn_pyramid (csrc/knn.cu; neighbours/subsampling k columns, upsampling its single live column)."""
-        assert mode == "val", "the graph covers the static-shape val/train-style forward; test mode adds an eager tail"
+        assert mode in ("val", "test")
         assert tables in ("host", "device")
         self.model, self.mode, self.B, self.tables = model, mode, batch["frames"], tables
         dev = next(model.parameters()).device
@@ -51,13 +57,23 @@ class InferenceEngine:
         self.kpt = torch.stack([k.to(torch.float32) for k in batch["fine_center_kpt_coors"]]).to(dev).contiguous()
         self.inline = torch.stack([k.to(torch.int64) for k in batch["fine_pc_inline_index"]]).to(dev).contiguous()
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sim_stats = torch.zeros(2, dtype=torch.int32, device=dev)  # re-ranked candidates, full-scan rows (accumulated)
         self.out: Dict[str, torch.Tensor] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self._host_in = None
         self._host_out = None
         self._stream = stream if stream is not None else torch.cuda.Stream(device=dev)
-        # warm-up (fills weight-pack / BN-fold / positional-encoding caches), then capture
+        self.use_graph = use_graph
+        self._capture()
+
+    def _capture(self):
+        """warm-up (fills weight-pack / BN-fold / positional-encoding caches), then capture.  The graph bakes in parameter
+        pointers and the packed / folded weight copies, so it is tied to the weights epoch (ops.weights_epoch) of this
+        moment: run() re-captures when parameters were reloaded or updated by an optimiser step since."""
+        dev = self.device
+        self.graph = None
+        self.epoch = ops.weights_epoch()
         with torch.no_grad():
             with torch.cuda.stream(self._stream):
                 for _ in range(2):
@@ -65,7 +81,7 @@ class InferenceEngine:
                     self._step_eager()
                     self.launches_per_step = _libmod.launch_count() - n0
                 self._stream.synchronize()
-                if use_graph:
+                if self.use_graph:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=self._stream):
                         self._step_eager()
@@ -81,6 +97,18 @@ class InferenceEngine:
         n1 = core["pc_decode_3"].shape[0] // B
         hw = m.pe_H * m.pe_W
         n4 = core["pc_norm"].shape[0] // B
+        if self.mode == "test":
+            t = m.tail_test_batched(core, self.inp["points"][-1], self.inp["points"][1], B, self.err, self.sim_stats)
+            C = t["patch"].shape[2]
+            fidx = ops.fine_match(t["patch"].view(B * n4, C, 16), t["fine_pc"].view(B * n4, C))   # eval_all.py:99-102
+            self.out = {
+                "img_norm": core["img_norm"], "pc_norm": core["pc_norm"],
+                "img_score": core["img_score"], "pc_score": core["pc_score"],
+                "patch": t["patch"], "fine_pc": t["fine_pc"], "fine_center_xy": t["fine_center_xy"],
+                "coarse_pc_points": t["coarse_pc_points"], "count": t["count"], "sel": t["sel"],
+                "fine_idx": fidx.view(B, n4),
+            }
+            return
         patches, fine = [], []
         for b in range(B):
             fine.append(ops.gather_rows(core["pc_decode_3"][b * n1:(b + 1) * n1], self.inline[b]))
@@ -95,6 +123,8 @@ class InferenceEngine:
     # ------------------------------------------------------------------------------------------ stepping
     def run(self):
         """One forward over whatever currently sits in the static input buffers (asynchronous)."""
+        if self.epoch != ops.weights_epoch():
+            self._capture()   # parameters changed since the capture: stale packs / folds / pointers must not be replayed
         with torch.no_grad():
             if self.graph is not None:
                 with torch.cuda.stream(self._stream):
@@ -137,8 +167,12 @@ class InferenceEngine:
 
     def download(self, stream=None) -> int:
         """Async D2H of the step's results into pinned host buffers; returns the bytes copied."""
-        flat = [self.out["img_norm"], self.out["pc_norm"], self.out["img_score"], self.out["pc_score"]] + \
-            list(self.out["patch"]) + list(self.out["fine_pc"]) + [self.err]
+        if self.mode == "test":
+            flat = [self.out[k] for k in ("img_norm", "pc_norm", "img_score", "pc_score", "patch", "fine_pc", "fine_center_xy",
+                                          "coarse_pc_points", "count", "sel", "fine_idx")] + [self.err]
+        else:
+            flat = [self.out["img_norm"], self.out["pc_norm"], self.out["img_score"], self.out["pc_score"]] + \
+                list(self.out["patch"]) + list(self.out["fine_pc"]) + [self.err]
         if self._host_out is None:
             self._host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in flat]
         nbytes = 0
@@ -149,16 +183,40 @@ class InferenceEngine:
         return nbytes
 
     def results(self) -> List[tuple]:
-        """Reference-layout 8-tuples per frame (synchronises)."""
+        """Reference-layout 8-tuples per frame (synchronises).  test mode: rows trimmed to each frame's match count."""
         self._stream.synchronize()
         m, B = self.model, self.B
         outs = []
         with torch.no_grad():
+            if self.mode == "test":
+                counts = self.out["count"][:, 0].tolist()
+                if min(counts) < 4:
+                    raise RuntimeError("fewer than 4 matches survive every threshold (the reference would loop forever)")
             for b in range(B):
                 pub = m._public(self.out, b, B)
-                outs.append(pub + (self.out["patch"][b], self.out["fine_pc"][b], None, None))
+                if self.mode == "test":
+                    n = counts[b]
+                    outs.append(pub + (self.out["patch"][b, :n].clone(), self.out["fine_pc"][b, :n].clone(),
+                                       self.out["fine_center_xy"][b, :, :n].clone(), self.out["coarse_pc_points"][b, :n].clone()))
+                else:
+                    outs.append(pub + (self.out["patch"][b], self.out["fine_pc"][b], None, None))
         assert int(self.err.item()) == 0, "extract_patch: window outside the feature map"
         return outs
+
+    def correspondences(self):
+        """test mode: per frame (imagePoints [n,2] fp32, objectPoints [n,3] fp32, fine index [n]) -- the inputs of the
+        caller's PnP (evaluation/eval_all.py:99-107), assembled from the graph's fine-match output (synchronises)."""
+        assert self.mode == "test"
+        self._stream.synchronize()
+        res = []
+        counts = self.out["count"][:, 0].tolist()
+        for b, n in enumerate(counts):
+            idx = self.out["fine_idx"][b, :n]
+            c = self.out["fine_center_xy"][b, :, :n]
+            x = c[0] - 2 + torch.div(idx, 4, rounding_mode="floor")     # eval_all.py:103-105 (its x += idx//4 convention)
+            y = c[1] - 2 + idx % 4
+            res.append((torch.stack([x, y], 1), self.out["coarse_pc_points"][b, :n].clone(), idx.clone()))
+        return res
 
 
 class PipelinedEngine:
@@ -166,12 +224,13 @@ class PipelinedEngine:
     lands in buffer set (i+1)%2 on a copy stream and the D2H of batch i-1 drains on a third stream (PCIe is full
     duplex).  Steady-state step time = max(H2D, compute, D2H) instead of their sum."""
 
-    def __init__(self, model, batch: Dict, depth: int = 2, tables: str = "host"):
+    def __init__(self, model, batch: Dict, depth: int = 2, tables: str = "host", mode: str = "val"):
         dev = next(model.parameters()).device
         self.compute = torch.cuda.Stream(device=dev)
         self.h2d = torch.cuda.Stream(device=dev)
         self.d2h = torch.cuda.Stream(device=dev)
-        self.engines = [InferenceEngine(model, batch, use_graph=True, stream=self.compute, tables=tables) for _ in range(depth)]
+        self.engines = [InferenceEngine(model, batch, mode=mode, use_graph=True, stream=self.compute, tables=tables)
+                        for _ in range(depth)]
         self.uploaded = [torch.cuda.Event() for _ in range(depth)]
         self.computed = [torch.cuda.Event() for _ in range(depth)]
         self.drained = [torch.cuda.Event() for _ in range(depth)]

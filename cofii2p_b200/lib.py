@@ -53,9 +53,15 @@ SIGNATURES = {
     "cofi_sim_argmin": (_i, [_vp, _l, _vp, _l, _l, _l, _i, _i, _vp, _vp, _i, _vp]),
     "cofi_sim_argmin_f16": (_i, [_vp, _l, _vp, _l, _l, _l, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "cofi_cast_f16": (_i, [_vp, _l, _l, _i, _vp, _l, _vp]),
+    "cofi_cast_f16_bound": (_i, [_vp, _l, _l, _i, _vp, _l, _vp, _vp]),
+    "cofi_sim_argmin_exact_workspace": (_l, [_l, _l, _i]),
+    "cofi_sim_argmin_exact": (_i, [_vp, _l, _vp, _l, _vp, _l, _vp, _l, _l, _l, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cofi_l2norm_rows_f16": (_i, [_vp, _l, _l, _i, _vp, _l, _vp, _l, _vp]),
     "cofi_select_matches": (_i, [_vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "cofi_nn_argmin": (_i, [_vp, _l, _vp, _l, _vp, _vp]),
     "cofi_extract_patch": (_i, [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp, _vp]),
+    "cofi_nn_argmin_batched": (_i, [_vp, _l, _vp, _l, _i, _vp, _vp]),
+    "cofi_extract_patch_batched": (_i, [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp, _vp]),
     "cofi_fine_match": (_i, [_vp, _vp, _l, _i, _vp, _vp]),
     # ---- training (backward.cu)
     "cofi_act_bwd": (_i, [_vp, _vp, _l, _i, _vp, _vp]),

@@ -21,15 +21,11 @@ def conv1x1(in_planes, out_planes, stride=1):
     return nn.Conv2d(in_planes, out_planes, kernel_size=1, stride=stride, bias=False)
 
 
-_PACK = {}
-
-
 def packed_conv_weight(conv: nn.Conv2d, cin_pad: int = None):
     """[Cout,Cin,KH,KW] -> [Cout, KH*KW*Cin] (ci fastest), cached per parameter version."""
     w = conv.weight
-    key = id(conv)
-    v = (w._version, w.data_ptr(), cin_pad)
-    hit = _PACK.get(key)
+    v = (w._version, w.data_ptr(), cin_pad, ops.weights_epoch())
+    hit = getattr(conv, "_cofi_pack", None)   # cached on the module itself (no global dict keyed by id())
     if hit is not None and hit[0] == v:
         return hit[1]
     with torch.no_grad():
@@ -37,7 +33,7 @@ def packed_conv_weight(conv: nn.Conv2d, cin_pad: int = None):
         if cin_pad is not None and cin_pad > wp.shape[3]:
             wp = torch.nn.functional.pad(wp, (0, cin_pad - wp.shape[3]))
         wp = wp.reshape(w.shape[0], -1).contiguous()
-    _PACK[key] = (v, wp)
+    conv._cofi_pack = (v, wp)
     return wp
 
 
@@ -150,20 +146,17 @@ class ImageEncoder(nn.Module):
         return [ops.nhwc_to_nchw(t) for t in self.forward_nhwc(x)]
 
 
-_FOLD = {}
-
-
 def _bn_fold(bn: nn.BatchNorm2d):
     """eval-mode BatchNorm as per-channel (scale, shift), cached per parameter/buffer version."""
     v = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
-         bn.weight.data_ptr())
-    hit = _FOLD.get(id(bn))
+         bn.weight.data_ptr(), ops.weights_epoch())
+    hit = getattr(bn, "_cofi_fold", None)
     if hit is not None and hit[0] == v:
         return hit[1], hit[2]
     with torch.no_grad():
         scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).contiguous()
         shift = (bn.bias - bn.running_mean * scale).contiguous()
-    _FOLD[id(bn)] = (v, scale, shift)
+    bn._cofi_fold = (v, scale, shift)
     return scale, shift
 
 

@@ -23,7 +23,8 @@ def nearest_upsample(x, upsample_indices, frames: int = 1, out=None):
 def maxpool(x, neighbor_indices, frames: int = 1):
     if _grad(x):
         return ad.maxpool_rows(x, neighbor_indices, frames)
-    if ops.engine_id() == ops.ENGINE_TF32 and x.shape[1] % 8 == 0:
-        # tf32 engine: gather an fp16 copy (monotonic rounding => exact max of the rounded rows), half the L2 bytes
-        return ops.maxpool_rows_f16(ops.cast_f16(x), neighbor_indices, frames)
-    return ops.maxpool_rows(x, neighbor_indices, frames)
+    with ops.group("pc_maxpool"):
+        if ops.engine_id() == ops.ENGINE_TF32 and x.shape[1] % 8 == 0:
+            # tf32 engine: gather an fp16 copy (monotonic rounding => exact max of the rounded rows), half the L2 bytes
+            return ops.maxpool_rows_f16(ops.cast_f16(x), neighbor_indices, frames)
+        return ops.maxpool_rows(x, neighbor_indices, frames)

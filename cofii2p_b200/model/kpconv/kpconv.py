@@ -40,7 +40,7 @@ class KPConv(nn.Module):
 
     def packed_weight(self):
         """[Cout, K*Cin]: the K-major operand of the weight-apply GEMM (cached per parameter version)."""
-        v = (self.weights._version, self.weights.data_ptr())
+        v = (self.weights._version, self.weights.data_ptr(), ops.weights_epoch())
         if self._wt is None or self._wt_version != v:
             with torch.no_grad():
                 self._wt = self.weights.detach().reshape(-1, self.out_channels).t().contiguous()
@@ -63,6 +63,10 @@ class KPConv(nn.Module):
 
     def forward(self, s_feats, q_points, s_points, neighbor_indices, frames: int = 1, want_stats: bool = False):
         """s_feats [B*N,Cin], q_points [B*M,3], s_points [B*N,3], neighbor_indices [B*M,H] -> [B*M,Cout]."""
+        with ops.group("kpconv"):
+            return self._forward(s_feats, q_points, s_points, neighbor_indices, frames, want_stats)
+
+    def _forward(self, s_feats, q_points, s_points, neighbor_indices, frames, want_stats):
         if ad.active(self):  # training: differentiable kernels (fp32 aggregate, engine-selected GEMMs)
             if want_stats and ops.colstats_ok(q_points.shape[0], frames, self.out_channels):
                 return ad.kpconv(s_feats, self.weights, self.bias, q_points, s_points, neighbor_indices, self.kernel_points,

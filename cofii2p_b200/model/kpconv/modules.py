@@ -50,6 +50,10 @@ class UnaryBlock(nn.Module):
         self.leaky_relu = nn.LeakyReLU(0.1) if has_relu else None
 
     def forward(self, x, frames: int = 1, residual=None, final_act: int = None):
+        with ops.group("pc_unary"):
+            return self._forward(x, frames, residual, final_act)
+
+    def _forward(self, x, frames, residual, final_act):
         act = ops.ACT_LRELU if self.leaky_relu is not None else ops.ACT_NONE
         if final_act is not None:
             act = final_act
@@ -72,9 +76,10 @@ class LastUnaryBlock(nn.Module):
         self.mlp = nn.Linear(in_channels, out_channels, bias=bias)
 
     def forward(self, x, frames: int = 1):
-        if ad.active(self):
-            return ad.linear(x, self.mlp.weight, self.mlp.bias)
-        return ops.gemm(x, self.mlp.weight, bias=self.mlp.bias)
+        with ops.group("pc_unary"):
+            if ad.active(self):
+                return ad.linear(x, self.mlp.weight, self.mlp.bias)
+            return ops.gemm(x, self.mlp.weight, bias=self.mlp.bias)
 
 
 class ConvBlock(nn.Module):

@@ -133,34 +133,44 @@ class CoFiI2P(nn.Module):
             img_pos = self._img_pos[key]
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            s2, s4, s8 = self.img_encoder.forward_nhwc(img)
+            with ops.group("img_encoder"):
+                s2, s4, s8 = self.img_encoder.forward_nhwc(img)
             s8n = l2(s8.reshape(B * hw, 128))                                             # :90 (feeds decoder too)
             f_img = l2(s8.reshape(B * hw, 128), img_pos)                                  # :113
             tokens_ready = torch.cuda.Event()
             tokens_ready.record(side)
-            up4 = self.img_upsample_1.forward_nhwc(s8n.view(B, self.pe_H, self.pe_W, 128), s4)   # :129
-            up2 = self.img_upsample_2.forward_nhwc(up4, s2)                               # :130
+            with ops.group("img_decoder"):
+                up4 = self.img_upsample_1.forward_nhwc(s8n.view(B, self.pe_H, self.pe_W, 128), s4)   # :129
+                up2 = self.img_upsample_2.forward_nhwc(up4, s2)                           # :130
             Bh, Hh, Wh, Ch = up2.shape
             up2n = l2(up2.reshape(-1, Ch)).view(Bh, Hh, Wh, Ch)
         # ---- point stream on the main stream
         pcs = self.pc_encoder(pc_data_dict, frames, taps)
         pc_decode_3 = l2(pcs[0])                                                         # network.py:82
         pc_pos = self.pc_pos_encoding(pc_data_dict["points"][-1])                         # :107
-        f_pc = l2(self._pc_feature(pcs[3]), pc_pos)                                       # :84,:114
+        with ops.group("pc_feature"):
+            f_pc = l2(self._pc_feature(pcs[3]), pc_pos)                                   # :84,:114
         main.wait_event(tokens_ready)
         f_img_side = f_img  # keep the side-stream allocation alive until the join (no cross-stream block reuse)
-        f_img, f_pc = self.transformer(f_img, f_pc, frames)                               # :115
-        pc_score = self._score_head(self.pc_score_layer, f_pc, frames)                    # :123
-        img_score = self._score_head(self.img_score_layer, f_img, frames)                 # :124
-        pc_norm = l2(f_pc)                                                                # :125
-        img_norm = l2(f_img)                                                              # :126
+        with ops.group("transformer"):
+            f_img, f_pc = self.transformer(f_img, f_pc, frames)                           # :115
+        with ops.group("score"):
+            pc_score = self._score_head(self.pc_score_layer, f_pc, frames)                # :123
+            img_score = self._score_head(self.img_score_layer, f_img, frames)             # :124
+        pc_norm_h = img_norm_h = None
+        if train:
+            pc_norm = l2(f_pc)                                                            # :125
+            img_norm = l2(f_img)                                                          # :126
+        else:  # inference: the fp16 copies the tensor-core similarity pass streams come out of the same kernel
+            pc_norm, pc_norm_h = ops.l2norm_rows_f16(f_pc)
+            img_norm, img_norm_h = ops.l2norm_rows_f16(f_img)
         main.wait_stream(side)  # join: decoder output (and every side-stream temporary) is complete from here on
         del f_img_side
         if taps is not None:
             taps.update(img_s2=s2, img_s4=s4, img_s8=s8, tr_img=f_img, tr_pc=f_pc, img_up4=up4, img_up2=up2n,
                         pc_decode_3=pc_decode_3)
         return dict(img_norm=img_norm, pc_norm=pc_norm, img_score=img_score, pc_score=pc_score, up2=up2n,
-                    pc_decode_3=pc_decode_3)
+                    pc_decode_3=pc_decode_3, img_norm_h=img_norm_h, pc_norm_h=pc_norm_h)
 
     # ------------------------------------------------------------------------------------------ matching tails
     def _tail_val(self, core: Dict, b: int, n1: int, kpt_coors, inline_index):
@@ -174,34 +184,55 @@ class CoFiI2P(nn.Module):
         patch = ops.extract_patch(core["up2"], b, kpt_coors.to(torch.float32), err)
         return patch, fine_pc, err
 
+    def tail_test_batched(self, core: Dict, points4: torch.Tensor, points1: torch.Tensor, frames: int,
+                          err: torch.Tensor, stats: Optional[torch.Tensor] = None) -> Dict:
+        """Test-mode matching of all B frames with fixed shapes and no host synchronisation (reference network.py:145-161,
+        :167-187, :250-264): CUDA-graph capturable.  Every per-frame output has N4 rows (the upper bound on the number of
+        matches); `count[b, 0]` says how many are real, the rest is valid padding (cofi_select_matches).
+          similarity + arg-min over all frames (tcgen05 candidate pass + exact fp32 re-rank)          :174-179
+          threshold loop + border mask + compaction                                                    :146-151,:181-187
+          coarse_pc_points = points4[sel]; point2node = arg-min over the level-1 cloud                 :152-153
+          4x4 patches around 4*coarse_xy, level-1 features of the matched nodes                        :156-161"""
+        dev = core["pc_norm"].device
+        B, n4 = frames, core["pc_norm"].shape[0] // frames
+        key = str(dev)
+        if key not in self._thr:
+            self._thr[key] = _thresholds(dev)
+        best, _ = ops.sim_argmin(core["pc_norm"], core["img_norm"], B, pt_h=core.get("pc_norm_h"),
+                                 px_h=core.get("img_norm_h"), stats=stats)
+        cnt, oidx, oxy = ops.select_matches(core["pc_score"], best, B, self.pe_H, self.pe_W, self._thr[key], 4,
+                                            xy_scale=4.0)
+        sel = oidx.view(-1)
+        coarse_pc_points = ops.gather_rows(points4, sel, frames=B)                        # [B*N4, 3]
+        cidx = ops.nn_argmin_batched(coarse_pc_points, points1, B)                        # [B*N4]
+        patch = ops.extract_patch_batched(core["up2"], oxy, err)                          # [B, N4, C, 4, 4]
+        fine_pc = ops.gather_rows(core["pc_decode_3"], cidx, frames=B)                    # [B*N4, C]
+        C = patch.shape[2]
+        return dict(count=cnt, sel=oidx, fine_center_xy=oxy, coarse_pc_points=coarse_pc_points.view(B, n4, 3),
+                    node_index=cidx.view(B, n4), patch=patch.view(B, n4, C, 16), fine_pc=fine_pc.view(B, n4, -1))
+
     def _tail_test(self, core: Dict, b: int, pc_data_dict: Dict, frames: int):
-        """Test-mode matching (reference network.py:145-161): threshold loop + argmin + border mask in one
-        kernel, one host sync to learn n, then point2node / extract_patch / gathers."""
+        """Test-mode matching of one frame (reference network.py:145-161): the batched tail on this frame's rows, one host
+        sync to learn n (the reference syncs 4x per key point), outputs trimmed to the reference's shapes."""
         dev = core["pc_norm"].device
         n4 = core["pc_norm"].shape[0] // frames
         n1 = core["pc_decode_3"].shape[0] // frames
         hw = self.pe_H * self.pe_W
-        key = str(dev)
-        if key not in self._thr:
-            self._thr[key] = _thresholds(dev)
-        pcn = core["pc_norm"][b * n4:(b + 1) * n4]
-        imn = core["img_norm"][b * hw:(b + 1) * hw]
-        best, _ = ops.sim_argmin(pcn, imn, 1)
-        cnt, oidx, oxy = ops.select_matches(core["pc_score"][b * n4:(b + 1) * n4], best, 1, self.pe_H, self.pe_W,
-                                            self._thr[key], 4, xy_scale=4.0)
-        n = int(cnt[0, 0].item())  # the one host sync of the frame (the reference syncs 4x per key point)
+        sub = dict(pc_norm=core["pc_norm"][b * n4:(b + 1) * n4], img_norm=core["img_norm"][b * hw:(b + 1) * hw],
+                   pc_score=core["pc_score"][b * n4:(b + 1) * n4], up2=core["up2"][b:b + 1],
+                   pc_decode_3=core["pc_decode_3"][b * n1:(b + 1) * n1])
+        if core.get("pc_norm_h") is not None:
+            sub["pc_norm_h"] = core["pc_norm_h"][b * n4:(b + 1) * n4]
+            sub["img_norm_h"] = core["img_norm_h"][b * hw:(b + 1) * hw]
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        t = self.tail_test_batched(sub, pc_data_dict["points"][-1][b * n4:(b + 1) * n4],
+                                   pc_data_dict["points"][1][b * n1:(b + 1) * n1], 1, err)
+        n = int(t["count"][0, 0].item())
         if n < 4:
             raise RuntimeError("fewer than 4 matches survive every threshold (the reference would loop forever)")
-        sel = oidx[0, :n].contiguous()
-        fine_center_xy = oxy[0, :, :n].contiguous()                                      # coarse_xy * 4, :156
-        pts4 = pc_data_dict["points"][-1][b * n4:(b + 1) * n4]
-        pts1 = pc_data_dict["points"][1][b * n1:(b + 1) * n1]
-        coarse_pc_points = ops.gather_rows(pts4, sel)                                     # :152
-        cidx = ops.nn_argmin(coarse_pc_points, pts1)                                      # :153
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
-        patch = ops.extract_patch(core["up2"], b, fine_center_xy, err).view(n, -1, 16)    # :157-158
-        fine_pc = ops.gather_rows(core["pc_decode_3"][b * n1:(b + 1) * n1], cidx)         # :161
-        return patch, fine_pc, fine_center_xy, coarse_pc_points, sel, err
+        return (t["patch"][0, :n].contiguous(), t["fine_pc"][0, :n].contiguous(),
+                t["fine_center_xy"][0, :, :n].contiguous(), t["coarse_pc_points"][0, :n].contiguous(),
+                t["sel"][0, :n].contiguous(), err)
 
     def _public(self, core: Dict, b: int, frames: int):
         """token layout -> the reference's output layout for frame b."""
@@ -226,9 +257,26 @@ class CoFiI2P(nn.Module):
         if not enabled:
             self._graphs = {}
 
+    def load_state_dict(self, *args, **kwargs):
+        """Parameter values change: every derived cache (weight packs, BN folds, captured graphs) is invalidated."""
+        res = super().load_state_dict(*args, **kwargs)
+        ops.bump_weights_epoch()
+        self._graphs = {}
+        return res
+
+    def _apply(self, fn, *args, **kwargs):
+        """.to() / .cuda() / .float(): parameter storage moves, captured graphs would read freed memory."""
+        res = super()._apply(fn, *args, **kwargs)
+        ops.bump_weights_epoch()
+        self._graphs = {}
+        return res
+
     def _core_graphed(self, pc_data_dict: Dict, img: torch.Tensor):
         key = (str(img.device), tuple(img.shape), tuple(int(p.shape[0]) for p in pc_data_dict["points"]),
-               tuple(int(t.shape[1]) for t in pc_data_dict["neighbors"]), ops.get_engine())
+               tuple(int(t.shape[1]) for t in pc_data_dict["neighbors"]), ops.get_engine(), tuple(sorted(ops.get_policy().items())),
+               ops.weights_epoch())
+        if len(self._graphs) > 8:  # stale epochs / shapes: captured pools are large, keep the cache bounded
+            self._graphs = {}
         entry = self._graphs.get(key)
         if entry is None:
             static = {
@@ -298,15 +346,24 @@ class CoFiI2P(nn.Module):
             imagenet.PER_FRAME_BN[0] = False
         n1 = core["pc_decode_3"].shape[0] // B
         outs, errs = [], []
-        for b in range(B):
+        if mode == "test":  # all frames through the fixed-shape tail, ONE host sync for the B match counts
+            err = torch.zeros(1, dtype=torch.int32, device=core["pc_norm"].device)
+            t = self.tail_test_batched(core, batch["pc_data_dict"]["points"][-1], batch["pc_data_dict"]["points"][1], B, err)
+            counts = t["count"][:, 0].tolist()
+            if min(counts) < 4:
+                raise RuntimeError("fewer than 4 matches survive every threshold (the reference would loop forever)")
+            for b, n in enumerate(counts):
+                outs.append(self._public(core, b, B) + (t["patch"][b, :n].contiguous(), t["fine_pc"][b, :n].contiguous(),
+                                                       t["fine_center_xy"][b, :, :n].contiguous(),
+                                                       t["coarse_pc_points"][b, :n].contiguous()))
+            errs.append(err)
+        elif mode not in ("train", "val"):
+            raise ValueError(mode)
+        for b in range(B if mode != "test" else 0):
             pub = self._public(core, b, B)
-            if mode in ("train", "val"):
-                patch, fine_pc, err = self._tail_val(core, b, n1, batch["fine_center_kpt_coors"][b],
-                                                     batch["fine_pc_inline_index"][b])
-                outs.append(pub + (patch, fine_pc, None, None))
-            else:
-                patch, fine_pc, xy, pts, _, err = self._tail_test(core, b, batch["pc_data_dict"], B)
-                outs.append(pub + (patch, fine_pc, xy, pts))
+            patch, fine_pc, err = self._tail_val(core, b, n1, batch["fine_center_kpt_coors"][b],
+                                                 batch["fine_pc_inline_index"][b])
+            outs.append(pub + (patch, fine_pc, None, None))
             errs.append(err)
         self.last_err = torch.stack(errs).sum()
         if check and int(self.last_err.item()) != 0:

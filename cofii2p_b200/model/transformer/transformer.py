@@ -10,6 +10,12 @@ from ... import ops
 from .linear_attention import FullAttention
 
 
+def _attn_tc(rows: int) -> bool:
+    """tcgen05 flash attention for the "tr_attn" precision group (V is then produced directly as V^T)."""
+    with ops.group("tr_attn"):
+        return ops.engine_id() == ops.ENGINE_TF32 and rows % 4 == 0
+
+
 class LoFTREncoderLayer(nn.Module):
     def __init__(self, d_model, nhead, attention="full"):
         super().__init__()
@@ -28,7 +34,7 @@ class LoFTREncoderLayer(nn.Module):
         C = x.shape[1]
         if source is None:
             source = x
-        if ad.active(self):  # training: differentiable kernels, SIMT attention with saved log-sum-exp
+        if ad.active(self):  # training: differentiable kernels, attention forward with saved log-sum-exp
             q = ad.colnorm(ad.linear(x, self.q_proj.weight), frames)
             k = ad.linear(source, self.k_proj.weight)
             v = ad.linear(source, self.v_proj.weight)
@@ -40,13 +46,14 @@ class LoFTREncoderLayer(nn.Module):
         # F.normalize(q) with default dim=1 == L2 over the sequence axis per (head, channel) (reference :53)
         q = ops.colnorm_rows(ops.gemm(x, self.q_proj.weight), frames)
         k = ops.gemm(source, self.k_proj.weight)
-        if ops.engine_id() == ops.ENGINE_TF32 and (source.shape[0] % 4 == 0):
+        if _attn_tc(source.shape[0]):
             # tcgen05 flash attention: V is produced directly as V^T (K-major operand) by swapping GEMM operands
             vt = ops.gemm(self.v_proj.weight, source)
             msg = ops.attention_vt(q, k, vt, frames, self.nhead, 1.0 / self.dim ** 0.5)
         else:
             v = ops.gemm(source, self.v_proj.weight)
-            msg = self.attention(q, k, v, frames, self.nhead)
+            with ops.group("tr_attn"):
+                msg = self.attention(q, k, v, frames, self.nhead)
         # message = norm1(merge(message)): Linear + LayerNorm fused in the GEMM epilogue
         m = ops.gemm_ln(msg, self.merge.weight, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         # mlp[0] on cat([x, message]) without materialising the concat: two K=C GEMMs accumulating into one output
@@ -65,7 +72,7 @@ class LoFTREncoderLayer(nn.Module):
         call over both streams; the rest runs stream after stream, writing into the halves of the output buffer."""
         C = both.shape[1]
         scale = 1.0 / self.dim ** 0.5
-        tc = ops.engine_id() == ops.ENGINE_TF32 and n % 4 == 0
+        tc = _attn_tc(n)
         q = ops.colnorm_rows(ops.gemm(both, self.q_proj.weight), 2 * frames)
         w1 = self.mlp[0].weight
         h = ops.gemm(both, w1[:, :C])
@@ -75,7 +82,9 @@ class LoFTREncoderLayer(nn.Module):
             if tc:
                 msg = ops.attention_vt(q[lo:lo + n], k, ops.gemm(self.v_proj.weight, src), frames, self.nhead, scale)
             else:
-                msg = self.attention(q[lo:lo + n], k, ops.gemm(src, self.v_proj.weight), frames, self.nhead)
+                v = ops.gemm(src, self.v_proj.weight)
+                with ops.group("tr_attn"):
+                    msg = self.attention(q[lo:lo + n], k, v, frames, self.nhead)
             m = ops.gemm_ln(msg, self.merge.weight, self.norm1.weight, self.norm1.bias, self.norm1.eps)
             hh = ops.gemm(m, w1[:, C:], out=h[lo:lo + n], accumulate=True, act=ops.ACT_RELU)
             ops.gemm_ln(hh, self.mlp[2].weight, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=both[lo:lo + n],

@@ -14,7 +14,18 @@ import torch
 
 from . import lib as _libmod
 
-_lib = _libmod.load()
+
+
+class _Lib:
+    """libcofi_b200.so, opened on first use (not at import: bench.py's CPU reference arm constructs the model class only to
+    mint its state_dict and must not map the product library into its process).  A missing or ABI-mismatched library
+    raises ImportError / AttributeError at the first call -- there is no fallback of any kind."""
+
+    def __getattr__(self, name):
+        return getattr(_libmod.load(), name)
+
+
+_lib = _Lib()
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 ENGINE_FP32, ENGINE_TF32, ENGINE_TF32X3 = 0, 1, 2
@@ -22,15 +33,87 @@ _ENGINES = {"fp32": ENGINE_FP32, "tf32": ENGINE_TF32, "tf32x3": ENGINE_TF32X3}
 _engine = ENGINE_FP32
 
 
+# Named presets = global engine + per-group policy (groups are tagged in the model code, see `group`).  "mixed": the
+# throughput engine with the precision-critical stages in 3xTF32 (chosen from tools/precision_sweep.py's measurements).
+PRESETS = {"mixed": ("tf32", {"score": "tf32x3"})}
+_preset = None
+
+
 def set_engine(name: str) -> None:
-    """Select the contraction engine for GEMM/conv/attention/similarity: 'fp32' (SIMT, exact-order parity
-    engine), 'tf32' (tcgen05 kind::tf32), 'tf32x3' (tcgen05 3xTF32 split, fp32-grade)."""
-    global _engine
-    _engine = _ENGINES[name]
+    """Select the contraction engine for GEMM/conv/attention: 'fp32' (SIMT, exact-order parity engine), 'tf32' (tcgen05
+    kind::tf32), 'tf32x3' (tcgen05 3xTF32 split, fp32-grade), or a preset of PRESETS (global engine + per-group policy)."""
+    global _engine, _preset
+    if name in PRESETS:
+        base, pol = PRESETS[name]
+        _engine, _preset = _ENGINES[base], name
+        set_policy(pol)
+        return
+    _engine, _preset = _ENGINES[name], None
+    set_policy(None)
 
 
 def get_engine() -> str:
-    return {v: k for k, v in _ENGINES.items()}[_engine]
+    return _preset if _preset is not None else {v: k for k, v in _ENGINES.items()}[_engine]
+
+
+# Weights epoch: every cache derived from parameter VALUES (K-major weight packs, fp16 copies, folded BatchNorm, captured
+# CUDA graphs) is keyed on it.  Raw-pointer updates (the fused Adam kernel, graph replays that update BatchNorm running
+# statistics) do not bump tensor._version, so whoever changes parameter values outside autograd's view calls
+# bump_weights_epoch() (TrainStep.step, CoFiI2P.load_state_dict, TrainStep._flatten).
+_weights_epoch = 0
+
+
+def bump_weights_epoch() -> int:
+    global _weights_epoch
+    _weights_epoch += 1
+    return _weights_epoch
+
+
+def weights_epoch() -> int:
+    return _weights_epoch
+
+
+# Per-group precision policy.  The model tags its stages (`with ops.group("kpconv"): ...`); a policy maps a group name to
+# an engine and overrides the global engine for the launches issued inside that group (innermost tagged group with a policy
+# entry wins).  `set_engine("mixed")`-style presets are built from this (see PRESETS) -- it is how the throughput engine keeps
+# the precision-critical stages in 3xTF32.  Host-side only: a captured CUDA graph bakes the choice in.
+_policy: dict = {}
+_groups: list = []
+
+
+def set_policy(policy: Optional[dict]) -> None:
+    """policy: {group name: engine name} (None / {} clears it)."""
+    global _policy
+    _policy = {k: _ENGINES[v] for k, v in (policy or {}).items()}
+
+
+def get_policy() -> dict:
+    inv = {v: k for k, v in _ENGINES.items()}
+    return {k: inv[v] for k, v in _policy.items()}
+
+
+class group:
+    """Context manager tagging the launches of a model stage (see set_policy)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        _groups.append(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        _groups.pop()
+        return False
+
+
+def _eng() -> int:
+    if _policy:
+        for g in reversed(_groups):
+            e = _policy.get(g)
+            if e is not None:
+                return e
+    return _engine
 
 
 def _chk(rc: int, name: str) -> None:
@@ -259,7 +342,7 @@ def gemm(a, w, bias=None, rowdiv=None, act: int = ACT_NONE, out: Optional[torch.
     ldc = out.stride(0) if M > 1 else max(N, out.stride(0))
     _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
     _call("cofi_gemm", _p(a), lda, _p(w), ldw, _p(out), ldc, M, N, K, _p(bias), _p(rowdiv), int(accumulate), act,
-                        _engine if engine is None else engine, _st())
+                        _eng() if engine is None else engine, _st())
     return out
 
 
@@ -272,7 +355,7 @@ def gemm_colstats(a, w, bias=None, rowdiv=None):
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     stats = torch.empty((M // 128, N, 2), dtype=torch.float32, device=a.device)
     _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
-    _call("cofi_gemm_colstats", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(rowdiv), _engine, _p(stats), _st())
+    _call("cofi_gemm_colstats", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(rowdiv), _eng(), _p(stats), _st())
     return out, stats
 
 
@@ -289,7 +372,7 @@ def gemm_f16_colstats(a_half, w_half, bias=None, rowdiv=None):
 
 def colstats_ok(rows: int, frames: int, n: int) -> bool:
     """GEMM-epilogue statistics apply on the tf32 engine when every frame is a whole number of 128-row tiles."""
-    return _engine == ENGINE_TF32 and rows % frames == 0 and (rows // frames) % 128 == 0 and n >= 16 and n % 4 == 0
+    return _eng() == ENGINE_TF32 and rows % frames == 0 and (rows // frames) % 128 == 0 and n >= 16 and n % 4 == 0
 
 
 def norm_rows_pre(x, stats, frames: int, groups: int, gamma, beta, eps: float = 1e-5, residual=None, act: int = ACT_NONE,
@@ -326,7 +409,7 @@ def gemm_ln(a, w, gamma, beta, eps: float = 1e-5, bias=None, act: int = ACT_NONE
         residual, ldr = _rows(residual, "residual")
     _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (2 if residual is not None else 1)))
     _call("cofi_gemm_ln", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(gamma), _p(beta), float(eps), act,
-          _p(residual), ldr, _engine if engine is None else engine, _st())
+          _p(residual), ldr, _eng() if engine is None else engine, _st())
     return out
 
 
@@ -344,7 +427,7 @@ def conv2d_nhwc(x, w_packed, kh: int, kw: int, stride: int, pad: int, scale=None
         residual = residual.contiguous()
     _meta(2.0 * B * Ho * Wo * Cout * kh * kw * Cin, 4.0 * (x.numel() + w_packed.numel() + y.numel()))
     _call("cofi_conv2d_nhwc", _p(x), B, H, W, Cin, _p(w_packed), Cout, kh, kw, stride, pad, _p(scale), _p(shift),
-                               _p(residual), act, _p(y), _engine if engine is None else engine, _st())
+                               _p(residual), act, _p(y), _eng() if engine is None else engine, _st())
     return y
 
 
@@ -473,7 +556,7 @@ def attention(q, k, v, frames: int, heads: int, scale: float, engine: Optional[i
     out = torch.empty_like(q)
     _meta(4.0 * frames * L * S * heads * D, 4.0 * (2 * q.numel() + 2 * k.numel()))
     _call("cofi_attention", _p(q), _p(k), _p(v), L, S, frames, heads, D, float(scale), _p(out),
-                             _engine if engine is None else engine, _st())
+                             _eng() if engine is None else engine, _st())
     return out
 
 
@@ -489,20 +572,72 @@ def attention_vt(q, k, vt, frames: int, heads: int, scale: float):
 
 
 def engine_id() -> int:
-    return _engine
+    """The engine in force for the current group (policy override or the global engine)."""
+    return _eng()
 
 
 # ------------------------------------------------------------------------------------------ matching
-def sim_argmin(pt, px, frames: int = 1, engine: Optional[int] = None):
+def sim_argmin(pt, px, frames: int = 1, engine: Optional[int] = None, pt_h=None, px_h=None, stats=None):
+    """Fused similarity + arg-min (reference model/network.py:174-179): (argmin pixel per point row, min distance).
+    engine None (every product path): the EXACT result -- on the tensor cores when C is 64 or 128 (tcgen05 fp16 candidate
+    pass + exact fp32 re-rank, bit-identical to the fp32 engine), on the fp32 SIMT kernel otherwise.  engine=ENGINE_FP32
+    forces the SIMT kernel; ENGINE_TF32 / TF32X3 select the approximate tcgen05 tf32 kernel (tests, tools)."""
     pt, ldpt = _rows(pt, "pt")
     px, ldpx = _rows(px, "px")
+    C = pt.shape[1]
+    if engine is None:
+        if C in (64, 128) and ldpx % 4 == 0 and px.data_ptr() % 16 == 0:
+            return sim_argmin_exact(pt, px, frames, pt_h, px_h, stats=stats)
+        engine = ENGINE_FP32
     Npt, Npx = pt.shape[0] // frames, px.shape[0] // frames
     idx = torch.empty((pt.shape[0],), dtype=torch.int64, device=pt.device)
     val = torch.empty((pt.shape[0],), dtype=torch.float32, device=pt.device)
     _meta(2.0 * frames * Npt * Npx * pt.shape[1], 4.0 * (pt.numel() + px.numel()) + 12.0 * pt.shape[0])
-    _call("cofi_sim_argmin", _p(pt), ldpt, _p(px), ldpx, Npt, Npx, pt.shape[1], frames, _p(idx), _p(val),
-                              ENGINE_FP32 if engine is None else engine, _st())
+    _call("cofi_sim_argmin", _p(pt), ldpt, _p(px), ldpx, Npt, Npx, pt.shape[1], frames, _p(idx), _p(val), engine, _st())
     return idx, val
+
+
+def cast_f16_bound(x, bound2_slot: torch.Tensor):
+    """fp16 copy of the rows of x; bound2_slot (1-element fp32 view, zeroed by the caller) receives max |row|^2."""
+    x, ldx = _rows(x, "x")
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _call("cofi_cast_f16_bound", _p(x), ldx, x.shape[0], x.shape[1], _p(y), x.shape[1], _p(bound2_slot), _st())
+    return y
+
+
+def sim_argmin_exact(pt, px, frames: int = 1, pt_h=None, px_h=None, stats=None):
+    """tcgen05 candidate pass over fp16 copies + exact fp32 re-rank (cofi_sim_argmin_exact).  pt_h / px_h: fp16 copies of
+    the rows when the producer already emitted them (l2norm_rows_f16: unit-norm rows, fixed margin); otherwise they are
+    made here together with the norm bound that scales the margin.  stats: optional int32[2] device tensor (accumulates
+    the number of re-ranked candidates and of rows that fell back to the full exact scan)."""
+    pt, ldpt = _rows(pt, "pt")
+    px, ldpx = _rows(px, "px")
+    Npt, Npx = pt.shape[0] // frames, px.shape[0] // frames
+    C = pt.shape[1]
+    bound2 = None
+    if pt_h is None or px_h is None:
+        bound2 = torch.zeros((2,), dtype=torch.float32, device=pt.device)
+        pt_h = cast_f16_bound(pt, bound2[0:1])
+        px_h = cast_f16_bound(px, bound2[1:2])
+    if pt_h.dtype != torch.float16 or px_h.dtype != torch.float16 or not pt_h.is_contiguous() or not px_h.is_contiguous():
+        raise RuntimeError("sim_argmin_exact: contiguous CUDA fp16 copies expected")
+    idx = torch.empty((pt.shape[0],), dtype=torch.int64, device=pt.device)
+    val = torch.empty((pt.shape[0],), dtype=torch.float32, device=pt.device)
+    ws = _ws(_lib.cofi_sim_argmin_exact_workspace(Npt, Npx, frames), pt.device)
+    _meta(2.0 * frames * Npt * Npx * C, 2.0 * (pt.numel() + px.numel()) + 12.0 * pt.shape[0])
+    _call("cofi_sim_argmin_exact", _p(pt), ldpt, _p(px), ldpx, _p(pt_h), C, _p(px_h), C, Npt, Npx, C, frames, _p(bound2),
+          _p(idx), _p(val), _p(ws), _p(stats), _st())
+    return idx, val
+
+
+def l2norm_rows_f16(x):
+    """-> (F.normalize(x) fp32, its fp16 copy): the producer of cofi_sim_argmin_exact's operands."""
+    x, ldx = _rows(x, "x")
+    rows, C = x.shape
+    y = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+    yh = torch.empty((rows, C), dtype=torch.float16, device=x.device)
+    _call("cofi_l2norm_rows_f16", _p(x), ldx, rows, C, _p(y), C, _p(yh), C, _st())
+    return y, yh
 
 
 def cast_f16(x):
@@ -607,6 +742,27 @@ def nn_argmin(points, nodes):
     return idx
 
 
+def nn_argmin_batched(points, nodes, frames: int):
+    """frame f: nearest row of nodes[f] for every row of points[f] (frame-local indices)."""
+    points, nodes = _f32(points, "points").contiguous(), _f32(nodes, "nodes").contiguous()
+    n, M = points.shape[0] // frames, nodes.shape[0] // frames
+    idx = torch.empty((frames * n,), dtype=torch.int64, device=points.device)
+    _call("cofi_nn_argmin_batched", _p(points), n, _p(nodes), M, frames, _p(idx), _st())
+    return idx
+
+
+def extract_patch_batched(map_nhwc, centers, err_flag: Optional[torch.Tensor] = None):
+    """map [B,H,W,C]; centers [B,2,n] fp32 -> [B,n,C,4,4]."""
+    _f32(map_nhwc, "map")
+    map_nhwc = map_nhwc.contiguous()
+    centers = _f32(centers, "centers").contiguous()
+    B, H, W, C = map_nhwc.shape
+    n = centers.shape[2]
+    out = torch.empty((B, n, C, 4, 4), dtype=torch.float32, device=map_nhwc.device)
+    _call("cofi_extract_patch_batched", _p(map_nhwc), H, W, C, B, _p(centers), n, _p(out), _p(err_flag), _st())
+    return out
+
+
 def extract_patch(map_nhwc, b: int, centers, err_flag: Optional[torch.Tensor] = None):
     """map [B,H,W,C]; centers [2,n] fp32 (x row 0, y row 1) -> [n,C,4,4]."""
     _f32(map_nhwc, "map")
@@ -671,7 +827,7 @@ def gemm_tn(a, b):
     out = torch.empty((Mo, No), dtype=torch.float32, device=a.device)
     ws = _ws(_lib.cofi_gemm_tn_workspace(R, Mo, No), a.device)
     _meta(2.0 * R * Mo * No, 4.0 * (R * Mo + R * No + Mo * No))
-    _call("cofi_gemm_tn", _p(a), lda, _p(b), ldb, _p(out), R, Mo, No, 0, _engine, _p(ws), _st())
+    _call("cofi_gemm_tn", _p(a), lda, _p(b), ldb, _p(out), R, Mo, No, 0, _eng(), _p(ws), _st())
     return out
 
 
@@ -786,7 +942,7 @@ def conv2d_wgrad_nhwc(x, dy, kh: int, kw: int, stride: int, pad: int):
     dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=x.device)
     ws = _ws(_lib.cofi_conv2d_wgrad_workspace(B, Ho, Wo, Cout, kh, kw, Cin), x.device)
     _meta(2.0 * B * Ho * Wo * Cout * kh * kw * Cin, 4.0 * (x.numel() + dy.numel() + dw.numel()))
-    _call("cofi_conv2d_wgrad_nhwc", _p(x), B, H, W, Cin, _p(dy), Cout, kh, kw, stride, pad, _p(dw), 0, _engine, _p(ws), _st())
+    _call("cofi_conv2d_wgrad_nhwc", _p(x), B, H, W, Cin, _p(dy), Cout, kh, kw, stride, pad, _p(dw), 0, _eng(), _p(ws), _st())
     return dw
 
 
@@ -796,7 +952,7 @@ def attention_fwd_lse(q, k, v, frames: int, heads: int, scale: float):
     out = torch.empty_like(q)
     lse = torch.empty((q.shape[0], heads), dtype=torch.float32, device=q.device)
     _meta(4.0 * frames * L * S * q.shape[1], 4.0 * (2 * q.numel() + 2 * k.numel()))
-    if _engine == ENGINE_TF32 and (frames * S) % 4 == 0:  # tcgen05 flash attention (K-major V^T operand)
+    if _eng() == ENGINE_TF32 and (frames * S) % 4 == 0:  # tcgen05 flash attention (K-major V^T operand)
         vt = transpose2d(v)
         _meta(4.0 * frames * L * S * q.shape[1], 4.0 * (2 * q.numel() + 2 * k.numel()))
         _call("cofi_attention_vt_lse", _p(q), _p(k), _p(vt), L, S, frames, heads, q.shape[1] // heads, float(scale), _p(out),
@@ -814,7 +970,7 @@ def attention_bwd(q, k, v, out, dout, lse, frames: int, heads: int, scale: float
     dsum = torch.empty((q.shape[0], heads), dtype=torch.float32, device=q.device)
     _meta(10.0 * frames * L * S * q.shape[1], 4.0 * (4 * q.numel() + 4 * k.numel()))
     D = q.shape[1] // heads
-    if _engine == ENGINE_TF32 and D == 32 and L % 4 == 0 and S % 4 == 0:
+    if _eng() == ENGINE_TF32 and D == 32 and L % 4 == 0 and S % 4 == 0:
         # tcgen05 backward (tf32 operands, fp32 accumulate); Q^T, dO^T, K^T copies live in the workspace
         ws = _ws(_lib.cofi_attention_bwd_tc_workspace(L, S, frames, heads, D), q.device)
         _call("cofi_attention_bwd_tc", _p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), L, S, frames, heads, D, float(scale),

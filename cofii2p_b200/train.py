@@ -45,9 +45,13 @@ def training_losses(out, sup: Dict, opt, points4: torch.Tensor):
     score = coarse_pc_score.reshape(-1)
     loss_coarse = overlap_loss(dev, score[kpt], score[outl])                             # :256-260
     rel = torch.floor(sup["fine_xy"]) - sup["fine_center_kpt_coors"].to(torch.float32) + 2   # :267 (integer pixels)
+    # the reference indexes label[arange, rel_index] directly and raises when the supervised pixel falls outside the 4x4
+    # window (:267-283).  Inside a captured graph nothing can raise, so the violation is recorded in a device flag that
+    # TrainStep.check_errors() surfaces; the index is clamped only to keep the scatter in bounds.
+    bad = ((rel < 0) | (rel > 3)).any().to(torch.int32)
     rel_index = (rel[1] * 4 + rel[0]).long().clamp_(0, 15)
     loss_fine = fine_circle_loss(dev, fine_patch, fine_pc, rel_index, n)                 # :283
-    return loss_desc + loss_coarse + loss_fine, (loss_desc.detach(), loss_coarse.detach(), loss_fine.detach())
+    return loss_desc + loss_coarse + loss_fine, (loss_desc.detach(), loss_coarse.detach(), loss_fine.detach()), bad
 
 
 class TrainStep:
@@ -63,7 +67,7 @@ class TrainStep:
         self.live: Optional[List[torch.nn.Parameter]] = None
         self.flat_p = self.flat_g = self.m = self.v = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self._static = self._g_loss = self._g_parts = self._g_err = None
+        self._static = self._g_loss = self._g_parts = self._g_err = self._g_bad = None
 
     # -------------------------------------------------------------------------------------------------------------
     def _flatten(self, live: List[torch.nn.Parameter]) -> None:
@@ -88,6 +92,34 @@ class TrainStep:
             p.grad = g
             off += sz
         self.live = live
+        # parameter storage moved: packed-weight caches and captured inference graphs hold the old pointers
+        ops.bump_weights_epoch()
+        if hasattr(self.model, "_graphs"):
+            self.model._graphs = {}
+        self._sync_replicas()
+
+    def _sync_replicas(self) -> None:
+        """Data parallel: every rank must hold the same flat layout and start from the same values.  The layout (names and
+        sizes of the live parameters, in order) is hashed and compared across ranks -- if the live sets differed, the
+        all-reduce would mix unrelated slots -- then parameters and all buffers (BatchNorm running statistics) are
+        broadcast from rank 0."""
+        if self.world <= 1:
+            return
+        import hashlib
+        dist = torch.distributed
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        desc = ";".join(f"{names.get(id(p), '?')}:{p.numel()}" for p in self.live)
+        h = int.from_bytes(hashlib.sha256(desc.encode()).digest()[:7], "little")
+        mine = torch.tensor([h, self.flat_p.numel()], dtype=torch.int64, device=self.flat_p.device)
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        if not (torch.equal(lo, mine) and torch.equal(hi, mine)):
+            raise RuntimeError("TrainStep: the live-parameter layout differs between ranks (different parameters received a "
+                               "gradient on the first step); the flat gradient all-reduce would mix unrelated slots")
+        dist.broadcast(self.flat_p, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        for b in self.model.buffers():
+            dist.broadcast(b, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
 
     def loss(self, batch: Dict, check: bool = True):
         """Mean over the rank's frames of the reference's per-frame loss."""
@@ -98,9 +130,11 @@ class TrainStep:
         for b in range(B):
             sup = {k: batch[k][b] for k in ("pc_kpt_idx", "pc_outline_idx", "coarse_img_kpt_idx", "K_4", "P", "fine_xy",
                                            "fine_center_kpt_coors")}
-            l, p = training_losses(outs[b], sup, self.opt, batch["pc_data_dict"]["points"][-1][b * n4:(b + 1) * n4])
+            l, p, bad = training_losses(outs[b], sup, self.opt, batch["pc_data_dict"]["points"][-1][b * n4:(b + 1) * n4])
             total = l if total is None else total + l
             parts.append(torch.stack(p))
+            flags = bad if b == 0 else flags + bad
+        self.last_bad_supervision = flags
         return total / B, torch.stack(parts).mean(0)
 
     def backward(self, batch: Dict):
@@ -115,6 +149,10 @@ class TrainStep:
         loss.backward()
         if self.live is None:
             self._flatten([p for p in self.model.parameters() if p.requires_grad and p.grad is not None])
+            if self.world > 1:  # that gradient predates the rank-0 broadcast of _sync_replicas: recompute it once
+                self.flat_g.zero_()
+                loss, parts = self.loss(batch)
+                loss.backward()
         return loss.detach(), parts
 
     # -------------------------------------------------------------------------------------------------------------
@@ -142,6 +180,7 @@ class TrainStep:
             l, parts = self.loss(batch, check=False)
             l.backward()
             self._g_loss, self._g_parts, self._g_err = l.detach(), parts, self.model.last_err
+            self._g_bad = self.last_bad_supervision
         self.graph, self._static = g, batch
 
     def _load_static(self, batch: Dict) -> None:
@@ -160,6 +199,10 @@ class TrainStep:
         """Host-side check of the captured step's out-of-map flag (synchronises)."""
         if self._g_err is not None and int(self._g_err.item()) != 0:
             raise AssertionError("extract_patch: a 4x4 window falls outside the feature map")
+        bad = self._g_bad if self.graph is not None else getattr(self, "last_bad_supervision", None)
+        if bad is not None and int(bad.item()) != 0:
+            raise IndexError("fine supervision outside the 4x4 patch window (the reference's label[...] indexing raises, "
+                             "train.py:267-283)")
 
     def step(self, batch: Dict):
         if self.graph is not None:
@@ -174,4 +217,7 @@ class TrainStep:
         self.step_count += 1
         ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
                       self.step_count, grad_scale=1.0 / self.world)
+        # the raw-pointer update (and the replayed BatchNorm running-stat updates) are invisible to tensor._version:
+        # invalidate every cache derived from parameter values (packed weights, BN folds, captured inference graphs)
+        ops.bump_weights_epoch()
         return loss, parts

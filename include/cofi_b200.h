@@ -218,6 +218,10 @@ int cofi_layer_norm_rows(const float* x, int64_t ldx, int64_t rows, int C, const
 int cofi_l2norm_rows(const float* x, int64_t ldx, int64_t rows, int C, const float* add, int64_t ldadd,
                      float* y, int64_t ldy, void* stream);
 
+/* Same without `add`, also writing the fp16 copy of y that cofi_sim_argmin_exact streams through the tensor cores. */
+int cofi_l2norm_rows_f16(const float* x, int64_t ldx, int64_t rows, int C, float* y, int64_t ldy, void* y_f16,
+                         int64_t ldh, void* stream);
+
 /* Column L2 normalisation over the L rows of each frame: F.normalize(q) with default dim=1 normalises Q
  * over the SEQUENCE axis (model/transformer/transformer.py:53).  In place allowed. `work` is a caller
  * workspace of cofi_colnorm_workspace(frames, C) bytes (8-byte aligned). */
@@ -279,6 +283,24 @@ int cofi_sim_argmin_f16(const void* pt, int64_t ldpt, const void* px, int64_t ld
                         int nsplit /* >1: the pixel range is split over nsplit CTAs per point tile (fills the machine when
                                       frames*Npt/256 < #SMs); partial results go to ws_* [nsplit, frames*Npt] and are merged */,
                         int64_t* ws_idx, float* ws_val, void* stream);
+/* Exact fused similarity + arg-min on the tensor cores (model/network.py:174-179; the kernel on every product path).
+ * Pass 1 (tcgen05 kind::f16 over the fp16 copies pt_h / px_h, matrix never written) is a candidate generator: for every
+ * point row it keeps the pixels whose fp16 score lies within a margin (2 x the rigorous bound of |fp16 score - fp32
+ * score|, 2.5e-3 for unit-norm rows) of the row's best fp16 score -- the only pixels that can win the exact comparison.
+ * Pass 2 re-ranks those few candidates with the exact fp32 arithmetic of cofi_sim_argmin(engine = FP32) (rounded products,
+ * ATen cascade-sum order, d = 1 - total, lowest index on ties) from the fp32 rows pt / px, so best_idx / best_val are
+ * bit-identical to the fp32 engine's.  A row whose candidate list overflows (16 entries per pixel-range split) is scanned
+ * exactly in full.  bound2: optional device float[2] = max squared row norm of pt, px (cofi_cast_f16_bound) scaling the
+ * margin for un-normalised inputs; NULL = every row has norm <= 1 (cofi_l2norm_rows_f16 output).
+ * work: cofi_sim_argmin_exact_workspace(Npt, Npx, frames) bytes, 16-byte aligned.  stats: optional device int32[2],
+ * accumulated: candidates re-ranked, rows that needed the full scan.  C = 64 or 128. */
+int64_t cofi_sim_argmin_exact_workspace(int64_t Npt, int64_t Npx, int frames);
+int cofi_sim_argmin_exact(const float* pt, int64_t ldpt, const float* px, int64_t ldpx, const void* pt_h, int64_t ldpth,
+                          const void* px_h, int64_t ldpxh, int64_t Npt, int64_t Npx, int C, int frames, const float* bound2,
+                          int64_t* best_idx, float* best_val, void* work, int32_t* stats, void* stream);
+/* y (fp16) = x (fp32) row by row, and *bound2_slot = max(*bound2_slot, |row|^2 * 1.0001) (caller zeroes the slot). */
+int cofi_cast_f16_bound(const float* x, int64_t ldx, int64_t rows, int C, void* y, int64_t ldy, float* bound2_slot,
+                        void* stream);
 /* y[rows, C] (fp16) = x[rows, C] (fp32), round to nearest. C, ldx, ldy even. */
 int cofi_cast_f16(const float* x, int64_t ldx, int64_t rows, int C, void* y, int64_t ldy, void* stream);
 
@@ -286,7 +308,9 @@ int cofi_cast_f16(const float* x, int64_t ldx, int64_t rows, int C, void* y, int
  * find the first threshold t in thresholds[0..nthr) with at least `min_count` points satisfying
  * score >= t AND the border mask on their matched pixel (2<=x<=xmax, 2<=y<=ymax);
  * emit those point indices in ascending order.  out_count[frame*2+0] = n, out_count[frame*2+1] = index of the
- * threshold used; out_index[frame*Npt ..]; out_xy[frame*2*Npt ..] laid out as [2][Npt] (x=col, y=row, fp32). */
+ * threshold used; out_index[frame*Npt ..]; out_xy[frame*2*Npt ..] laid out as [2][Npt] (x=col, y=row, fp32).
+ * Rows n..Npt-1 of out_index / out_xy are padded with a valid dummy (index 0, centre (2,2)*xy_scale) so that fixed-shape
+ * consumers inside a captured CUDA graph stay in bounds; at most 128 thresholds. */
 int cofi_select_matches(const float* score, const int64_t* best_idx, int64_t Npt, int frames, int gridH, int gridW,
                         int xmax, int ymax /* border mask 2 <= x <= xmax, 2 <= y <= ymax; the reference hard-codes 62 / 18
                                               (network.py:184) for every grid */,
@@ -295,12 +319,18 @@ int cofi_select_matches(const float* score, const int64_t* best_idx, int64_t Npt
 
 /* point2node (model/network.py:250-264): idx[i] = argmin_j clamp(|p_i|^2 + |n_j|^2 - 2 p_i.n_j, 1e-12). */
 int cofi_nn_argmin(const float* points, int64_t n, const float* nodes, int64_t M, int64_t* idx, void* stream);
+/* Batched form: frame f matches points[f*n:(f+1)*n] against nodes[f*M:(f+1)*M]; idx is frame-local. */
+int cofi_nn_argmin_batched(const float* points, int64_t n, const float* nodes, int64_t M, int frames, int64_t* idx,
+                           void* stream);
 
 /* extract_patch (model/network.py:206-226): out[i,c,dy,dx] = map[b, floor(cy-2)+dy, floor(cx-2)+dx, c],
  * map NHWC [B,H,W,C], centres [2,n] as fp32 (x row 0, y row 1), out [n,C,4,4].  Out-of-range windows
  * return COFI_EINVAL semantics via `err_flag` (device int set to 1), mirroring the reference's assert. */
 int cofi_extract_patch(const float* map, int H, int W, int C, int b, const float* centers, int64_t n, float* out,
                        int32_t* err_flag, void* stream);
+/* Batched form: centers [frames, 2, n], frame f reads image f of map [frames,H,W,C]; out [frames, n, C, 4, 4]. */
+int cofi_extract_patch_batched(const float* map, int H, int W, int C, int frames, const float* centers, int64_t n,
+                               float* out, int32_t* err_flag, void* stream);
 
 /* Caller-side fine match (evaluation/eval_all.py:99-105): argmax over the 16 patch pixels of the cosine
  * similarity with the point feature; patch [n,C,16], pc [n,C] -> idx [n]. */

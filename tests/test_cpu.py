@@ -355,35 +355,6 @@ def test_pose_step_on_reference_golden_outputs():
     assert max(ev.pose_error(T, T)) < 1e-12
 
 
-def test_reorder_relabelling_is_consistent():
-    """cofii2p_b200/reorder.py (host-side index algebra): after Morton re-labelling every table row still points at the
-    same physical points, and per-point results map back to the caller's order."""
-    from cofii2p_b200 import reorder
-    from cofii2p_b200.frames import stack_frames
-    B = 2
-    d = stack_frames([get_frame(s, 4096) for s in (0, 1)])["pc_data_dict"]
-    perms = reorder.morton_permutations(d["points"], B)
-    d1 = reorder.permute_pyramid(d, perms, B)
-    for l in range(5):
-        n = d["points"][l].shape[0] // B
-        for f in range(B):
-            P0, P1 = d["points"][l][f * n:(f + 1) * n], d1["points"][l][f * n:(f + 1) * n]
-            i = torch.arange(0, n, 7)
-            old = perms[l][f][i]
-            assert torch.equal(P1[i], P0[old])
-            assert torch.equal(P1[d1["neighbors"][l][f * n:(f + 1) * n][i]], P0[d["neighbors"][l][f * n:(f + 1) * n][old]])
-            if l < 4:
-                m = d["points"][l + 1].shape[0] // B
-                S0, S1 = d["points"][l + 1][f * m:(f + 1) * m], d1["points"][l + 1][f * m:(f + 1) * m]
-                assert torch.equal(S1[d1["upsampling"][l][f * n:(f + 1) * n][i]], S0[d["upsampling"][l][f * n:(f + 1) * n][old]])
-                j = torch.arange(0, m, 5)
-                oldq = perms[l + 1][f][j]
-                assert torch.equal(P1[d1["subsampling"][l][f * m:(f + 1) * m][j]], P0[d["subsampling"][l][f * m:(f + 1) * m][oldq]])
-    x = torch.randn(d["points"][4].shape[0], 3)
-    assert torch.equal(reorder.unpermute_rows(reorder._rows(x, perms[4]), perms[4]), x)
-    assert torch.equal(d1["feats"], reorder._rows(d["feats"], perms[0]))
-
-
 def test_committed_bench_lines_follow_the_contract():
     """The bench lines committed under profiles/ (written by bench.py on the B200) carry every key of the measurement
     contract: metric/value/unit, e2e with host<->device byte counts, gpu_launches, roofline, cpu_baseline, clocks."""

@@ -317,7 +317,7 @@ def test_model_gradients_vs_oracle_autograd(seeded_sd):
                else v.clone()) for k, v in seeded_sd.items()}
     out = restate.forward(sdr, frame["pc_data_dict"], frame["img"], frame["fine_center_kpt_coors"], frame["fine_xy"],
                           frame["fine_pc_inline_index"], "train", bn_training=True)
-    ref_loss, ref_parts = training_losses(out, _sup(frame), opt, frame["pc_data_dict"]["points"][-1])
+    ref_loss, ref_parts, _ = training_losses(out, _sup(frame), opt, frame["pc_data_dict"]["points"][-1])
     ref_loss.backward()
     ref_loss = ref_loss.detach()
     assert abs(float(loss) - float(ref_loss)) < 1e-4 * max(1.0, abs(float(ref_loss))), (float(loss), float(ref_loss))
@@ -443,3 +443,50 @@ def test_attention_backward_tcgen05(L, S, frames):
             assert _nrm_err(got, ref) < 3e-3, (name, _nrm_err(got, ref))
     finally:
         ops.set_engine("fp32")
+
+
+@pytest.mark.parametrize("captured", [False, True])
+def test_eval_after_training_uses_the_updated_weights(seeded_sd, captured):
+    """The fused Adam kernel writes parameters through raw pointers (no tensor._version bump) and a replayed step graph
+    updates BatchNorm running statistics the same way: the eval-path caches (K-major KPConv / conv weight packs, folded
+    BatchNorm, captured inference graphs) must be invalidated by the step (ops.weights_epoch).  Train k steps, then
+    compare model.eval() -- eager, graph-cached forward and a pre-built InferenceEngine -- against a FRESH model loaded
+    from the trained state_dict (the reference validates inside its training loop, train.py:70)."""
+    from cofii2p_b200 import ops
+    from cofii2p_b200.engine import InferenceEngine
+    from cofii2p_b200.frames import frame_to, stack_frames
+    from cofii2p_b200.model.network import CoFiI2P
+    from cofii2p_b200.options import Options_KITTI
+    from cofii2p_b200.train import TrainStep
+    ops.set_engine("fp32")
+    frame = frame_to(get_frame(0, 4096), "cuda")
+    batch = stack_frames([frame])
+    args = [frame[k] for k in ("pc_data_dict", "img", "fine_center_kpt_coors", "fine_xy", "fine_pc_inline_index")]
+    model, opt = _fresh_model(seeded_sd)
+    model.eval()
+    with torch.no_grad():
+        before = model(*args, "val")                      # fills every eval-path cache with the initial weights
+    model.enable_cuda_graph(True)
+    with torch.no_grad():
+        model(*args, "val")                               # ... and captures a graph of them
+    eng = InferenceEngine(model, batch, mode="val", use_graph=True)
+    ts = TrainStep(model, opt, lr=1e-3)
+    if captured:
+        ts.enable_cuda_graph(stack_frames([frame_to(get_frame(0, 4096), "cuda")]))
+    for _ in range(3):
+        ts.step(batch)
+    fresh = CoFiI2P(Options_KITTI())
+    fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, strict=True)
+    fresh = fresh.cuda().eval()
+    model.eval()
+    with torch.no_grad():
+        want = fresh(*args, "val")
+        got_graph = model(*args, "val")
+        model.enable_cuda_graph(False)
+        got_eager = model(*args, "val")
+    eng.run()
+    got_engine = eng.results()[0]
+    assert rel_err(want[0], before[0]) > 1e-4             # the three steps really moved the weights
+    for got in (got_graph, got_eager, got_engine):
+        for a, b in zip(got[:6], want[:6]):
+            assert rel_err(a, b) < 1e-5, rel_err(a, b)

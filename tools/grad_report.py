@@ -33,7 +33,7 @@ def main():
                           frame["fine_pc_inline_index"], "train", bn_training=True)
     sup = {k: frame[k] for k in ("pc_kpt_idx", "pc_outline_idx", "coarse_img_kpt_idx", "K_4", "P", "fine_xy",
                                  "fine_center_kpt_coors")}
-    ref_loss, _ = training_losses(out, sup, opt, frame["pc_data_dict"]["points"][-1])
+    ref_loss, _, _ = training_losses(out, sup, opt, frame["pc_data_dict"]["points"][-1])
     ref_loss.backward()
     print("loss", float(loss), float(ref_loss))
     rows = []

@@ -7,7 +7,7 @@ import torch
 from bench import build_model
 from cofii2p_b200 import ops
 from cofii2p_b200.frames import make_frame, stack_frames
-from cofii2p_b200.reorder import morton_permutations, permute_pyramid
+from reorder import morton_permutations, permute_pyramid
 
 ops.set_engine("tf32")
 dev = torch.device("cuda", 0)

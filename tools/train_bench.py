@@ -59,7 +59,7 @@ def cpu_train_step(sd, frame, opt, threads=None):
     t = time.perf_counter()
     out = restate.forward(sdr, frame["pc_data_dict"], frame["img"], frame["fine_center_kpt_coors"], frame["fine_xy"],
                           frame["fine_pc_inline_index"], "train", run_dead=True, bn_training=True)
-    loss, _ = training_losses(out, {k: frame[k] for k in SUP}, opt, frame["pc_data_dict"]["points"][-1])
+    loss, _, _ = training_losses(out, {k: frame[k] for k in SUP}, opt, frame["pc_data_dict"]["points"][-1])
     loss.backward()
     return time.perf_counter() - t, float(loss.detach())
 
@@ -92,6 +92,81 @@ def run_reference(args):
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} iterations, oracle/restate.py forward + torch autograd backward, {cores} threads"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+
+
+def train_leg(args, dev, world, rank, local, steps=None):
+    """The data-parallel training step (configs[4]) as one leg of bench.py's default line: 4 frames per GPU, forward (train
+    mode) + the reference's three losses + backward captured in a CUDA graph, NCCL gradient all-reduce over NVLink, fused
+    Adam.  Returns a dict for rank 0's JSON line: frames/s over all ranks (max over ranks of the device time), ms per step,
+    and the all-reduce cost: `allreduce_ms_isolated` (the collective timed alone) and `allreduce_ms_exposed` (step time with
+    the collective minus the same step with it skipped) -- all measured in this run."""
+    import torch.distributed as dist
+    import bench
+    from cofii2p_b200 import ops
+    from cofii2p_b200.frames import make_frame, stack_frames
+    from cofii2p_b200.options import Options_KITTI
+    from cofii2p_b200.shard import frames_for_rank
+    from cofii2p_b200.train import TrainStep
+    steps = steps or args.steps
+    engine = "tf32" if args.engine == "mixed" else args.engine
+    ops.set_engine(engine)
+    model, _ = bench.build_model(dev)
+    model.train()
+    opt = Options_KITTI()
+    B = args.train_batch
+    frames = [make_frame(s, num_pc=args.num_pc, cache_dir="/tmp/cofi_frames", device=f"cuda:{local}")
+              for s in frames_for_rank(rank, world, B)]
+    batch = _map(stack_frames(frames), lambda t: t.to(dev))
+    ts = TrainStep(model, opt)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    losses = []
+    for _ in range(2):
+        losses.append(float(ts.step(batch)[0]))
+    if not args.no_graph:
+        ts.enable_cuda_graph(batch)
+    for _ in range(3):
+        ts.step(batch)
+    ms = timed(lambda: ts.step(batch), steps)
+    losses.append(float(ts.step(batch)[0]))
+    ts.check_errors()
+    out = {"metric": METRIC, "value": world * B * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps,
+           "frames_per_gpu_per_step": B, "engine": engine, "cuda_graph": ts.graph is not None, "parallelism": f"dp{world}",
+           "live_parameters": int(ts.flat_p.numel()), "loss_first_last": [losses[0], losses[-1]],
+           "allreduce_bytes_per_step": int(ts.flat_g.numel() * 4) if world > 1 else 0,
+           "efficiency_basis": "weak scaling: 4 frames per GPU at every N; efficiency = value(N) / (N * value(1)) from the "
+                               "train.value of the N=1 line of the same scaling run",
+           "what": "configs[4]: forward(train) + desc/overlap/fine circle losses + backward (one CUDA graph), one NCCL all-reduce "
+                   "of the flat gradient, one fused Adam kernel"}
+    if world > 1:
+        ms_ar = timed(lambda: dist.all_reduce(ts.flat_g), steps)
+        w, ts.world = ts.world, 1          # the same step with the collective skipped (timing only; gradients unscaled)
+        ms_no = timed(lambda: ts.step(batch), steps)
+        ts.world = w
+        out["allreduce_ms_isolated"] = ms_ar / steps
+        out["allreduce_ms_exposed"] = max(ms - ms_no, 0.0) / steps
+        out["ms_per_step_without_allreduce"] = ms_no / steps
+    del ts, model
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_train(args):
