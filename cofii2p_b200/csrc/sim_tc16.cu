@@ -177,36 +177,43 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const float cm = fmaxf(fmaxf(fmaxf(m01[0], m01[1]), fmaxf(m01[2], m01[3])),
                                        fmaxf(fmaxf(m01[4], m01[5]), fmaxf(m01[6], m01[7])));
                 if (CAND) {
-                    if (cm > thr) {  // some score of this chunk is within the margin of the running best
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float v = __uint_as_float(raw[i]);
-                            if (v > thr) {
-                                if (v > best) {
-                                    best = v;
-                                    bidx = base + c * 32 + i;
-                                    thr = best - margin;
+                    // A lane enters when its chunk holds a score within the margin of its running best (a handful of
+                    // times per row).  Lanes diverge here, so the body is kept branch-light: the running best is updated
+                    // from the chunk maximum first, then only the 4-score groups whose partial maximum (m01, already
+                    // computed for cm) passes the threshold are visited, and a visited score is stored unconditionally
+                    // at the list tail, which advances only when the score qualifies.
+                    if (cm > thr) {
+                        best = fmaxf(best, cm);
+                        thr = best - margin;
+                        if (cnt >= S16_CAP - 4) {  // make room: drop what fell out of the margin since it was appended
+                            int k2 = 0;
+                            for (int k = 0; k < cnt; ++k) {
+                                const float ov = lv[k * S16_ROWS + r];
+                                if (ov > thr) {
+                                    lv[k2 * S16_ROWS + r] = ov;
+                                    li[k2 * S16_ROWS + r] = li[k * S16_ROWS + r];
+                                    ++k2;
                                 }
-                                if (cnt == S16_CAP) {  // compact: drop what fell out of the margin since it was appended
-                                    int k2 = 0;
-                                    for (int k = 0; k < S16_CAP; ++k) {
-                                        const float ov = lv[k * S16_ROWS + r];
-                                        if (ov > thr) {
-                                            lv[k2 * S16_ROWS + r] = ov;
-                                            li[k2 * S16_ROWS + r] = li[k * S16_ROWS + r];
-                                            ++k2;
-                                        }
-                                    }
-                                    cnt = k2;
-                                    if (cnt == S16_CAP) {
-                                        ovf = true;
-                                        cnt = S16_CAP - 1;
-                                    }
-                                }
-                                lv[cnt * S16_ROWS + r] = v;
-                                li[cnt * S16_ROWS + r] = base + c * 32 + i;
-                                ++cnt;
                             }
+                            cnt = k2;
+                        }
+#pragma unroll
+                        for (int g2 = 0; g2 < 8; ++g2) {
+                            if (m01[g2] > thr) {  // m01[g2] = max of raw[2g2], raw[2g2+1], raw[2g2+16], raw[2g2+17]
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int i = 2 * g2 + (e & 1) + (e >> 1) * 16;
+                                    const float v = __uint_as_float(raw[i]);
+                                    const int slot = cnt < S16_CAP ? cnt : S16_CAP - 1;
+                                    lv[slot * S16_ROWS + r] = v;
+                                    li[slot * S16_ROWS + r] = base + c * 32 + i;
+                                    cnt += (v > thr) ? 1 : 0;
+                                }
+                            }
+                        }
+                        if (cnt >= S16_CAP) {  // the tail slot may have been overwritten: the row is re-scanned exactly
+                            ovf = true;
+                            cnt = S16_CAP;
                         }
                     }
                 } else if (cm > best) {  // rare once the running best has warmed up; strict > keeps the lowest index on ties
@@ -231,7 +238,7 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             p.best_val[o] = CAND ? best : 1.0f - best;   // CAND: the raw fp16-engine score (the re-rank thresholds on it)
             if (CAND) {
                 int k2 = 0;
-                for (int k = 0; k < cnt; ++k) {
+                for (int k = 0; k < cnt && !ovf; ++k) {
                     const float ov = lv[k * S16_ROWS + r];
                     if (ov > thr) {
                         p.cand_val[o * S16_CAP + k2] = ov;

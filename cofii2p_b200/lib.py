@@ -23,6 +23,7 @@ SIGNATURES = {
     "cofi_maxpool_rows": (_i, [_vp, _l, _i, _vp, _i, _l, _l, _i, _vp, _l, _vp]),
     "cofi_maxpool_rows_f16": (_i, [_vp, _l, _i, _vp, _i, _l, _l, _i, _vp, _l, _vp]),
     "cofi_gather_rows": (_i, [_vp, _l, _i, _vp, _l, _l, _l, _i, _vp, _l, _vp]),
+    "cofi_half_sample_pyramid": (_i, [_vp, _l, _i, _i, ctypes.c_uint64, _vp, _vp, _vp]),
     "cofi_knn_pyramid_workspace": (_l, [_vp, _i, _i]),
     "cofi_knn_pyramid": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "cofi_knn_table_workspace": (_l, [_l, _l, _i]),

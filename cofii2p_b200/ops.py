@@ -720,6 +720,24 @@ def knn_pyramid(points, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT, w
     return out
 
 
+def half_sample_pyramid(points0, frames: int = 1, levels: int = 5, seed: int = 0, want_index: bool = False):
+    """Device-side random half-sampling (reference model/kpconv/preprocess_data.py:52-68, WITH replacement; counter-based
+    Philox draw, see cofi_half_sample_pyramid).  points0 [frames*n0, 3] -> list of `levels` clouds [frames*(n0>>l), 3]
+    (entry 0 is points0 itself) and, with want_index, the frame-local level-0 row every sampled row was copied from."""
+    points0 = _f32(points0, "points0").contiguous()
+    n0 = points0.shape[0] // frames
+    if points0.dim() != 2 or points0.shape[1] != 3 or n0 * frames != points0.shape[0] or (n0 >> (levels - 1)) < 1:
+        raise RuntimeError(f"half_sample_pyramid: expected [frames*n0, 3] with n0 >= 2^(levels-1), got {tuple(points0.shape)}")
+    dev = points0.device
+    outs = [points0] + [torch.empty((frames * (n0 >> l), 3), dtype=torch.float32, device=dev) for l in range(1, levels)]
+    idxs = [None] + [torch.empty((frames * (n0 >> l),), dtype=torch.int64, device=dev) for l in range(1, levels)] \
+        if want_index else None
+    po = (ctypes.c_void_p * levels)(*[t.data_ptr() for t in outs])
+    pi = (ctypes.c_void_p * levels)(*[0 if t is None else t.data_ptr() for t in idxs]) if want_index else None
+    _call("cofi_half_sample_pyramid", _p(points0), n0, frames, levels, int(seed) & 0xFFFFFFFFFFFFFFFF, po, pi, _st())
+    return (outs, idxs) if want_index else outs
+
+
 def knn_table(src, qry, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT):
     """out[frames*nq, k]: the k nearest rows of src for every row of qry (`knn(nodes, points, k)`,
     reference model/kpconv/preprocess_data.py:131-143)."""

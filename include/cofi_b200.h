@@ -110,6 +110,15 @@ int cofi_gather_rows(const float* x, int64_t ldx, int C, const int64_t* idx, int
                                model/kpconv/preprocess_data.py:110-143 (precompute_point_cloud_cuda) */
 #define COFI_KNN_NOCULL 0x100 /* OR-ed into `mode`: open every tile (brute force; same result, test/debug only) */
 
+/* Random half-sampling of the pyramid on the device (model/kpconv/preprocess_data.py:52-68: level l+1 = level l at
+ * n/2 indices drawn WITH replacement).  The draw is counter-based so that the host oracle restates it exactly:
+ * u = Philox4x32-10(counter (j, frame, level, 0), key seed)[0], index = (u * n_{level-1}) >> 32 for output row j.
+ * pts0 [frames*n0, 3]; out_levels / out_index: HOST arrays of `levels` device pointers (entry 0 unused; out_index or its
+ * entries may be NULL): out_levels[l] [frames*(n0>>l), 3], out_index[l] [frames*(n0>>l)] = frame-local level-0 row copied.
+ * One launch for all levels and frames. */
+int cofi_half_sample_pyramid(const float* pts0, int64_t n0, int frames, int levels, uint64_t seed,
+                             float* const* out_levels, int64_t* const* out_index, void* stream);
+
 /* Exact k-nearest-neighbour tables of a whole point pyramid, all frames and all tables in two launches
  * (Morton sort + warp-per-query search).  Replaces the 13 KNNSearch / knn() calls of
  * model/kpconv/preprocess_data.py:75-99 (stack mode) and :172-190 (cuda mode).

@@ -62,6 +62,40 @@ def half_sample_pyramid(points: np.ndarray, num_stages: int, rng=np.random):
     return levels
 
 
+def philox4x32_10_word0(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11), first output word, vectorised over numpy uint32 arrays."""
+    u32, u64 = np.uint32, np.uint64
+    c0, c1, c2, c3 = (np.asarray(c, dtype=u32) for c in np.broadcast_arrays(c0, c1, c2, c3))
+    k0, k1 = u32(k0), u32(k1)
+    for _ in range(10):
+        p0 = u64(0xD2511F53) * c0.astype(u64)
+        p1 = u64(0xCD9E8D57) * c2.astype(u64)
+        n0 = (p1 >> u64(32)).astype(u32) ^ c1 ^ k0
+        n1 = p1.astype(u32)
+        n2 = (p0 >> u64(32)).astype(u32) ^ c3 ^ k1
+        n3 = p0.astype(u32)
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = u32((int(k0) + 0x9E3779B9) & 0xFFFFFFFF)
+        k1 = u32((int(k1) + 0xBB67AE85) & 0xFFFFFFFF)
+    return c0
+
+
+def half_sample_pyramid_philox(points0: np.ndarray, num_stages: int, seed: int, frame: int = 0):
+    """The device sampler's definition (csrc/sample.cu), restated: points0 [N, 3] -> (levels [N_i, 3], level-0 indices).
+    Same distribution as preprocess_data.py:58 (n // 2 indices WITH replacement per stage), drawn from a counter-based
+    generator instead of numpy's global stream: index_j = (Philox(j, frame, level, 0; seed)[0] * n_prev) >> 32."""
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    levels, index = [np.ascontiguousarray(points0, dtype=f32)], [np.arange(points0.shape[0], dtype=np.int64)]
+    for l in range(1, num_stages):
+        n_prev = levels[-1].shape[0]
+        j = np.arange(n_prev // 2, dtype=np.uint32)
+        u = philox4x32_10_word0(j, np.uint32(frame), np.uint32(l), np.uint32(0), k0, k1)
+        pick = ((u.astype(np.uint64) * np.uint64(n_prev)) >> np.uint64(32)).astype(np.int64)
+        levels.append(levels[-1][pick])
+        index.append(index[-1][pick])
+    return levels, index
+
+
 def pyramid_tables(levels, k: int = 128, mode: int = DIRECT):
     """dict(neighbors, subsampling, upsampling) of int64 tables (preprocess_data.py:75-99)."""
     L = len(levels)
