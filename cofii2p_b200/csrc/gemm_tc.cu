@@ -12,10 +12,9 @@
 //   warp 1     MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) four times
 //              per k-block on UMMA shared-memory descriptors; fp32 accumulator lives in TMEM (BN columns);
 //              tcgen05.commit releases ring slots and finally signals the epilogue.
-//   warps 2-9  epilogue (two warps per TMEM lane quarter, alternating over the 32-column chunks; warps 2-5 only for
-//              3xTF32): tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused rowdiv / per-channel
+//   warps 2-9  epilogue (two warps per TMEM lane quarter, alternating over the 32-column chunks): tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused rowdiv / per-channel
 //              affine / bias / residual / accumulate / activation, 128-byte vector stores.
-//   warps 6-9  (TF32X3 only) operand splitters: rewrite each landed tile in place as hi = tf32-truncated value and
+//   warps 10-15 (TF32X3 only) operand splitters: rewrite each landed tile in place as hi = tf32-truncated value and
 //              write lo = x - hi into a second buffer; the issuer then runs hi*hi + lo*hi + hi*lo (3xTF32), which
 //              restores fp32-grade accuracy on the tensor cores.  The split is element-wise, hence swizzle-agnostic.
 #include <stdlib.h>
@@ -180,9 +179,10 @@ struct Cfg {
     static constexpr int NS = (BN == 128) ? 3 : 4;
     static constexpr int RING = STAGE * NS * (X3 ? 2 : 1);
     static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */ + 12 * BN * 4 /* epilogue vectors + column statistics */;
-    static constexpr int EPI_SETS = X3 ? 1 : 2;  // epilogue warp sets (4 warps each, one per TMEM lane quarter); the sets
+    static constexpr int EPI_SETS = 2;           // epilogue warp sets (4 warps each, one per TMEM lane quarter); the sets
                                                  // interleave over the 32-column chunks of the tile
-    static constexpr int THREADS = 320;          // 2 + 4 * EPI_SETS warps (+ 4 operand splitters for 3xTF32)
+    static constexpr int SPLIT_WARPS = X3 ? 6 : 0;                       // operand splitters (3xTF32 only)
+    static constexpr int THREADS = 32 * (2 + 4 * EPI_SETS + SPLIT_WARPS);  // TMA warp, MMA warp, epilogue sets, splitters
 };
 
 template <int BN, bool CONV, bool X3, bool HALF = false>
@@ -225,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < C::NS; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
-            mbar_init(&ready[s], 4);
+            mbar_init(&ready[s], C::SPLIT_WARPS > 0 ? C::SPLIT_WARPS : 1);
         }
         mbar_init(tmem_full, 1);
         mbar_fence_init();
@@ -547,27 +547,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
     } else if (X3) {
         // ================================ operand splitters (3xTF32) ==================
-        const int t = threadIdx.x - 192;  // 0..127
+        constexpr int NT = C::SPLIT_WARPS * 32;
+        const int t = threadIdx.x - 32 * (2 + 4 * C::EPI_SETS);  // 0 .. NT-1
         for (int kb = 0; kb < p.num_kb; ++kb) {
             const int s = kb % C::NS;
             const uint32_t ph = (uint32_t)(kb / C::NS) & 1u;
             mbar_wait(&full[s], ph);
-            float4* hi = reinterpret_cast<float4*>(smem + s * C::STAGE);
-            float4* lo = reinterpret_cast<float4*>(lo_base + s * C::STAGE);
+            uint4* hi = reinterpret_cast<uint4*>(smem + s * C::STAGE);
+            uint4* lo = reinterpret_cast<uint4*>(lo_base + s * C::STAGE);
+            // hi = x rounded to tf32 (half-up on the bit pattern: 2 integer ops), lo = (x - hi) rounded the same way: both are
+            // exact inputs of the tensor core, so the only error left is the 2^-22-relative rounding of lo.  This loop sits
+            // between the TMA landing and the MMA issue of every k-block: ~5 ALU operations per element.
 #pragma unroll 4
-            for (int i = t; i < C::STAGE / 16; i += 128) {
-                const float4 x = hi[i];
-                float4 h, l;
-                // hi = x rounded to tf32 (nearest-even), lo = (x - hi) rounded to tf32: both are then exact inputs
-                // of the tensor core, so the only error left is the unbiased 2^-23 rounding of lo
-                h.x = rn_tf32(x.x);
-                h.y = rn_tf32(x.y);
-                h.z = rn_tf32(x.z);
-                h.w = rn_tf32(x.w);
-                l.x = rn_tf32(x.x - h.x);
-                l.y = rn_tf32(x.y - h.y);
-                l.z = rn_tf32(x.z - h.z);
-                l.w = rn_tf32(x.w - h.w);
+            for (int i = t; i < C::STAGE / 16; i += NT) {
+                const uint4 x = hi[i];
+                uint4 h, l;
+                h.x = (x.x + 0x1000u) & 0xFFFFE000u;
+                h.y = (x.y + 0x1000u) & 0xFFFFE000u;
+                h.z = (x.z + 0x1000u) & 0xFFFFE000u;
+                h.w = (x.w + 0x1000u) & 0xFFFFE000u;
+                l.x = (__float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x)) + 0x1000u) & 0xFFFFE000u;
+                l.y = (__float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) + 0x1000u) & 0xFFFFE000u;
+                l.z = (__float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) + 0x1000u) & 0xFFFFE000u;
+                l.w = (__float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) + 0x1000u) & 0xFFFFE000u;
                 hi[i] = h;
                 lo[i] = l;
             }

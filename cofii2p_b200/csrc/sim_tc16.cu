@@ -53,6 +53,17 @@ __device__ __forceinline__ float sim_margin(float base, const float* bound2) {
     return m + 2.5e-7f;
 }
 
+// explicit shared-state-space accesses: the dynamic-smem base is re-aligned through integer arithmetic, after which the
+// compiler only knows a GENERIC pointer and would emit ST.E / LD.E (64-bit generic addressing) in the hot candidate scan
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 template <bool CAND>
 __global__ void __launch_bounds__(320)
 sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -68,8 +79,11 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t* s_full = empty + S16_RING;   // [2]
     uint64_t* s_empty = s_full + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
-    float* lv = reinterpret_cast<float*>(smem + S16_SMEM - 1024);   // [S16_CAP][S16_ROWS] (CAND only; past the 1 KB align slack)
-    int* li = reinterpret_cast<int*>(lv + S16_CAP * S16_ROWS);
+    // candidate lists (CAND only; past the 1 KB alignment slack): values [S16_CAP][S16_ROWS] then indices, as shared-space
+    // byte addresses; slot k of row r lives at lv_s + k * SLOT_B + r * 4
+    const uint32_t lv_s = smem_u32(smem + S16_SMEM - 1024);
+    const uint32_t li_s = lv_s + S16_CAP * S16_ROWS * 4;
+    constexpr uint32_t SLOT_B = S16_ROWS * 4;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int frame = blockIdx.y;
@@ -188,10 +202,10 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         if (cnt >= S16_CAP - 4) {  // make room: drop what fell out of the margin since it was appended
                             int k2 = 0;
                             for (int k = 0; k < cnt; ++k) {
-                                const float ov = lv[k * S16_ROWS + r];
-                                if (ov > thr) {
-                                    lv[k2 * S16_ROWS + r] = ov;
-                                    li[k2 * S16_ROWS + r] = li[k * S16_ROWS + r];
+                                const uint32_t ov = lds32(lv_s + k * SLOT_B + r * 4);
+                                if (__uint_as_float(ov) > thr) {
+                                    sts32(lv_s + k2 * SLOT_B + r * 4, ov);
+                                    sts32(li_s + k2 * SLOT_B + r * 4, lds32(li_s + k * SLOT_B + r * 4));
                                     ++k2;
                                 }
                             }
@@ -204,9 +218,9 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                 for (int e = 0; e < 4; ++e) {
                                     const int i = 2 * g2 + (e & 1) + (e >> 1) * 16;
                                     const float v = __uint_as_float(raw[i]);
-                                    const int slot = cnt < S16_CAP ? cnt : S16_CAP - 1;
-                                    lv[slot * S16_ROWS + r] = v;
-                                    li[slot * S16_ROWS + r] = base + c * 32 + i;
+                                    const uint32_t off = (uint32_t)(cnt < S16_CAP ? cnt : S16_CAP - 1) * SLOT_B + r * 4;
+                                    sts32(lv_s + off, raw[i]);
+                                    sts32(li_s + off, (uint32_t)(base + c * 32 + i));
                                     cnt += (v > thr) ? 1 : 0;
                                 }
                             }
@@ -239,10 +253,10 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (CAND) {
                 int k2 = 0;
                 for (int k = 0; k < cnt && !ovf; ++k) {
-                    const float ov = lv[k * S16_ROWS + r];
+                    const float ov = __uint_as_float(lds32(lv_s + k * SLOT_B + r * 4));
                     if (ov > thr) {
                         p.cand_val[o * S16_CAP + k2] = ov;
-                        p.cand_idx[o * S16_CAP + k2] = li[k * S16_ROWS + r];
+                        p.cand_idx[o * S16_CAP + k2] = (int32_t)lds32(li_s + k * SLOT_B + r * 4);
                         ++k2;
                     }
                 }

@@ -331,6 +331,23 @@ def test_preprocess_surface_without_gpu():
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
+def test_philox_known_answers_and_sampler_oracle():
+    """oracle/knn.py::philox4x32_10_word0 against the published Random123 known-answer vectors (kat_vectors: philox4x32
+    10 rounds), and the sampler restatement's shape / range / determinism."""
+    from oracle import knn as ok
+    assert int(ok.philox4x32_10_word0(0, 0, 0, 0, 0, 0)) == 0x6627e8d5
+    assert int(ok.philox4x32_10_word0(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)) == 0x408f276d
+    assert int(ok.philox4x32_10_word0(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)) == 0xd16cfe09
+    pts = np.random.default_rng(0).normal(size=(2048, 3)).astype(np.float32)
+    a, ia = ok.half_sample_pyramid_philox(pts, 5, seed=42, frame=1)
+    b, ib = ok.half_sample_pyramid_philox(pts, 5, seed=42, frame=1)
+    c, _ = ok.half_sample_pyramid_philox(pts, 5, seed=43, frame=1)
+    assert [x.shape[0] for x in a] == [2048, 1024, 512, 256, 128]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and not np.array_equal(a[1], c[1])
+    for l in range(1, 5):
+        assert ia[l].min() >= 0 and ia[l].max() < 2048 and np.array_equal(a[l], pts[ia[l]])
+
+
 # ---------------------------------------------------------------------------------------------- pose step (row f2)
 def test_pose_step_on_reference_golden_outputs():
     """oracle/evaluate.py (eval_all.py:99-105) + the shared cv2 / get_P_diff wrappers on the reference's frozen test-mode

@@ -230,3 +230,29 @@ def test_precompute_point_cloud_cuda_surface():
     for name in ("neighbors", "subsampling", "upsampling"):
         for i, t in enumerate(want[name]):
             assert np.array_equal(out[name][i].numpy(), t), (name, i)
+
+
+@pytest.mark.parametrize("n0,frames,levels,seed", [(20480, 2, 5, 0), (4096, 3, 5, 12345678901234), (1000, 1, 4, 7)])
+def test_device_half_sampling_matches_the_oracle(n0, frames, levels, seed):
+    """cofi_half_sample_pyramid (reference preprocess_data.py:52-68 semantics: n//2 draws WITH replacement per stage; the
+    draw itself is the counter-based Philox definition) against oracle/knn.py::half_sample_pyramid_philox, bit for bit,
+    including the level-0 index of every sampled row; and the sampled pyramid feeds the table builder."""
+    import numpy as np
+    from cofii2p_b200 import ops
+    from oracle import knn as ok
+    g = torch.Generator().manual_seed(n0)
+    pts = (torch.rand((frames * n0, 3), generator=g) - 0.5) * 100
+    levels_d, index_d = ops.half_sample_pyramid(pts.cuda(), frames, levels, seed, want_index=True)
+    assert levels_d[0].data_ptr() != 0 and len(levels_d) == levels
+    for f in range(frames):
+        ref_l, ref_i = ok.half_sample_pyramid_philox(pts[f * n0:(f + 1) * n0].numpy(), levels, seed, frame=f)
+        for l in range(1, levels):
+            nl = n0 >> l
+            assert tuple(levels_d[l].shape) == (frames * nl, 3)
+            assert np.array_equal(levels_d[l][f * nl:(f + 1) * nl].cpu().numpy(), ref_l[l])
+            assert np.array_equal(index_d[l][f * nl:(f + 1) * nl].cpu().numpy(), ref_i[l])
+    # the draw is with replacement: duplicates exist -- 2 (1 - e^-0.5) = 79 % of the n/2 draws are distinct
+    hit = torch.unique(index_d[1][:n0 // 2]).numel() / (n0 // 2)
+    assert 0.70 < hit < 0.87, hit
+    tabs = ops.knn_pyramid(levels_d, frames=frames, k=16)
+    assert tabs["neighbors"][1].shape == (frames * (n0 >> 1), 16)

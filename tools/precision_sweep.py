@@ -32,11 +32,13 @@ def main():
     ops.set_engine("tf32")
     model, _ = bench.build_model(dev)
     batch = stack_frames([make_frame(i, cache_dir="/tmp/cofi_frames", device="cuda") for i in range(8)])
-    configs = [("tf32", "tf32", {}), ("tf32x3", "tf32x3", {}), ("fp32", "fp32", {})]
-    for g in GROUPS:
-        configs.append((f"tf32 + {g}@x3", "tf32", {g: "tf32x3"}))
-    for g in GROUPS:
-        configs.append((f"x3 + {g}@tf32", "tf32x3", {g: "tf32"}))
+    configs = [("tf32", "tf32", {}), ("tf32x3", "tf32x3", {})]
+    if "--only-policies" not in sys.argv:
+        configs.append(("fp32", "fp32", {}))
+        for g in GROUPS:
+            configs.append((f"tf32 + {g}@x3", "tf32", {g: "tf32x3"}))
+        for g in GROUPS:
+            configs.append((f"x3 + {g}@tf32", "tf32x3", {g: "tf32"}))
     for extra in sys.argv[1:]:
         if extra.startswith("--policy="):  # e.g. --policy=tf32:kpconv=tf32x3,score=tf32x3
             base, _, rest = extra[len("--policy="):].partition(":")
