@@ -172,24 +172,31 @@ __device__ __forceinline__ float rn_tf32(float x) {
     return __uint_as_float(b & 0xFFFFE000u);
 }
 
-template <int BN, bool X3>
+// LIGHT (3xTF32 only): the configuration for short contractions (K <= 256).  Those launches are one load -> split -> MMA ->
+// epilogue chain per CTA with nothing to overlap inside the CTA, so what matters is how many CTAs an SM holds: a 2-stage
+// ring (hi + lo copies: <= 96 KB for BN <= 64), one epilogue set and four splitter warps = 320 threads at <= 102 registers,
+// two CTAs per SM -- the same residency as the plain tf32 kernel.  The deep configuration (3 stages, two epilogue sets, six
+// splitter warps, one CTA per SM) serves the long, tensor-bound contractions.
+template <int BN, bool X3, bool LIGHT = false>
 struct Cfg {
     static constexpr int B_BYTES = BN * TK * 4;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int NS = (BN == 128) ? 3 : 4;
+    static constexpr int NS = LIGHT ? 2 : ((BN == 128) ? 3 : 4);
     static constexpr int RING = STAGE * NS * (X3 ? 2 : 1);
     static constexpr int SMEM = RING + 1024 /* alignment slack */ + 256 /* barriers */ + 12 * BN * 4 /* epilogue vectors + column statistics */;
-    static constexpr int EPI_SETS = 2;           // epilogue warp sets (4 warps each, one per TMEM lane quarter); the sets
-                                                 // interleave over the 32-column chunks of the tile
-    static constexpr int SPLIT_WARPS = X3 ? 6 : 0;                       // operand splitters (3xTF32 only)
+    static constexpr int EPI_SETS = LIGHT ? 1 : 2;  // epilogue warp sets (4 warps each, one per TMEM lane quarter); the sets
+                                                    // interleave over the 32-column chunks of the tile
+    static constexpr int SPLIT_WARPS = X3 ? (LIGHT ? 4 : 6) : 0;         // operand splitters (3xTF32 only)
     static constexpr int THREADS = 32 * (2 + 4 * EPI_SETS + SPLIT_WARPS);  // TMA warp, MMA warp, epilogue sets, splitters
+    static constexpr int MIN_CTAS = LIGHT ? 2 : 1;
+    static_assert(!LIGHT || (X3 && BN <= 64), "LIGHT is the short-K 3xTF32 configuration");
 };
 
-template <int BN, bool CONV, bool X3, bool HALF = false>
-__global__ void __launch_bounds__(Cfg<BN, X3>::THREADS)
+template <int BN, bool CONV, bool X3, bool HALF = false, bool LIGHT = false>
+__global__ void __launch_bounds__(Cfg<BN, X3, LIGHT>::THREADS, Cfg<BN, X3, LIGHT>::MIN_CTAS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const Params p) {
-    using C = Cfg<BN, X3>;
+    using C = Cfg<BN, X3, LIGHT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* lo_base = smem + C::STAGE * C::NS;  // X3 only
@@ -585,16 +592,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-template <int BN, bool CONV, bool X3, bool HALF = false>
+template <int BN, bool CONV, bool X3, bool HALF = false, bool LIGHT = false>
 static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p_in, dim3 grid,
                       cudaStream_t st) {
     Params p = p_in;
     p.tma_store = (c != nullptr && !CONV) ? 1 : 0;
     if (!c) c = a;  // placeholder, never dereferenced by the kernel
-    using C = Cfg<BN, X3>;
+    using C = Cfg<BN, X3, LIGHT>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, X3, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, X3, HALF, LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::SMEM);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(smem=%d): %s", C::SMEM, cudaGetErrorString(e));
@@ -602,14 +609,20 @@ static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensor
         }
         attr_done = true;
     }
-    gemm_tc_kernel<BN, CONV, X3, HALF><<<grid, C::THREADS, C::SMEM, st>>>(*a, *b, *c, p);
+    gemm_tc_kernel<BN, CONV, X3, HALF, LIGHT><<<grid, C::THREADS, C::SMEM, st>>>(*a, *b, *c, p);
     return check_launch(CONV ? "cofi_conv2d_nhwc(tcgen05)" : "cofi_gemm(tcgen05)");
 }
+
+constexpr int X3_LIGHT_MAX_KB = 8;  // K <= 256
 
 template <bool CONV>
 static int dispatch(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p, int bn, bool x3,
                     dim3 grid, cudaStream_t st) {
     if (x3) {
+        if (!CONV && bn <= 64 && p.num_kb <= X3_LIGHT_MAX_KB) {  // short contraction: two CTAs per SM (see Cfg)
+            if (bn == 32) return launch_one<32, CONV, true, false, true>(a, b, c, p, grid, st);
+            return launch_one<64, CONV, true, false, true>(a, b, c, p, grid, st);
+        }
         if (bn == 32) return launch_one<32, CONV, true>(a, b, c, p, grid, st);
         if (bn == 64) return launch_one<64, CONV, true>(a, b, c, p, grid, st);
         return launch_one<128, CONV, true>(a, b, c, p, grid, st);
@@ -668,7 +681,10 @@ static const CUtensorMap* c_tmap(const float* C, int64_t ldc, int64_t M, int N) 
 int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
                    int K, const Epilogue& ep, int engine, cudaStream_t st, float* stat_out) {
     using namespace tc;
-    const int bn = pick_bn(N, ceil_div(M, TM), ep.ln_gamma != nullptr);
+    int bn = pick_bn(N, ceil_div(M, TM), ep.ln_gamma != nullptr);
+    // 3xTF32, short K: 64-column tiles keep the hi + lo ring under 96 KB = two CTAs per SM (a fused LayerNorm needs the
+    // whole row in one tile and keeps 128)
+    if (engine == COFI_GEMM_TF32X3 && bn == 128 && ep.ln_gamma == nullptr && (K + TK - 1) / TK <= X3_LIGHT_MAX_KB) bn = 64;
     uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * 4};
     uint32_t bA[2] = {TK, TM};
     uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldw * 4};
