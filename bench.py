@@ -45,10 +45,11 @@ def parse():
     ap.add_argument("--train-batch", type=int, default=4, help="training frames per GPU per step (configs[4])")
     ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
     ap.add_argument("--num-pc", type=int, default=20480)
-    ap.add_argument("--engine", default=os.environ.get("COFI_ENGINE", "tf32"), choices=["fp32", "tf32", "tf32x3", "mixed"])
+    ap.add_argument("--engine", default=os.environ.get("COFI_ENGINE", "parity"), choices=["fp32", "tf32", "tf32x3", "parity"],
+                    help="engine of the headline numbers; 'parity' (default) meets the north star's 1e-3 / exact-correspondence bar")
     ap.add_argument("--mode", default="test", choices=["test", "val"], help="forward mode of the timed step")
-    ap.add_argument("--parity-engine", default="tf32x3", choices=["fp32", "tf32x3", "none"],
-                    help="second leg on the engine that meets the 1e-3 / exact-correspondence parity bar")
+    ap.add_argument("--other-engine", default="tf32", choices=["fp32", "tf32", "tf32x3", "parity", "none"],
+                    help="second leg: the same step on another engine (default: the tf32 throughput engine)")
     ap.add_argument("--no-train-leg", action="store_true", help="skip the data-parallel training leg (configs[4])")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip val-mode / host-table extra keys")
     ap.add_argument("--no-graph", action="store_true")
@@ -382,15 +383,17 @@ def run_cofi(args):
     # ---- parity, measured: this engine and the parity-grade engine against the real reference's golden outputs --------
     parity = {"engine": args.engine, **golden_parity(model, dev),
               "what": "forward(test) of this engine on the 20480-point golden frame vs outputs frozen from the real reference"}
-    parity_engine = None
-    if args.parity_engine != "none" and args.parity_engine != args.engine:
-        ops.set_engine(args.parity_engine)
+    other_engine = None
+    if args.other_engine != "none" and args.other_engine != args.engine:
+        ops.set_engine(args.other_engine)
         pv, pms, plp, _ = resident_fps("host", mode)
         pe2e = pipelined_fps("device", mode)
-        parity_engine = {"engine": args.parity_engine, "value": pv, "ms_per_step": pms, "unit": UNIT, "launches_per_step": plp,
-                         "e2e": pe2e["value"], "e2e_ms_per_step": pe2e["ms_per_step"], **golden_parity(model, dev),
-                         "what": "the same step on the engine that meets the north star's parity bar (<= 1e-3 relative, "
-                                 "correspondences bit-exact)"}
+        other_engine = {"engine": args.other_engine, "policy": ops.get_policy(), "value": pv, "ms_per_step": pms, "unit": UNIT,
+                        "launches_per_step": plp, "e2e": pe2e["value"], "e2e_ms_per_step": pe2e["ms_per_step"],
+                        "parity": golden_parity(model, dev),
+                        "what": "the same step on the tf32 throughput engine (tcgen05 kind::tf32 everywhere, fp16 KPConv / "
+                                "max-pool operands): faster, but its measured error exceeds the 1e-3 bar, so it is NOT the "
+                                "headline" if args.other_engine == "tf32" else "the same step on another engine"}
         ops.set_engine(args.engine)
 
     # ---- roofline of the dominant kernel family: eager pass bracketed by CUDA events per launch --------
@@ -474,7 +477,9 @@ def run_cofi(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "mixed": "tf32+tf32x3"}[args.engine], "data": "synthetic",
+        "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3",
+                  "parity": "tf32x3 (3xTF32 on tcgen05, fp32-grade; attention tf32, KPConv operands fp16)"}[args.engine],
+        "data": "synthetic",
         "config": {"workload": "configs[1]: single-GPU inference, batch=8 synthetic KITTI frames (3x160x512 img, "
                                f"20480x3 cloud, 5-level KNN-128 tables), {mode}-mode forward incl. the matching stage "
                                "(evaluation/eval_all.py:96)",
@@ -494,8 +499,8 @@ def run_cofi(args):
                             "full_scan_rows": sim_stats[1],
                             "what": "tcgen05 similarity pass -> exact fp32 re-rank: candidates evaluated per super-point, rows "
                                     "whose candidate list overflowed (accumulated over every run of the headline engine)"}
-    if parity_engine is not None:
-        line["parity_engine"] = parity_engine
+    if other_engine is not None:
+        line["throughput_engine" if args.other_engine == "tf32" else "other_engine"] = other_engine
     if train is not None:
         line["train"] = train
     line.update(extra)

@@ -399,3 +399,87 @@ class _ExtractPatch(torch.autograd.Function):
 
 def extract_patch(fmap, b, centers, err):
     return _ExtractPatch.apply(fmap.contiguous(), b, centers.contiguous(), err)
+
+
+class _ExtractPatchBatched(torch.autograd.Function):
+    """All frames in one launch each way: fmap [B,H,W,C], centers [B,2,n] -> [B,n,C,4,4]; one zero-initialised map gradient
+    for the whole batch (the per-frame form returns a full-size map gradient per frame for autograd to sum)."""
+
+    @staticmethod
+    def forward(ctx, fmap, centers, err):
+        ctx.save_for_backward(centers)
+        ctx.shape = tuple(fmap.shape)
+        return ops.extract_patch_batched(fmap, centers, err)
+
+    @staticmethod
+    def backward(ctx, dpatch):
+        (centers,) = ctx.saved_tensors
+        return ops.extract_patch_batched_bwd(dpatch, ctx.shape, centers), None, None
+
+
+def extract_patch_batched(fmap, centers, err):
+    return _ExtractPatchBatched.apply(fmap.contiguous(), centers.contiguous(), err)
+
+
+# ------------------------------------------------------------------------------------------ fused training losses
+class _DescLoss(torch.autograd.Function):
+    """sum over frames of desc_loss (reference model/loss.py:69-93) from token-layout descriptor maps + row indices."""
+
+    @staticmethod
+    def forward(ctx, img_tok, pc_tok, pix, kpt, mask, frames, pos_margin, neg_margin, log_scale):
+        loss, _, d_img, d_pc = ops.desc_loss_fwd(img_tok, pix, pc_tok, kpt, mask, frames, pos_margin, neg_margin, log_scale)
+        ctx.save_for_backward(d_img, d_pc, pix, kpt)
+        ctx.meta = (frames, img_tok.shape[0] // frames, pc_tok.shape[0] // frames)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        d_img, d_pc, pix, kpt = ctx.saved_tensors
+        frames, img_rows, pc_rows = ctx.meta
+        g = dloss.contiguous()   # [frames]: the upstream gradient of every frame's loss
+        return (ops.scatter_scaled_rows(d_img, pix, img_rows, frames, g), ops.scatter_scaled_rows(d_pc, kpt, pc_rows, frames, g),
+                None, None, None, None, None, None, None)
+
+
+def desc_loss_tokens(img_tok, pc_tok, pix, kpt, mask, frames, pos_margin, neg_margin, log_scale=10.0):
+    return _DescLoss.apply(img_tok, pc_tok, pix, kpt, mask, frames, pos_margin, neg_margin, log_scale)
+
+
+class _OverlapLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score_tok, idx, n_in, frames):
+        loss, d = ops.overlap_loss_fwd(score_tok, idx, n_in, frames)
+        ctx.save_for_backward(d, idx)
+        ctx.meta = (frames, score_tok.numel() // frames, tuple(score_tok.shape))
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        d, idx = ctx.saved_tensors
+        frames, rows, shape = ctx.meta
+        g = dloss.contiguous()
+        return ops.scatter_scaled_rows(d.reshape(-1, 1), idx, rows, frames, g).view(shape), None, None, None
+
+
+def overlap_loss_tokens(score_tok, idx, n_in, frames):
+    return _OverlapLoss.apply(score_tok, idx, n_in, frames)
+
+
+class _FineCircleLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, patch, fpc, rel, frames, bad_flag):
+        loss, d_patch, d_fpc = ops.fine_circle_loss_fwd(patch, fpc, rel, frames, bad_flag)
+        ctx.save_for_backward(d_patch, d_fpc)
+        ctx.frames = frames
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        d_patch, d_fpc = ctx.saved_tensors
+        g = dloss.contiguous()
+        return (ops.scatter_scaled_rows(d_patch, None, 0, ctx.frames, g), ops.scatter_scaled_rows(d_fpc, None, 0, ctx.frames, g),
+                None, None, None)
+
+
+def fine_circle_loss_rows(patch, fpc, rel, frames, bad_flag=None):
+    return _FineCircleLoss.apply(patch, fpc, rel, frames, bad_flag)

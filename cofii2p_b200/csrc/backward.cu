@@ -730,9 +730,17 @@ dilate2_nhwc_kernel(const float* __restrict__ x, int B, int H, int W, int C, flo
 // dmap[b, top+dy, left+dx, c] += dpatch[i, c, dy, dx]
 __global__ void __launch_bounds__(256)
 extract_patch_bwd_kernel(const float* __restrict__ dpatch, int H, int W, int C, int b, const float* __restrict__ centers,
-                         int64_t n, float* __restrict__ dmap) {
-    const int64_t total = n * C * 16;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+                         int64_t n, float* __restrict__ dmap, int frames = 1) {
+    const int64_t per = n * C * 16, total = per * frames;
+    const float* centers0 = centers;
+    const float* dpatch0 = dpatch;
+    const int b0 = b;
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(t0 / per);      // batched form: frame f reads centres [f,2,n], dpatch [f,n,C,16], image b0 + f
+        const int64_t t = t0 - (int64_t)f * per;
+        centers = centers0 + (int64_t)f * 2 * n;
+        dpatch = dpatch0 + (int64_t)f * per;
+        b = b0 + f;
         const int c = (int)(t % C);
         const int64_t r = t / C;
         const int pix = (int)(r % 16);
@@ -1222,6 +1230,15 @@ extern "C" int cofi_extract_patch_bwd(const float* dpatch, int H, int W, int C, 
     if (n == 0) return COFI_OK;
     extract_patch_bwd_kernel<<<ew_blocks_b(n * C * 16, 256), 256, 0, ST>>>(dpatch, H, W, C, b, centers, n, dmap);
     return check_launch("cofi_extract_patch_bwd");
+}
+
+extern "C" int cofi_extract_patch_batched_bwd(const float* dpatch, int H, int W, int C, int frames, const float* centers,
+                                              int64_t n, float* dmap, void* stream) {
+    COFI_REQUIRE(dpatch && centers && dmap && H >= 4 && W >= 4 && C > 0 && frames > 0 && n >= 0,
+                 "cofi_extract_patch_batched_bwd: bad argument");
+    if (n == 0) return COFI_OK;
+    extract_patch_bwd_kernel<<<ew_blocks_b(n * C * 16 * frames, 256), 256, 0, ST>>>(dpatch, H, W, C, 0, centers, n, dmap, frames);
+    return check_launch("cofi_extract_patch_batched_bwd");
 }
 
 static int tn_splits(int64_t R) {

@@ -173,7 +173,9 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tc_fence_after();
             const int base = (t0 + j) * S16_N;
             const bool last = base + S16_N > p.Npx;
-#pragma unroll
+            // CAND: the candidate scan makes the chunk body large; unrolled four times it no longer fits the instruction
+            // cache (ncu: stall_no_inst on every reconvergence point), so the chunk loop stays rolled in that variant
+#pragma unroll(CAND ? 1 : 4)
             for (int c = 0; c < 4; ++c) {
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + lane_off + (uint32_t)((h * 2 + b) * S16_N + c * 32), raw);

@@ -83,6 +83,7 @@ SIGNATURES = {
     "cofi_maxpool2d_3x3s2_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "cofi_dilate2_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "cofi_extract_patch_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp]),
+    "cofi_extract_patch_batched_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _l, _vp, _vp]),
     "cofi_gemm_tn_workspace": (_l, [_l, _i, _i]),
     "cofi_gemm_tn": (_i, [_vp, _l, _vp, _l, _vp, _l, _i, _i, _i, _i, _vp, _vp]),
     "cofi_conv2d_wgrad_workspace": (_l, [_i, _i, _i, _i, _i, _i, _i]),
@@ -91,6 +92,10 @@ SIGNATURES = {
     "cofi_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "cofi_attention_bwd_tc_workspace": (_l, [_l, _l, _i, _i, _i]),
     "cofi_attention_bwd_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cofi_desc_loss": (_i, [_vp, _vp, _l, _vp, _vp, _l, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "cofi_overlap_loss": (_i, [_vp, _vp, _l, _i, _i, _i, _vp, _vp, _vp]),
+    "cofi_fine_circle_loss": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "cofi_scatter_scaled_rows": (_i, [_vp, _vp, _l, _l, _i, _i, _vp, _f, _vp, _vp]),
     "cofi_adam_step": (_i, [_vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _i, _f, _vp]),
 }
 

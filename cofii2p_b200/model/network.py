@@ -334,6 +334,27 @@ class CoFiI2P(nn.Module):
         return (img_feature_norm, pc_feature_norm, img_score, pc_score, patch, fine_pc, fine_center_xy,
                 coarse_pc_points)
 
+    def forward_train_tokens(self, batch: Dict):
+        """Train-mode forward of B stacked frames in TOKEN layout for the fused losses (cofii2p_b200/train.py): the core
+        dict (img_norm [B*HW,128], pc_norm [B*N4,128], pc_score [B*N4,1], ...) plus the supervised 4x4 patches
+        [B*n, C, 16] and level-1 point features [B*n, C] gathered for all frames at once (reference network.py:132-143).
+        The out-of-map flag of extract_patch is left in `self.last_err`."""
+        B = batch["frames"]
+        imagenet.PER_FRAME_BN[0] = True
+        try:
+            core = self.core(batch["pc_data_dict"], batch["img"], B)
+        finally:
+            imagenet.PER_FRAME_BN[0] = False
+        dev = core["pc_norm"].device
+        centers = torch.stack([k.to(torch.float32) for k in batch["fine_center_kpt_coors"]]).to(dev)      # [B, 2, n]
+        inline = torch.stack([k.to(torch.int64) for k in batch["fine_pc_inline_index"]]).to(dev).view(-1)  # [B*n]
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        n = centers.shape[2]
+        fine_pc = ad.gather(core["pc_decode_3"], inline, 1, B)
+        patch = ad.extract_patch_batched(core["up2"], centers, err)
+        self.last_err = err.sum()
+        return core, patch.view(B * n, patch.shape[2], 16), fine_pc
+
     def forward_batch(self, batch: Dict, mode: str = "val", check: bool = True):
         """B frames stacked along rows (see cofii2p_b200.frames.stack_frames). Returns a list of 8-tuples.
         check=False defers the one host synchronisation (the out-of-map flag of extract_patch) to the caller: the flag

@@ -15,14 +15,50 @@ from typing import Dict, List, Optional
 
 import torch
 
+from . import autograd as ad
 from . import ops
-from .model.loss import desc_loss, fine_circle_loss, overlap_loss
+from .model.loss import desc_loss_algebra as desc_loss, fine_circle_loss_algebra as fine_circle_loss, \
+    overlap_loss_algebra as overlap_loss
 
-__all__ = ["training_losses", "TrainStep"]
+__all__ = ["training_losses", "fused_training_losses", "TrainStep"]
+
+
+def fused_training_losses(model, batch: Dict, opt):
+    """The same three losses for ALL B stacked frames of a step through the fused forward + backward kernels (csrc/loss.cu),
+    straight from the token-layout network outputs: no per-frame NCHW transposes, fancy-index gathers or autograd graphs of
+    ~60 element-wise ops per frame.  Returns (mean loss over frames, [desc, overlap, fine] means, bad-supervision flag).
+    What stays tensor algebra is the 64 x 64 projection mask of train.py:237-251 (a dozen tiny batched launches per step)."""
+    B = batch["frames"]
+    core, patch, fine_pc = model.forward_train_tokens(batch)
+    dev = core["pc_norm"].device
+    n4 = core["pc_norm"].shape[0] // B
+    W = model.pe_W
+    kpt = torch.stack(batch["pc_kpt_idx"]).to(dev)                                       # [B, n]
+    outl = torch.stack(batch["pc_outline_idx"]).to(dev)
+    pix = torch.stack(batch["coarse_img_kpt_idx"]).to(dev)
+    P, K4 = torch.stack(batch["P"]).to(dev), torch.stack(batch["K_4"]).to(dev)           # [B,4,4], [B,3,3]
+    pts4 = batch["pc_data_dict"]["points"][-1].view(B, n4, 3)
+    xyz = torch.gather(pts4, 1, kpt.unsqueeze(-1).expand(-1, -1, 3)).transpose(1, 2)     # [B,3,n]            train.py:237
+    img_xy = torch.stack(((pix % W).to(torch.float32), torch.div(pix, W, rounding_mode="floor").to(torch.float32)), 1)  # :245
+    proj = K4 @ (P[:, 0:3, 0:3] @ xyz + P[:, 0:3, 3:])                                   # :247
+    proj_xy = proj[:, 0:2] / proj[:, 2:]
+    mask = (torch.sqrt(torch.sum(torch.square(img_xy.unsqueeze(-1) - proj_xy.unsqueeze(-2)), dim=1))
+            <= opt.dist_thres).float()                                                   # [B, n_img, n_pc]   :251
+    l_desc = ad.desc_loss_tokens(core["img_norm"], core["pc_norm"], pix, kpt, mask, B, opt.pos_margin, opt.neg_margin)   # :254
+    l_coarse = ad.overlap_loss_tokens(core["pc_score"], torch.cat((kpt, outl), 1), kpt.shape[1], B)                      # :256-260
+    fine_xy = torch.stack(batch["fine_xy"]).to(dev)
+    centers = torch.stack([k.to(torch.float32) for k in batch["fine_center_kpt_coors"]]).to(dev)
+    rel = torch.floor(fine_xy) - centers + 2                                             # [B,2,n]            :267
+    bad = ((rel < 0) | (rel > 3)).any().to(torch.int32)
+    rel_index = (rel[:, 1] * 4 + rel[:, 0]).long().clamp_(0, 15).reshape(-1)
+    l_fine = ad.fine_circle_loss_rows(patch, fine_pc, rel_index, B)                      # :283
+    parts = torch.stack((l_desc.detach().mean(), l_coarse.detach().mean(), l_fine.detach().mean()))
+    return (l_desc.sum() + l_coarse.sum() + l_fine.sum()) / B, parts, bad
 
 
 def training_losses(out, sup: Dict, opt, points4: torch.Tensor):
-    """Losses of one frame (reference train.py:233-283). `out` is the model's 8-tuple in train mode, `sup` the frame's
+    """Losses of one frame (reference train.py:233-283) as plain tensor algebra on the model's public outputs -- the
+    definition the fused path (fused_training_losses) is tested against. `out` is the model's 8-tuple in train mode, `sup` the frame's
     supervision (pc_kpt_idx, pc_outline_idx, coarse_img_kpt_idx, K_4, P, fine_xy, fine_center_kpt_coors), `points4`
     the frame's coarsest-level points [n4,3]."""
     img_features, pc_features, _, coarse_pc_score, fine_patch, fine_pc = out[:6]
@@ -57,8 +93,12 @@ def training_losses(out, sup: Dict, opt, points4: torch.Tensor):
 class TrainStep:
     """One optimisation step over B stacked frames per rank (Adam, reference train.py:156 defaults)."""
 
-    def __init__(self, model, opt, lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8, group=None):
+    def __init__(self, model, opt, lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8, group=None,
+                 fused_losses: bool = True):
+        """fused_losses: the three losses of all frames through csrc/loss.cu (fused_training_losses); False = the reference's
+        formulas as tensor algebra, frame by frame (training_losses) -- the path the fused kernels are tested against."""
         self.model, self.opt = model, opt
+        self.fused_losses = fused_losses
         self.lr = float(opt.lr if lr is None else lr)
         self.betas, self.eps = betas, eps
         self.group = group
@@ -124,6 +164,11 @@ class TrainStep:
     def loss(self, batch: Dict, check: bool = True):
         """Mean over the rank's frames of the reference's per-frame loss."""
         model, B = self.model, batch["frames"]
+        if self.fused_losses:
+            total, parts, self.last_bad_supervision = fused_training_losses(model, batch, self.opt)
+            if check and int(model.last_err.item()) != 0:
+                raise AssertionError("extract_patch: a 4x4 window falls outside the feature map")
+            return total, parts
         outs = model.forward_batch(batch, "train", check=check)
         n4 = batch["pc_data_dict"]["points"][-1].shape[0] // B
         total, parts = None, []

@@ -380,6 +380,9 @@ int cofi_maxpool2d_3x3s2_bwd(const float* x, const float* dy, int B, int H, int 
 int cofi_dilate2_nhwc(const float* x, int B, int H, int W, int C, float* y, void* stream);
 int cofi_extract_patch_bwd(const float* dpatch, int H, int W, int C, int b, const float* centers, int64_t n, float* dmap,
                            void* stream);
+/* Batched form (cofi_extract_patch_batched): dpatch [frames, n, C, 4, 4], centers [frames, 2, n], dmap [frames,H,W,C] (+=). */
+int cofi_extract_patch_batched_bwd(const float* dpatch, int H, int W, int C, int frames, const float* centers, int64_t n,
+                                   float* dmap, void* stream);
 /* C[Mo,No] (+)= A[R,Mo]^T B[R,No]: weight gradient of a Linear without transposes (A = dY, B = X).
  * engine COFI_GEMM_TF32: tcgen05 with both operands MN-major (the reduction index is the outer one in HBM), split over R;
  * any other engine: SIMT fp32.  Partial tiles are folded by a deterministic reduction. */
@@ -403,6 +406,35 @@ int64_t cofi_attention_bwd_tc_workspace(int64_t L, int64_t S, int frames, int he
 int cofi_attention_bwd_tc(const float* q, const float* k, const float* v, const float* out, const float* dout,
                           const float* lse, int64_t L, int64_t S, int frames, int heads, int D, float scale, float* dq,
                           float* dk, float* dv, float* dsum_work, void* tr_work, void* stream);
+/* ---------------------------------------------------------------------------------------------------
+ * Training losses (model/loss.py:9-93; called from train.py:254-283), fused forward + analytic backward,
+ * batched over `frames` stacked frames: loss[frames] per frame, gradients w.r.t. the gathered rows in compact
+ * buffers (NULL = forward only); cofi_scatter_scaled_rows applies the upstream gradient and scatters them.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* desc_loss (model/loss.py:69-93).  img_tok [frames*img_rows, C] / pc_tok [frames*pc_rows, C]: token-layout descriptor maps;
+ * pix / kpt [frames, n]: frame-local rows of the n supervised pixels / points; mask [frames, n, n] (1 = positive pair,
+ * rows = pixels).  dists [frames, n, n] optional output (the matrix the reference returns); d_img / d_pc [frames, n, C]. */
+int cofi_desc_loss(const float* img_tok, const int64_t* pix, int64_t img_rows, const float* pc_tok, const int64_t* kpt,
+                   int64_t pc_rows, const float* mask, int n, int C, int frames, float pos_margin, float neg_margin,
+                   float log_scale, float* loss, float* dists, float* d_img, float* d_pc, void* stream);
+
+/* overlap_loss (model/loss.py:53-60): BCE of score[idx] against 1 for the first n_in indices, 0 for the next n_out.
+ * score [frames*rows] token layout; idx [frames, n_in + n_out] frame-local; d_score [frames, n_in + n_out]. */
+int cofi_overlap_loss(const float* score, const int64_t* idx, int64_t rows, int n_in, int n_out, int frames, float* loss,
+                      float* d_score, void* stream);
+
+/* fine_circle_loss (model/loss.py:9-51).  patch [frames*n, C, 16], fpc [frames*n, C], rel [frames*n] in 0..15 (outside:
+ * *bad_flag = 1, the reference's label[...] indexing raises).  d_patch / d_fpc: same shapes as patch / fpc. */
+int cofi_fine_circle_loss(const float* patch, const float* fpc, const int64_t* rel, int n, int C, int frames, float m,
+                          float gamma, float* loss, float* d_patch, float* d_fpc, int32_t* bad_flag, void* stream);
+
+/* dst[f*rows_dst + idx[f*R + r], :] += scale * src[f*R + r, :]  (dst zero-initialised by the caller; idx NULL:
+ * dst[f*R + r, :] = scale * src[f*R + r, :]).  scale = scale_host * scale_dev[f] (scale_dev: device float[frames] or NULL):
+ * the upstream gradient of every frame's loss is a device value inside a captured training step. */
+int cofi_scatter_scaled_rows(const float* src, const int64_t* idx, int64_t R, int64_t rows_dst, int frames, int C,
+                             const float* scale_dev, float scale_host, float* dst, void* stream);
+
 /* fused Adam step (torch.optim.Adam semantics, reference train.py:154); grad_scale folds the 1/world_size of the
  * data-parallel gradient average. */
 int cofi_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

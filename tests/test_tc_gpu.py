@@ -69,17 +69,19 @@ def test_conv_tc(engine, cin, cout, k, pad, h, w):
         ops.set_engine("fp32")
 
 
-@pytest.mark.parametrize("engine,tol", [("tf32x3", 1e-3), ("tf32", 5e-2)])
-def test_forward_golden_tc(cuda_model, engine, tol):
-    """Full forward on the tensor-core engines vs the real-reference golden (20480 points).
-    3xTF32 must meet the north-star tolerance (1e-3) with identical correspondences; plain TF32 is the throughput
-    mode and is reported with its own (looser) error bound."""
+@pytest.mark.parametrize("seed,num_pc", [(0, 20480), (0, 4096), (1, 4096)])
+@pytest.mark.parametrize("engine,tol", [("parity", 1e-3), ("tf32x3", 1e-3), ("tf32", 5e-2)])
+def test_forward_golden_tc(cuda_model, engine, tol, seed, num_pc):
+    """Full forward on the tensor-core engines vs the real-reference goldens (20480 and 4096 points).
+    The `parity` preset -- the engine bench.py reports: 3xTF32 + tf32 attention + fp16 KPConv operands -- and plain 3xTF32
+    must meet the north-star tolerance (1e-3) with bit-identical correspondences on every golden; plain TF32 is the
+    throughput mode and is reported with its own (looser) error bound."""
     import os
     import numpy as np
     from cofii2p_b200 import ops
     from cofii2p_b200.frames import frame_to
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frame_s0_n20480.npz"))
-    f = frame_to(get_frame(0, 20480), "cuda")
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"frame_s{seed}_n{num_pc}.npz"))
+    f = frame_to(get_frame(seed, num_pc), "cuda")
     ops.set_engine(engine)
     try:
         with torch.no_grad():
@@ -96,13 +98,15 @@ def test_forward_golden_tc(cuda_model, engine, tol):
     try:  # keep the measured end-to-end errors as an artefact when run under gpurun
         out_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out")
         os.makedirs(out_dir, exist_ok=True)
-        open(os.path.join(out_dir, f"forward_err_{engine}.json"), "w").write(__import__("json").dumps(errs))
+        open(os.path.join(out_dir, f"forward_err_{engine}_s{seed}_n{num_pc}.json"), "w").write(__import__("json").dumps(errs))
     except OSError:
         pass
     assert max(errs.values()) < tol, errs
-    if engine == "tf32x3":
+    if engine != "tf32":
         assert torch.equal(test[6].cpu(), torch.from_numpy(z["test/fine_center_xy"]))
         assert torch.equal(test[7].cpu(), torch.from_numpy(z["test/coarse_pc_points"]))
+        for i, nm in ((4, "fine_img_feature_patch"), (5, "fine_pc_inline_feature")):
+            assert rel_err(test[i], torch.from_numpy(z["test/" + nm])) < tol, nm
 
 
 @pytest.mark.parametrize("L,S,frames", [(1280, 1280, 1), (1280, 1280, 2), (300, 516, 2), (130, 64, 1), (128, 1024, 1)])

@@ -490,3 +490,66 @@ def test_eval_after_training_uses_the_updated_weights(seeded_sd, captured):
     for got in (got_graph, got_eager, got_engine):
         for a, b in zip(got[:6], want[:6]):
             assert rel_err(a, b) < 1e-5, rel_err(a, b)
+
+
+# ---------------------------------------------------------------------------------------------- fused losses (row f3)
+def test_fused_loss_kernels_match_the_reference_formulas():
+    """csrc/loss.cu (forward + analytic backward in one launch) against torch autograd through the reference's formulas
+    (model/loss.py:9-93 restated in cofii2p_b200/model/loss.py::*_algebra, bit-exact vs the reference on CPU)."""
+    from cofii2p_b200.model import loss as L
+    g = torch.Generator().manual_seed(5)
+    n, C = 64, 128
+    img = F.normalize(torch.randn((C, n), generator=g), dim=0)
+    pc = F.normalize(img + 0.7 * torch.randn((C, n), generator=g), dim=0)
+    mask = (torch.rand((n, n), generator=g) < 0.04).float()
+    mask[torch.arange(n), torch.arange(n)] = 1.0
+    a_ref, b_ref = _leaf(img), _leaf(pc)
+    l_ref, d_ref = L.desc_loss_algebra("cpu", a_ref, b_ref, mask, pos_margin=0.2, neg_margin=1.8)
+    l_ref.backward()
+    a, b = _cuda_leaf(img), _cuda_leaf(pc)
+    l, d = L.desc_loss("cuda", a, b, mask.cuda(), pos_margin=0.2, neg_margin=1.8)
+    (l * 1.0).backward()
+    assert abs(float(l) - float(l_ref)) < 1e-5 * abs(float(l_ref)) and rel_err(d, d_ref) < 1e-6
+    assert _nrm_err(a.grad, a_ref.grad) < 1e-5 and _nrm_err(b.grad, b_ref.grad) < 1e-5
+    # overlap (BCE), including a saturated score
+    si, so = torch.rand((64,), generator=g) * 0.98 + 0.01, torch.rand((64,), generator=g) * 0.98 + 0.01
+    si[0], so[0] = 1.0 - 1e-7, 1e-7
+    si_r, so_r = _leaf(si), _leaf(so)
+    lo_ref = L.overlap_loss_algebra("cpu", si_r, so_r)
+    lo_ref.backward()
+    si_c, so_c = _cuda_leaf(si), _cuda_leaf(so)
+    lo = L.overlap_loss("cuda", si_c, so_c)
+    lo.backward()
+    assert abs(float(lo) - float(lo_ref)) < 1e-5 * abs(float(lo_ref))
+    assert _nrm_err(si_c.grad, si_r.grad) < 1e-5 and _nrm_err(so_c.grad, so_r.grad) < 1e-5
+    # fine circle loss
+    patch = F.normalize(torch.randn((64, 64, 4, 4), generator=g), dim=1)
+    fpc = F.normalize(torch.randn((64, 64), generator=g) + 2.0 * patch[:, :, 1, 2], dim=1)
+    rel = torch.randint(0, 16, (64,), generator=g)
+    p_r, f_r = _leaf(patch), _leaf(fpc)
+    lf_ref = L.fine_circle_loss_algebra("cpu", p_r, f_r, rel, 64)
+    lf_ref.backward()
+    p_c, f_c = _cuda_leaf(patch), _cuda_leaf(fpc)
+    lf = L.fine_circle_loss("cuda", p_c, f_c, rel.cuda(), 64)
+    lf.backward()
+    assert abs(float(lf) - float(lf_ref)) < 1e-5 * abs(float(lf_ref))
+    assert _nrm_err(p_c.grad, p_r.grad) < 1e-5 and _nrm_err(f_c.grad, f_r.grad) < 1e-5
+
+
+def test_fused_training_losses_equal_the_per_frame_path(seeded_sd):
+    """TrainStep(fused_losses=True) -- token-layout outputs, batched fused loss kernels -- gives the loss and the gradient of
+    TrainStep(fused_losses=False) -- the reference's per-frame formulas on the public outputs through torch autograd."""
+    from cofii2p_b200 import ops
+    from cofii2p_b200.frames import frame_to, stack_frames
+    from cofii2p_b200.train import TrainStep
+    ops.set_engine("fp32")
+    batch = stack_frames([frame_to(get_frame(s, 4096), "cuda") for s in (0, 1)])
+    res = {}
+    for fused in (False, True):
+        model, opt = _fresh_model(seeded_sd)
+        ts = TrainStep(model, opt, fused_losses=fused)
+        l, parts = ts.backward(batch)
+        res[fused] = (float(l), parts.clone(), ts.flat_g.clone())
+    assert abs(res[True][0] - res[False][0]) < 1e-5 * abs(res[False][0])
+    assert rel_err(res[True][1], res[False][1]) < 1e-5
+    assert float((res[True][2] - res[False][2]).norm() / res[False][2].norm()) < 1e-4

@@ -108,7 +108,7 @@ def train_leg(args, dev, world, rank, local, steps=None):
     from cofii2p_b200.shard import frames_for_rank
     from cofii2p_b200.train import TrainStep
     steps = steps or args.steps
-    engine = "tf32" if args.engine == "mixed" else args.engine
+    engine = "tf32" if args.engine == "parity" else args.engine   # training runs the tf32 contraction engine
     ops.set_engine(engine)
     model, _ = bench.build_model(dev)
     model.train()
