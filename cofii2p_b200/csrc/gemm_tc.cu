@@ -188,7 +188,7 @@ struct Cfg {
                                                     // interleave over the 32-column chunks of the tile
     static constexpr int SPLIT_WARPS = X3 ? (LIGHT ? 4 : 6) : 0;         // operand splitters (3xTF32 only)
     static constexpr int THREADS = 32 * (2 + 4 * EPI_SETS + SPLIT_WARPS);  // TMA warp, MMA warp, epilogue sets, splitters
-    static constexpr int MIN_CTAS = LIGHT ? 2 : 1;
+    static constexpr int MIN_CTAS = (X3 && !LIGHT) ? 1 : 2;  // register budget: two resident CTAs except for the deep 3xTF32 config
     static_assert(!LIGHT || (X3 && BN <= 64), "LIGHT is the short-K 3xTF32 configuration");
 };
 

@@ -348,6 +348,72 @@ def test_philox_known_answers_and_sampler_oracle():
         assert ia[l].min() >= 0 and ia[l].max() < 2048 and np.array_equal(a[l], pts[ia[l]])
 
 
+# ---------------------------------------------------------------------------------------------- dataset front-end (row f4)
+def _kitti_opt(root, num_pc):
+    class Opt:
+        pass
+    o = Opt()
+    o.data_path, o.num_pc, o.num_kpt, o.img_H, o.img_W = root, num_pc, 64, 160, 512
+    o.P_tx_amplitude, o.P_ty_amplitude, o.P_tz_amplitude = 10, 0, 10
+    o.P_Rx_amplitude, o.P_Ry_amplitude, o.P_Rz_amplitude = 0, 2 * np.pi, 0
+    return o
+
+
+def test_kitti_front_end_host_logic(tmp_path):
+    """cofii2p_b200/data/kitti.py on a synthetic sequence written in the reference's on-disk layout (data/kitti.py:111-141):
+    same keys / shapes / dtypes as the reference's __getitem__ (:374-393), per-index determinism (:261-264), supervision
+    invariants (key points project inside the 1/8 map, fine pixel inside its 4x4 patch window, nearest level-1 node).
+    The tables come from the CPU oracle here (the product builds them on the GPU)."""
+    from cofii2p_b200.data.kitti import KittiCalib, KittiFrames, voxel_down_sample, write_synthetic_sequence
+    from oracle import knn as ok
+    root = str(tmp_path)
+    write_synthetic_sequence(root, 9, 2, n_points=20000)
+
+    def builder(pc, inten, sn, lengths, stages):
+        levels = ok.half_sample_pyramid(pc, stages)
+        t = ok.pyramid_tables(levels, 128, ok.DIRECT)
+        return {"points": [torch.from_numpy(l) for l in levels], "lengths": [lengths >> i for i in range(stages)],
+                **{k: [torch.from_numpy(x) for x in v] for k, v in t.items()}}
+
+    def p2n(nodes, pts):
+        return ((pts[:, None, :] - nodes[None, :, :]) ** 2).sum(-1).argmin(1)
+
+    ds = KittiFrames(_kitti_opt(root, 2048), "val", table_builder=builder, point2node=p2n)
+    assert len(ds) == 4                                             # 2 frames x (P2, P3)
+    a, b = ds[1], ds[1]
+    assert set(a) == {"img", "pc_data_dict", "fine_pc_inline_index", "K", "K_4", "P", "index", "coarse_img_mask", "pc_kpt_idx",
+                      "pc_outline_idx", "fine_xy_coors", "coarse_img_kpt_idx", "fine_img_kpt_index", "fine_center_kpt_coors",
+                      "coarse_img_outline_index"}
+    for k in a:
+        if torch.is_tensor(a[k]):
+            assert torch.equal(a[k], b[k]), k                       # item i is a pure function of i
+    assert a["img"].shape == (3, 160, 512) and a["img"].dtype == torch.float32 and float(a["img"].max()) <= 1.0
+    d = a["pc_data_dict"]
+    assert [tuple(p.shape) for p in d["points"]] == [(2048 >> l, 3) for l in range(5)] and d["feats"].shape == (2048, 4)
+    assert all(t.dtype == torch.int64 and t.shape[1] == 128 for t in d["neighbors"] + d["subsampling"] + d["upsampling"])
+    n = a["pc_kpt_idx"].numel()
+    assert 4 <= n <= 64 and a["fine_center_kpt_coors"].dtype == torch.int32 and a["fine_center_kpt_coors"].shape == (2, n)
+    rel = a["fine_xy_coors"].float() - a["fine_center_kpt_coors"].float() + 2
+    assert float(rel.min()) >= 0 and float(rel.max()) <= 3          # what train.py:267-283 indexes the 4x4 label with
+    x8, y8 = a["coarse_img_kpt_idx"] % 64, a["coarse_img_kpt_idx"] // 64
+    assert int(x8.min()) >= 1 and int(x8.max()) <= 61 and int(y8.min()) >= 1 and int(y8.max()) <= 17
+    assert bool((a["coarse_img_mask"].reshape(-1)[a["coarse_img_kpt_idx"]] == 1).all())
+    # the key points really project where the supervision says: K_4 * (P * X) with P = inverse random transform
+    X = d["points"][-1][a["pc_kpt_idx"]].T.double()
+    cam = a["P"][0:3, 0:3].double() @ X + a["P"][0:3, 3:].double()
+    uv = a["K_4"].double() @ cam
+    uv = torch.floor(uv[0:2] / uv[2:] + 0.5)
+    assert torch.equal(uv[0].long(), x8) and torch.equal(uv[1].long(), y8)
+    # nearest level-1 node of every key point
+    nodes, kp = d["points"][1], d["points"][-1][a["pc_kpt_idx"]]
+    assert torch.equal(a["fine_pc_inline_index"], p2n(nodes, kp))
+    # voxel grid: one point per occupied voxel, means preserved
+    pc = np.random.default_rng(0).uniform(0, 1, (3, 5000)).astype(np.float32)
+    v, i, s = voxel_down_sample(pc, np.ones((1, 5000), np.float32), np.tile([[0.0], [0.0], [1.0]], (1, 5000)).astype(np.float32), 0.25)
+    assert v.shape[1] <= 5 ** 3 and np.allclose(i, 1.0) and np.allclose(s[2], 1.0)
+    assert KittiCalib(root).get_matrix(9, "Tr").shape == (4, 4)
+
+
 # ---------------------------------------------------------------------------------------------- pose step (row f2)
 def test_pose_step_on_reference_golden_outputs():
     """oracle/evaluate.py (eval_all.py:99-105) + the shared cv2 / get_P_diff wrappers on the reference's frozen test-mode

@@ -260,3 +260,34 @@ def test_pose_matches_reference_pipeline(cuda_model, seed, n):
         rte_r, rre_r = ev.pose_error(T_ref, T_gt)
         assert abs(mine["rte"] - rte_r) <= 1e-3 and abs(mine["rre"] - rre_r) <= 1e-3
         assert np.allclose(mine["T"], T_ref, atol=1e-9)
+
+
+def test_kitti_front_end_feeds_the_model(cuda_model, tmp_path):
+    """Row f4 end to end: a frame read from the reference's on-disk layout (synthetic sequence), pyramid + KNN-128 tables
+    built on the GPU by the library, through forward(test) and forward(val) -- the call pattern of evaluation/eval_all.py:60-96."""
+    import numpy as np
+    from cofii2p_b200 import ops
+    from cofii2p_b200.data.kitti import KittiFrames, write_synthetic_sequence
+    from cofii2p_b200.frames import frame_to
+    from oracle import knn as ok
+    sys_path_opt = __import__("test_cpu")._kitti_opt
+    root = str(tmp_path)
+    write_synthetic_sequence(root, 9, 1, n_points=60000)
+    ds = KittiFrames(sys_path_opt(root, 20480), "val")
+    item = ds[0]
+    d = item["pc_data_dict"]
+    assert d["points"][0].is_cuda and d["neighbors"][0].shape == (20480, 128)
+    # the device-built tables equal the CPU oracle's on the same pyramid (spot check of one level)
+    ref = ok.knn_table(d["points"][3].cpu().numpy(), d["points"][3].cpu().numpy(), 128, ok.DIRECT)
+    dist = lambda t: ((d["points"][3].cpu()[:, None, :] - d["points"][3].cpu()[t]) ** 2).sum(-1)
+    assert torch.equal(dist(torch.from_numpy(ref)), dist(d["neighbors"][3].cpu()))       # equal up to ties
+    ops.set_engine("fp32")
+    f = frame_to(item, "cuda")
+    n = item["pc_kpt_idx"].numel()
+    with torch.no_grad():
+        out = cuda_model(f["pc_data_dict"], f["img"].unsqueeze(0), f["fine_center_kpt_coors"], f["fine_xy_coors"].float(),
+                         f["fine_pc_inline_index"], "val")
+        out_t = cuda_model(f["pc_data_dict"], f["img"].unsqueeze(0), f["fine_center_kpt_coors"], None, None, "test")
+    assert out[0].shape == (1, 128, 20, 64) and out[4].shape == (n, 64, 4, 4) and out[5].shape == (n, 64)
+    assert out_t[6].shape[0] == 2 and out_t[7].shape[1] == 3 and out_t[6].shape[1] == out_t[7].shape[0] >= 4
+    assert all(bool(torch.isfinite(t).all()) for t in out[:6])
