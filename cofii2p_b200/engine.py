@@ -28,7 +28,8 @@ def _pin(t: torch.Tensor) -> torch.Tensor:
 
 
 class InferenceEngine:
-    def __init__(self, model, batch: Dict, mode: str = "val", use_graph: bool = True, stream=None, tables: str = "host"):
+    def __init__(self, model, batch: Dict, mode: str = "val", use_graph: bool = True, stream=None, tables: str = "host",
+                 knn_stream=None):
         """`batch`: output of frames.stack_frames (CPU or CUDA tensors) that fixes all shapes.
         `stream`: compute stream shared by several engines (PipelinedEngine).
         `tables`: "host" = the KNN index tables arrive with the batch, as the reference's data loader supplies them;
@@ -49,10 +50,19 @@ class InferenceEngine:
             "lengths": d["lengths"],
         }
         self.knn_k = int(d["neighbors"][0].shape[1])
+        self.graph_knn: Optional[torch.cuda.CUDAGraph] = None
+        self._knn_stream = None
         if tables == "device":
+            # the tables are static buffers written by the builder's own graph on its own stream: in the pipelined engine the
+            # (ALU-bound) table build of batch i+1 overlaps the (latency / HBM-bound) forward of batch i
             n = [p.shape[0] // self.B for p in self.inp["points"]]
             import ctypes
             self.knn_ws = ops._ws(_libmod.load().cofi_knn_pyramid_workspace((ctypes.c_int64 * len(n))(*n), len(n), self.B), dev)
+            self._knn_stream = knn_stream if knn_stream is not None else torch.cuda.Stream(device=dev)
+            self._tables_ready = torch.cuda.Event()
+            self._tables_free = torch.cuda.Event()
+            for key in ("neighbors", "subsampling", "upsampling"):   # never the batch's own tables: the builder fills them
+                self.inp[key] = [torch.zeros_like(t) for t in self.inp[key]]
         self.img = batch["img"].to(dev).contiguous()
         self.kpt = torch.stack([k.to(torch.float32) for k in batch["fine_center_kpt_coors"]]).to(dev).contiguous()
         self.inline = torch.stack([k.to(torch.int64) for k in batch["fine_pc_inline_index"]]).to(dev).contiguous()
@@ -74,10 +84,12 @@ class InferenceEngine:
         dev = self.device
         self.graph = None
         self.epoch = ops.weights_epoch()
+        self.graph_knn = None
         with torch.no_grad():
             with torch.cuda.stream(self._stream):
                 for _ in range(2):
                     n0 = _libmod.launch_count()
+                    self._knn_eager()
                     self._step_eager()
                     self.launches_per_step = _libmod.launch_count() - n0
                 self._stream.synchronize()
@@ -86,13 +98,35 @@ class InferenceEngine:
                     with torch.cuda.graph(g, stream=self._stream):
                         self._step_eager()
                     self.graph = g
+            if self.use_graph and self.tables == "device":
+                with torch.cuda.stream(self._knn_stream):
+                    gk = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gk, stream=self._knn_stream):
+                        self._knn_eager()
+                    self.graph_knn = gk
         torch.cuda.synchronize(dev)
+
+    def _knn_eager(self):
+        """tables="device": the 13 KNN tables of the batch from its point pyramid, into the static table buffers."""
+        if self.tables != "device":
+            return
+        ops.knn_pyramid(self.inp["points"], frames=self.B, k=self.knn_k, k_up=1, workspace=self.knn_ws,
+                        out={k: self.inp[k] for k in ("neighbors", "subsampling", "upsampling")})
+
+    def run_knn(self, stream=None):
+        """Enqueue the table build (tables="device") on `stream` (default: the engine's table stream)."""
+        if self.tables != "device":
+            return
+        st = stream if stream is not None else self._knn_stream
+        with torch.no_grad(), torch.cuda.stream(st):
+            if self.graph_knn is not None:
+                self.graph_knn.replay()
+            else:
+                self._knn_eager()
 
     # one forward over the static buffers; fills self.out
     def _step_eager(self):
         m, B = self.model, self.B
-        if self.tables == "device":
-            self.inp.update(ops.knn_pyramid(self.inp["points"], frames=B, k=self.knn_k, k_up=1, workspace=self.knn_ws))
         core = m.core(self.inp, self.img, B)
         n1 = core["pc_decode_3"].shape[0] // B
         hw = m.pe_H * m.pe_W
@@ -123,8 +157,22 @@ class InferenceEngine:
     # ------------------------------------------------------------------------------------------ stepping
     def run(self):
         """One forward over whatever currently sits in the static input buffers (asynchronous)."""
+        self._refresh()
+        if self.tables == "device":  # stand-alone use: tables first (their own stream), then the forward
+            self._tables_free.record(self._stream)
+            self._knn_stream.wait_event(self._tables_free)      # the previous forward has finished reading the tables
+            self.run_knn()
+            self._tables_ready.record(self._knn_stream)
+            self._stream.wait_event(self._tables_ready)
+        self.run_forward()
+
+    def _refresh(self):
         if self.epoch != ops.weights_epoch():
             self._capture()   # parameters changed since the capture: stale packs / folds / pointers must not be replayed
+
+    def run_forward(self):
+        """The forward over the static buffers (tables included), on the engine's compute stream."""
+        self._refresh()
         with torch.no_grad():
             if self.graph is not None:
                 with torch.cuda.stream(self._stream):
@@ -222,15 +270,19 @@ class InferenceEngine:
 class PipelinedEngine:
     """Double-buffered end-to-end pipeline: while the graph of buffer set i computes, the H2D copy of batch i+1
     lands in buffer set (i+1)%2 on a copy stream and the D2H of batch i-1 drains on a third stream (PCIe is full
-    duplex).  Steady-state step time = max(H2D, compute, D2H) instead of their sum."""
+    duplex); with tables="device" the KNN-table graph of batch i+1 runs on a fourth stream beside the forward of batch i.
+    Steady-state step time = max(H2D, compute, D2H) instead of their sum."""
 
     def __init__(self, model, batch: Dict, depth: int = 2, tables: str = "host", mode: str = "val"):
         dev = next(model.parameters()).device
         self.compute = torch.cuda.Stream(device=dev)
         self.h2d = torch.cuda.Stream(device=dev)
         self.d2h = torch.cuda.Stream(device=dev)
-        self.engines = [InferenceEngine(model, batch, mode=mode, use_graph=True, stream=self.compute, tables=tables)
-                        for _ in range(depth)]
+        self.knn = torch.cuda.Stream(device=dev)   # tables="device": table build of batch i+1 runs beside the forward of batch i
+        self.tables = tables
+        self.engines = [InferenceEngine(model, batch, mode=mode, use_graph=True, stream=self.compute, tables=tables,
+                                        knn_stream=self.knn) for _ in range(depth)]
+        self.tabled = [torch.cuda.Event() for _ in range(depth)]
         self.uploaded = [torch.cuda.Event() for _ in range(depth)]
         self.computed = [torch.cuda.Event() for _ in range(depth)]
         self.drained = [torch.cuda.Event() for _ in range(depth)]
@@ -246,9 +298,15 @@ class PipelinedEngine:
         self.h2d.wait_event(self.computed[k])      # buffer set k is free once its previous compute finished
         nin = eng.upload(host, self.h2d)
         self.uploaded[k].record(self.h2d)
-        self.compute.wait_event(self.uploaded[k])
+        if self.tables == "device":
+            self.knn.wait_event(self.uploaded[k])  # (the upload itself waited for the previous forward over buffer set k)
+            eng.run_knn(self.knn)
+            self.tabled[k].record(self.knn)
+            self.compute.wait_event(self.tabled[k])
+        else:
+            self.compute.wait_event(self.uploaded[k])
         self.compute.wait_event(self.drained[k])   # outputs of set k were copied out
-        eng.run()
+        eng.run_forward()
         self.computed[k].record(self.compute)
         self.d2h.wait_event(self.computed[k])
         nout = eng.download(self.d2h)
@@ -258,6 +316,7 @@ class PipelinedEngine:
 
     def synchronize(self):
         self.h2d.synchronize()
+        self.knn.synchronize()
         self.compute.synchronize()
         self.d2h.synchronize()
 

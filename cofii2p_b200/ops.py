@@ -374,8 +374,8 @@ def gemm_f16_colstats(a_half, w_half, bias=None, rowdiv=None):
 
 
 def colstats_ok(rows: int, frames: int, n: int) -> bool:
-    """GEMM-epilogue statistics apply on the tf32 engine when every frame is a whole number of 128-row tiles."""
-    return _eng() == ENGINE_TF32 and rows % frames == 0 and (rows // frames) % 128 == 0 and n >= 16 and n % 4 == 0
+    """GEMM-epilogue statistics apply on the tensor-core engines when every frame is a whole number of 128-row tiles."""
+    return _eng() in (ENGINE_TF32, ENGINE_TF32X3) and rows % frames == 0 and (rows // frames) % 128 == 0 and n >= 16 and n % 4 == 0
 
 
 def norm_rows_pre(x, stats, frames: int, groups: int, gamma, beta, eps: float = 1e-5, residual=None, act: int = ACT_NONE,
@@ -689,7 +689,7 @@ KNN_DIRECT, KNN_EXPANDED, KNN_NOCULL = 0, 1, 0x100
 
 
 def knn_pyramid(points, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT, want=("neighbors", "subsampling", "upsampling"),
-                workspace: Optional[torch.Tensor] = None, k_up: Optional[int] = None):
+                workspace: Optional[torch.Tensor] = None, k_up: Optional[int] = None, out: Optional[dict] = None):
     """All KNN-k tables of a point pyramid in two launches (reference model/kpconv/preprocess_data.py:75-99,172-190).
     points: list of [frames*n_l, 3] fp32 CUDA tensors -> dict(neighbors, subsampling, upsampling) of int64 tables with
     frame-local indices, rows ascending in (distance, index).  k_up: columns of the upsampling tables (default k; the
@@ -704,13 +704,14 @@ def knn_pyramid(points, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT, w
     n_arr = (ctypes.c_int64 * L)(*n)
     if workspace is None:
         workspace = _ws(_lib.cofi_knn_pyramid_workspace(n_arr, L, frames), dev)
-    out = {"neighbors": [], "subsampling": [], "upsampling": []}
-    if "neighbors" in want:
-        out["neighbors"] = [torch.empty((frames * n[l], k), dtype=torch.int64, device=dev) for l in range(L)]
-    if "subsampling" in want:
-        out["subsampling"] = [torch.empty((frames * n[l + 1], k), dtype=torch.int64, device=dev) for l in range(L - 1)]
-    if "upsampling" in want:
-        out["upsampling"] = [torch.empty((frames * n[l], k_up), dtype=torch.int64, device=dev) for l in range(L - 1)]
+    if out is None:  # `out`: tables of a previous call with the same arguments, overwritten in place (static engine buffers)
+        out = {"neighbors": [], "subsampling": [], "upsampling": []}
+        if "neighbors" in want:
+            out["neighbors"] = [torch.empty((frames * n[l], k), dtype=torch.int64, device=dev) for l in range(L)]
+        if "subsampling" in want:
+            out["subsampling"] = [torch.empty((frames * n[l + 1], k), dtype=torch.int64, device=dev) for l in range(L - 1)]
+        if "upsampling" in want:
+            out["upsampling"] = [torch.empty((frames * n[l], k_up), dtype=torch.int64, device=dev) for l in range(L - 1)]
 
     def arr(ts):
         return (ctypes.c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts]) if ts else None

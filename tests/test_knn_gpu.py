@@ -208,6 +208,31 @@ def test_engine_builds_tables_on_device():
             assert torch.equal(x, y)
     hb = b.host_buffers(batch)
     assert hb["neighbors"] == [] and b.upload(hb) < 2 * (4096 * 2 * 3 * 4 + 4096 * 16 + 3 * 160 * 512 * 4) + 4096
+    # another batch: the table graph (its own stream) must rebuild the tables from the uploaded pyramid every step, also
+    # inside the pipelined engine where it runs beside the previous batch's forward
+    from cofii2p_b200.engine import PipelinedEngine
+    batch2 = stack_frames([frames[1], frames[0]])
+    tabs2 = ops.knn_pyramid([p.cuda() for p in batch2["pc_data_dict"]["points"]], frames=2, k=128)
+    for name in ("neighbors", "subsampling", "upsampling"):
+        batch2["pc_data_dict"][name] = tabs2[name]
+    a.upload(a.host_buffers(batch2))
+    b.upload(b.host_buffers(batch2))
+    for e in (a, b):
+        e.run()
+    ref2 = a.results()
+    for ra, rb in zip(ref2, b.results()):
+        for x, y in zip(ra[:6], rb[:6]):
+            assert torch.equal(x, y)
+    ref1 = InferenceEngine(m, batch, tables="host")
+    ref1.run()
+    ref1 = ref1.results()
+    pipe = PipelinedEngine(m, batch, depth=2, tables="device")
+    hosts = [pipe.engines[0].host_buffers(bt) for bt in (batch, batch2)]
+    for i in range(5):
+        pipe.step(hosts[i % 2])
+        for ra, rb in zip(ref1 if i % 2 == 0 else ref2, pipe.last_results()):
+            for x, y in zip(ra[:6], rb[:6]):
+                assert torch.equal(x, y)
 
 
 def test_precompute_point_cloud_cuda_surface():
