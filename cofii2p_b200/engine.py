@@ -267,6 +267,19 @@ class InferenceEngine:
         return res
 
 
+    def correspondences_padded(self):
+        """test mode, no host synchronisation: (imagePoints [B,N4,2] fp32, objectPoints [B,N4,3] fp32, match counts [B,2]
+        int32) on the device -- the inputs of the batched pose step (cofii2p_b200.evaluate.solve_pose_batch); rows beyond a
+        frame's count are padding."""
+        assert self.mode == "test"
+        with torch.no_grad(), torch.cuda.stream(self._stream):
+            idx = self.out["fine_idx"].to(torch.float32)
+            c = self.out["fine_center_xy"]
+            x = c[:, 0] - 2 + torch.floor(idx / 4)       # eval_all.py:103-105 (its x += idx // 4 convention)
+            y = c[:, 1] - 2 + idx % 4
+            return torch.stack([x, y], 2).contiguous(), self.out["coarse_pc_points"], self.out["count"]
+
+
 class PipelinedEngine:
     """Double-buffered end-to-end pipeline: while the graph of buffer set i computes, the H2D copy of batch i+1
     lands in buffer set (i+1)%2 on a copy stream and the D2H of batch i-1 drains on a third stream (PCIe is full

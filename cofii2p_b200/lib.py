@@ -92,6 +92,7 @@ SIGNATURES = {
     "cofi_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "cofi_attention_bwd_tc_workspace": (_l, [_l, _l, _i, _i, _i]),
     "cofi_attention_bwd_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cofi_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _f, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cofi_desc_loss": (_i, [_vp, _vp, _l, _vp, _vp, _l, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "cofi_overlap_loss": (_i, [_vp, _vp, _l, _i, _i, _i, _vp, _vp, _vp]),
     "cofi_fine_circle_loss": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),

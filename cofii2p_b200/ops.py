@@ -1011,6 +1011,31 @@ def attention_bwd(q, k, v, out, dout, lse, frames: int, heads: int, scale: float
     return dq, dk, dv
 
 
+# ------------------------------------------------------------------------------------------ pose step
+def pnp_ransac(image_points, object_points, cam, count: Optional[torch.Tensor] = None, iterations: int = 10000,
+               threshold: float = 8.0, seed: int = 0):
+    """Batched P3P-RANSAC (cofi_pnp_ransac).  image_points [B,n,2], object_points [B,n,3], cam [B,4] (fx, fy, cx, cy) fp32;
+    count: optional int32 [B] or [B,s] (column 0 = real rows per frame).  -> (inlier count [B] i32, winning hypothesis [B]
+    i32, pose [B,12] f64 (R row-major, t), inlier mask [B,n] u8)."""
+    image_points, object_points = _f32(image_points, "image_points").contiguous(), _f32(object_points, "object_points").contiguous()
+    cam = _f32(cam, "cam").contiguous()
+    B, n = image_points.shape[0], image_points.shape[1]
+    dev = image_points.device
+    stride = 0
+    if count is not None:
+        if count.dtype != torch.int32 or not count.is_cuda or not count.is_contiguous():
+            raise RuntimeError("pnp_ransac: count must be a contiguous CUDA int32 tensor")
+        stride = 1 if count.dim() == 1 else count.shape[1]
+    o_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    o_hyp = torch.empty((B,), dtype=torch.int32, device=dev)
+    o_pose = torch.empty((B, 12), dtype=torch.float64, device=dev)
+    o_inl = torch.empty((B, n), dtype=torch.uint8, device=dev)
+    ws = torch.empty((B,), dtype=torch.int64, device=dev)
+    _call("cofi_pnp_ransac", _p(image_points), _p(object_points), _p(count), stride, n, B, _p(cam), int(iterations), float(threshold),
+          int(seed) & 0xFFFFFFFFFFFFFFFF, _p(o_cnt), _p(o_hyp), _p(o_pose), _p(o_inl), _p(ws), _st())
+    return o_cnt, o_hyp, o_pose, o_inl
+
+
 # ------------------------------------------------------------------------------------------ fused training losses
 def desc_loss_fwd(img_tok, pix, pc_tok, kpt, mask, frames: int, pos_margin: float, neg_margin: float, log_scale: float = 10.0,
                   want_grad: bool = True, want_dists: bool = False):

@@ -407,6 +407,22 @@ int cofi_attention_bwd_tc(const float* q, const float* k, const float* v, const 
                           const float* lse, int64_t L, int64_t S, int frames, int heads, int D, float scale, float* dq,
                           float* dk, float* dv, float* dsum_work, void* tr_work, void* stream);
 /* ---------------------------------------------------------------------------------------------------
+ * Pose step after the hot path (evaluation/eval_all.py:107: cv2.solvePnPRansac, 10000 iterations per frame on the CPU)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Batched P3P-RANSAC: all `iterations` hypotheses of all frames in one launch (one thread per hypothesis), winner = most
+ * inliers (squared reprojection error <= reproj_threshold^2, positive depth), lowest hypothesis index on ties.
+ * image_points [frames, n_max, 2] pixels, object_points [frames, n_max, 3]; count (optional device int32, frame f reads
+ * count[f * count_stride]) = real rows per frame, NULL = n_max; cam [frames, 4] = fx, fy, cx, cy.  Sampling is
+ * counter-based (Philox4x32-10 keyed by seed) so that the host oracle restates it.  Outputs: out_count [frames] inliers of
+ * the winner (0 = no valid hypothesis), out_hypothesis [frames] its index (-1), out_pose [frames, 12] float64 = R row-major
+ * then t (X_cam = R X + t), out_inlier [frames, n_max] uint8.  work: 8 * frames bytes, 8-byte aligned.  The caller refines
+ * on the inliers (cv2.solvePnP ITERATIVE -- what solvePnPRansac itself ends with). */
+int cofi_pnp_ransac(const float* image_points, const float* object_points, const int32_t* count, int count_stride, int n_max,
+                    int frames, const float* cam, int iterations, float reproj_threshold, uint64_t seed, int32_t* out_count,
+                    int32_t* out_hypothesis, double* out_pose, uint8_t* out_inlier, void* work, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Training losses (model/loss.py:9-93; called from train.py:254-283), fused forward + analytic backward,
  * batched over `frames` stacked frames: loss[frames] per frame, gradients w.r.t. the gathered rows in compact
  * buffers (NULL = forward only); cofi_scatter_scaled_rows applies the upstream gradient and scatters them.

@@ -348,6 +348,48 @@ def test_philox_known_answers_and_sampler_oracle():
         assert ia[l].min() >= 0 and ia[l].max() < 2048 and np.array_equal(a[l], pts[ia[l]])
 
 
+def _pnp_case(seed, n=300, outlier_frac=0.6, noise=0.5):
+    import cv2
+    rng = np.random.default_rng(seed)
+    K = np.array([[360.0, 0, 256], [0, 360.0, 80], [0, 0, 1]])
+    R, _ = cv2.Rodrigues(rng.uniform(-0.5, 0.5, 3))
+    t = rng.uniform(-2, 2, 3) + np.array([0, 0, 5.0])
+    obj = rng.uniform(-10, 10, (n, 3)) + np.array([0, 0, 20.0])
+    cam = obj @ R.T + t
+    img = cam[:, :2] / cam[:, 2:] * 360.0 + np.array([256.0, 80.0]) + rng.normal(0, noise, (n, 2))
+    out = rng.random(n) < outlier_frac
+    img[out] = rng.uniform(0, 500, (int(out.sum()), 2))
+    return K, img.astype(np.float32), obj.astype(np.float32), R, t, ~out
+
+
+def test_pnp_ransac_oracle_vs_opencv():
+    """oracle/pnp.py (the restatement the device RANSAC is tested against) vs the reference's own solver call
+    (cv2.solvePnPRansac, evaluation/eval_all.py:107) on synthetic correspondences with a known pose, 60 % outliers:
+    P3P recovers exact poses, the winning inlier set is OpenCV's, and OpenCV's final refinement on it gives OpenCV's pose."""
+    import cv2
+    from oracle import pnp
+    rng = np.random.default_rng(0)
+    hit = 0
+    for _ in range(100):
+        R, _ = cv2.Rodrigues(rng.uniform(-0.5, 0.5, 3))
+        t = rng.uniform(-2, 2, 3) + np.array([0, 0, 5.0])
+        P = rng.uniform(-3, 3, (3, 3)) + np.array([0, 0, 8.0])
+        Xc = P @ R.T + t
+        sols = pnp.p3p(Xc / np.linalg.norm(Xc, axis=1, keepdims=True), P)
+        hit += min([np.abs(Rs - R).max() + np.abs(ts - t).max() for Rs, ts in sols] + [9.0]) < 1e-6
+    assert hit >= 97
+    for seed in (1, 2):
+        K, img, obj, R, t, truth = _pnp_case(seed)
+        best = pnp.ransac(K, img, obj, iterations=400, threshold=8.0, seed=seed)
+        cv2.setRNGSeed(0)
+        ok, rvec, tvec, inl = cv2.solvePnPRansac(obj, img, K, None, iterationsCount=10000)
+        cv_inl = np.zeros(img.shape[0], bool)
+        cv_inl[inl[:, 0]] = True
+        assert ok and np.array_equal(cv_inl, best["inliers"]) and best["count"] >= int(truth.sum())
+        ok2, rv2, tv2 = cv2.solvePnP(obj[best["inliers"]], img[best["inliers"]], K, None, flags=cv2.SOLVEPNP_ITERATIVE)
+        assert ok2 and np.abs(rv2 - rvec).max() < 1e-6 and np.abs(tv2 - tvec).max() < 1e-6
+
+
 # ---------------------------------------------------------------------------------------------- dataset front-end (row f4)
 def _kitti_opt(root, num_pc):
     class Opt:

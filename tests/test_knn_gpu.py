@@ -214,7 +214,10 @@ def test_engine_builds_tables_on_device():
     batch2 = stack_frames([frames[1], frames[0]])
     tabs2 = ops.knn_pyramid([p.cuda() for p in batch2["pc_data_dict"]["points"]], frames=2, k=128)
     for name in ("neighbors", "subsampling", "upsampling"):
-        batch2["pc_data_dict"][name] = tabs2[name]
+        batch2["pc_data_dict"][name] = [t.cpu() for t in tabs2[name]]     # host_buffers() pins host tensors
+    batch = stack_frames(frames)                                          # (the first batch again, host tensors throughout)
+    for name in ("neighbors", "subsampling", "upsampling"):
+        batch["pc_data_dict"][name] = [t.cpu() for t in tabs[name]]
     a.upload(a.host_buffers(batch2))
     b.upload(b.host_buffers(batch2))
     for e in (a, b):
