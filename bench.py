@@ -354,6 +354,31 @@ def run_cofi(args):
     clk = clocks.stop()
     value = frames_total / (ms_total / 1000.0)
     sim_stats = eng.sim_stats.tolist() if mode == "test" else None
+    # ---- the step right after the path (evaluation/eval_all.py:107): batched device RANSAC vs cv2.solvePnPRansac ----------
+    pose_step = None
+    if mode == "test":
+        try:
+            import numpy as np
+            from cofii2p_b200 import evaluate as ev
+            ipts, opts_, cnt = eng.correspondences_padded()
+            Kh = frames[0]["K_half"].numpy()
+            cam = torch.tensor([[Kh[0, 0], Kh[1, 1], Kh[0, 2], Kh[1, 2]]] * B, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(eng.stream):
+                for _ in range(2):
+                    ops.pnp_ransac(ipts, opts_, cam, cnt, 10000, 8.0, 0)
+            ms_r = timed_on(eng.stream, lambda: ops.pnp_ransac(ipts, opts_, cam, cnt, 10000, 8.0, 0), 5) / 5
+            corr = eng.correspondences()
+            t0 = time.perf_counter()
+            for c in corr[:2]:
+                ev.solve_pose(Kh, c[0].cpu().numpy(), c[1].cpu().numpy())
+            ms_cv = (time.perf_counter() - t0) * 1e3 / 2
+            pose_step = {"device_ransac_ms_per_batch": ms_r, "frames_per_batch": B, "hypotheses_per_frame": 10000,
+                         "opencv_solvePnPRansac_ms_per_frame": ms_cv, "matches_per_frame": [int(x) for x in cnt[:, 0].tolist()],
+                         "what": "cofi_pnp_ransac (one launch for all frames, P3P, one thread per hypothesis) on the engine's padded "
+                                 "device correspondences vs the reference's cv2.solvePnPRansac(iterationsCount=10000) call on the "
+                                 "host, same correspondences (random-weight descriptors: no consensus, so OpenCV runs all iterations)"}
+        except Exception as e:
+            pose_step = {"unavailable": repr(e)[:200]}
     runs = max(args.warmup, 3) + args.steps + 2   # + the two eager warm-ups of the capture
     stream = eng.stream
 
@@ -499,6 +524,8 @@ def run_cofi(args):
                             "full_scan_rows": sim_stats[1],
                             "what": "tcgen05 similarity pass -> exact fp32 re-rank: candidates evaluated per super-point, rows "
                                     "whose candidate list overflowed (accumulated over every run of the headline engine)"}
+    if pose_step is not None:
+        line["pose_step"] = pose_step
     if other_engine is not None:
         line["throughput_engine" if args.other_engine == "tf32" else "other_engine"] = other_engine
     if train is not None:

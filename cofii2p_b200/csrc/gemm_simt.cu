@@ -185,7 +185,7 @@ bool gemm_tc_supported(int64_t lda, int64_t ldw, int64_t ldc, int64_t M, int N, 
 int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
                        int K, const Epilogue& ep, cudaStream_t st, float* stat_out = nullptr);
 bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
-int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW, int pad,
+int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW, int stride, int pad,
                    float* y, const Epilogue& ep, int engine, cudaStream_t st);
 
 }  // namespace cofi
@@ -223,7 +223,7 @@ extern "C" int cofi_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, co
     COFI_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0, "cofi_conv2d_nhwc: 16-byte alignment");
     Epilogue ep{nullptr, nullptr, scale, shift, residual, Cout, 0, act, nullptr, nullptr, 0.0f};
     if ((engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3) && conv_tc_supported(B, H, W, Cin, Cout, KH, KW, stride, pad))
-        return conv_tc_launch(x, B, H, W, Cin, w, Cout, KH, KW, pad, y, ep, engine, (cudaStream_t)stream);
+        return conv_tc_launch(x, B, H, W, Cin, w, Cout, KH, KW, stride, pad, y, ep, engine, (cudaStream_t)stream);
     return conv_simt_launch(x, B, H, W, Cin, w, Cout, KH, KW, stride, pad, y, ep, (cudaStream_t)stream);
 }
 

@@ -160,7 +160,7 @@ struct Params {
     int num_kb;
     Epilogue ep;
     // convolution geometry (CONV only)
-    int Ho, Wo, Cin, cpt /* 32-channel chunks per tap */, KW, pad, tiles_w, tiles_per_img;
+    int Ho, Wo, Cin, cpt /* 32-channel chunks per tap */, KW, pad, tiles_w, tiles_per_img, cstride /* conv stride (1 or 2) */;
     int tma_store;    // dense output with 16-byte aligned rows: tiles leave through TMA stores (tmC), else per-thread stores
     float* stat_out;  // optional [row tiles][N][2] per-tile column (sum, sum of squares) of the stored output
     int dbg;  // COFI_TC_DEBUG bits (perf triage only): 1 = skip global stores, 2 = skip TMA+MMA
@@ -256,7 +256,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (CONV) {
                     const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                    tma_load_4d(&tmA, &full[s], a_dst, cc * TK, cw0 + kw - p.pad, ch0 + kh - p.pad, cb);
+                    // strided conv: the tensor map carries elementStrides {1, s, s, 1}, coordinates are in input pixels
+                    tma_load_4d(&tmA, &full[s], a_dst, cc * TK, cw0 * p.cstride + kw - p.pad, ch0 * p.cstride + kh - p.pad, cb);
                     tma_load_2d(&tmB, &full[s], b_dst, tap * p.Cin + cc * TK, n0);
                 } else {
                     // k-block = 128 bytes of K: 32 fp32 or 64 fp16 elements
@@ -737,25 +738,28 @@ int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, f
 // ---------------------------------------------------------------------------------------------- conv entry
 bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
     (void)B;
-    const int Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
-    if (stride != 1) return false;                      // strided convs (3 of 28) stay on the SIMT engine
+    if (stride != 1 && stride != 2) return false;
+    const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
     if (Wo % tc::CONV_TW || Ho % tc::CONV_TH) return false;
     if (Cin % 4 || Cout < 16) return false;
     return tc::encode_fn() != nullptr;
 }
 
-int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW, int pad,
+int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW, int stride, int pad,
                    float* y, const Epilogue& ep, int engine, cudaStream_t st) {
     using namespace tc;
-    const int Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
+    const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
     const int bn = pick_bn(Cout, (int64_t)B * (Wo / CONV_TW) * (Ho / CONV_TH));
     const int Ktot = KH * KW * Cin;
     uint64_t dA[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t sA[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
-    uint32_t bA[4] = {TK, CONV_TW, CONV_TH, 1};
+    // stride 2 (the ResNet stem and layer2's first block, reference model/imagenet.py:199-212): the box spans 2x the
+    // pixels and elementStrides {1, 2, 2, 1} keep every second one, so the tile lands dense in shared memory
+    uint32_t bA[4] = {TK, (uint32_t)(CONV_TW * stride), (uint32_t)(CONV_TH * stride), 1};
+    uint32_t eA[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     uint64_t dB[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sB[1] = {(uint64_t)Ktot * 4};
     uint32_t bB[2] = {TK, (uint32_t)bn};
-    const CUtensorMap* ta = get_tmap_f32(x, 4, dA, sA, bA);
+    const CUtensorMap* ta = stride == 1 ? get_tmap_f32(x, 4, dA, sA, bA) : get_tmap_any(x, 4, dA, sA, bA, 0, eA, 0);
     const CUtensorMap* tb = get_tmap_f32(w, 2, dB, sB, bB);
     if (!ta || !tb) return COFI_ECUDA;
     Params p{};
@@ -771,6 +775,7 @@ int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w,
     p.Cin = Cin;
     p.KW = KW;
     p.pad = pad;
+    p.cstride = stride;
     p.tiles_w = Wo / CONV_TW;
     p.tiles_per_img = p.tiles_w * (Ho / CONV_TH);
     dim3 grid((unsigned)(B * p.tiles_per_img), (unsigned)ceil_div(Cout, bn));

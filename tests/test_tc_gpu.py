@@ -69,6 +69,28 @@ def test_conv_tc(engine, cin, cout, k, pad, h, w):
         ops.set_engine("fp32")
 
 
+@pytest.mark.parametrize("engine", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("cin,cout,k,pad,h,w", [(4, 64, 7, 3, 160, 512), (64, 128, 3, 1, 40, 128), (64, 128, 1, 0, 40, 128),
+                                                (32, 48, 3, 1, 8, 256)])
+def test_conv_tc_stride2(engine, cin, cout, k, pad, h, w):
+    """The three stride-2 convolutions of the image branch (reference model/imagenet.py:199-212: 7x7 stem on the 4-channel
+    padded input, layer2's 3x3 and its 1x1 down-sample) on tcgen05: TMA boxes with elementStrides {1,2,2,1}."""
+    from cofii2p_b200 import lib, ops
+    g = torch.Generator().manual_seed(cin + cout + k + h)
+    x = torch.randn((2, cin, h, w), generator=g)
+    wt = torch.randn((cout, cin, k, k), generator=g) / math.sqrt(cin * k * k)
+    ref = F.relu(F.conv2d(x.double(), wt.double(), None, 2, pad).float())
+    ops.set_engine(engine)
+    try:
+        xn = ops.nchw_to_nhwc(x.cuda())
+        wp = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().cuda()
+        y = ops.conv2d_nhwc(xn, wp, k, k, 2, pad, act=ops.ACT_RELU)
+        assert tuple(y.shape) == (2, ref.shape[2], ref.shape[3], cout)
+        assert rel_err(ops.nhwc_to_nchw(y), ref) < tol_for(engine, cin * k * k), rel_err(ops.nhwc_to_nchw(y), ref)
+    finally:
+        ops.set_engine("fp32")
+
+
 @pytest.mark.parametrize("seed,num_pc", [(0, 20480), (0, 4096), (1, 4096)])
 @pytest.mark.parametrize("engine,tol", [("parity", 1e-3), ("tf32x3", 1e-3), ("tf32", 5e-2)])
 def test_forward_golden_tc(cuda_model, engine, tol, seed, num_pc):
