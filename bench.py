@@ -466,7 +466,8 @@ def run_cofi(args):
             with open(tpath) as f:
                 tj = json.load(f)
             traffic = tj.get(name, tj.get(name.split(" [")[0]) if tname == "traffic.json" else None)
-            tsrc = "profiles/" + tname + ("" if name in tj else " (family average over all launches of the entry point)")
+            tsrc = "profiles/" + tname + (" (ncu, averaged over the same calls as `kernel`: tools/ncu_summary.py traffic_calls)"
+                                          if name in tj else " (family average over all launches of the entry point)")
             if traffic is not None:
                 break
     roof.update({"traffic": traffic, "traffic_source": tsrc, "kernel": name, "launches_profiled": d["calls"],

@@ -135,7 +135,7 @@ def profile_start() -> None:
     _prof = []
 
 
-def profile_stop(ridge: Optional[float] = None):
+def profile_stop(ridge: Optional[float] = None, raw: bool = False):
     """-> {op: dict(calls, ms, flops, bytes)} (synchronises).  With `ridge` (flop per byte at which the tensor roof meets the
     HBM roof) the contraction entry points are split per call into "<op>|tensor" (arithmetic intensity above the ridge) and
     "<op>|hbm": one entry point serves both the K <= 128 streaming contractions and the large-K ones, and a single
@@ -144,15 +144,17 @@ def profile_stop(ridge: Optional[float] = None):
     rec, _prof = _prof, None
     torch.cuda.synchronize()
     out = {}
-    for name, e0, e1, fl, by in rec:
+    calls = []
+    for name, e0, e1, nl, fl, by in rec:
         if ridge is not None and (name.startswith("cofi_gemm") or name.startswith("cofi_conv2d")) and by > 0:
             name = name + ("|tensor" if fl / by > ridge else "|hbm")
+        calls.append((name, nl))
         d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
         d["calls"] += 1
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += fl
         d["bytes"] += by
-    return out
+    return (out, calls) if raw else out   # calls: [(op name, kernels launched)] in launch order (tools/ncu_traffic.py)
 
 
 def _meta(flops: float = 0.0, nbytes: float = 0.0) -> None:
@@ -167,10 +169,11 @@ def _call(name: str, *args) -> None:
         rc = getattr(_lib, name)(*args)
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _libmod.launch_count()
         e0.record()
         rc = getattr(_lib, name)(*args)
         e1.record()
-        _prof.append((name, e0, e1) + _prof_meta)
+        _prof.append((name, e0, e1, _libmod.launch_count() - n0) + _prof_meta)
     _prof_meta = (0.0, 0.0)
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {_libmod.last_error()}")

@@ -116,5 +116,48 @@ def traffic(path, out):
         print(f"{k:32s} launches={agg[k][0]:4d} avg_dram_MB_per_launch={v/1e6:9.2f} total_GB={v*agg[k][0]/1e9:7.2f}")
 
 
+def traffic_calls(path, calls_json, out):
+    """DRAM bytes per launch averaged over EXACTLY the launches of each op family bench.py reports (incl. the hbm- / tensor-
+    bound split of the contraction entry points): the ncu kernel list of one eager step is cut into C-ABI calls with the
+    per-call kernel counts that tools/profile_step.py --emit-calls recorded for the same step."""
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        d = per.setdefault(row["ID"], {"name": re.sub(r"\(.*", "", row["Kernel Name"]), "bytes": 0.0, "us": 0.0})
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        if row["Metric Name"].startswith("dram__bytes"):
+            d["bytes"] += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        elif row["Metric Name"] == "gpu__time_duration.sum":
+            d["us"] += v / 1e3 if u == "ns" else (v if u == "us" else v * 1e3)
+    kernels = list(per.values())
+    calls = json.load(open(calls_json))
+    assert sum(n for _, n in calls) == len(kernels), (sum(n for _, n in calls), len(kernels))
+    agg = collections.OrderedDict()
+    i = 0
+    for name, n in calls:
+        base, _, bound = name.partition("|")
+        key = "cofi_gemm*" if base.startswith("cofi_gemm") else ("cofi_kpconv_aggregate*" if base.startswith("cofi_kpconv_aggregate") else base)
+        if bound:
+            key += " [" + bound + "-bound calls]"
+        a = agg.setdefault(key, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += sum(k["bytes"] for k in kernels[i:i + n])
+        a[2] += sum(k["us"] for k in kernels[i:i + n])
+        i += n
+    res = {k: v[1] / v[0] for k, v in agg.items()}
+    res["_meta"] = {"what": "ncu dram__bytes_read.sum + dram__bytes_write.sum per C-ABI call, averaged per op family of one eager "
+                            "8-frame step (cold-cache serialised launches)", "launches": {k: v[0] for k, v in agg.items()},
+                    "ncu_us_per_family": {k: round(v[2], 1) for k, v in agg.items()}}
+    json.dump(res, open(out, "w"), indent=1)
+    tot = sum(v[2] for v in agg.values())
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][2]):
+        print(f"{k:44s} calls={v[0]:4d} avg_dram_MB={v[1]/v[0]/1e6:9.2f} total_GB={v[1]/1e9:7.2f} ncu_us={v[2]:9.1f} share={v[2]/tot:.3f}")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic_calls":
+        traffic_calls(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
