@@ -71,7 +71,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_c
     uint64_t* acc_full = bars + 7;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int head = blockIdx.y, frame = blockIdx.z;
     const int64_t r0 = (int64_t)blockIdx.x * BR;
 
@@ -100,29 +100,37 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_c
     const uint32_t tmem_X = tmem_base, tmem_Y = tmem_base + BT, tmem_A0 = tmem_base + 2 * BT, tmem_A1 = tmem_A0 + BD;
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(r_full, 2 * R_BYTES);
-            tma_load_2d(&tmR1, r_full, sR1, head * BD, (int)(frame * p.NR + r0));
-            tma_load_2d(&tmR2, r_full, sR2, head * BD, (int)(frame * p.NR + r0));
+        {   // whole warp runs the loop, the elected lane issues (tc_common.cuh: elect_one)
+            const bool leader = elect_one();
+            if (leader) {
+                mbar_expect_tx(r_full, 2 * R_BYTES);
+                tma_load_2d(&tmR1, r_full, sR1, head * BD, (int)(frame * p.NR + r0));
+                tma_load_2d(&tmR2, r_full, sR2, head * BD, (int)(frame * p.NR + r0));
+            }
+            __syncwarp();
             for (int t = 0; t < p.num_tiles; ++t) {
                 const int s = t % B_STAGES;
                 const uint32_t ph = (uint32_t)(t / B_STAGES) & 1u;
                 mbar_wait(&t_empty[s], ph ^ 1u);
-                mbar_expect_tx(&t_full[s], STAGE);
                 uint8_t* d = sT + s * STAGE;
                 const int row0 = (int)(frame * p.NT + (int64_t)t * BT);
-                tma_load_2d(&tmT1, &t_full[s], d, head * BD, row0);
-                tma_load_2d(&tmT2, &t_full[s], d + T_BYTES, head * BD, row0);
+                if (leader) {
+                    mbar_expect_tx(&t_full[s], STAGE);
+                    tma_load_2d(&tmT1, &t_full[s], d, head * BD, row0);
+                    tma_load_2d(&tmT2, &t_full[s], d + T_BYTES, head * BD, row0);
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    tma_load_2d(&tmU1, &t_full[s], d + 2 * T_BYTES + c * (BD * 32 * 4), row0 + c * 32, head * BD);
-                    if (DKV)
-                        tma_load_2d(&tmU2, &t_full[s], d + 2 * T_BYTES + U_BYTES + c * (BD * 32 * 4), row0 + c * 32, head * BD);
+                    for (int c = 0; c < 2; ++c) {
+                        tma_load_2d(&tmU1, &t_full[s], d + 2 * T_BYTES + c * (BD * 32 * 4), row0 + c * 32, head * BD);
+                        if (DKV)
+                            tma_load_2d(&tmU2, &t_full[s], d + 2 * T_BYTES + U_BYTES + c * (BD * 32 * 4), row0 + c * 32, head * BD);
+                    }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc_x = umma_idesc(2, BR, BT);   // 128 x 64
             constexpr uint32_t idesc_a = umma_idesc(2, BR, BD);   // 128 x 32
             mbar_wait(r_full, 0);
@@ -136,33 +144,40 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_c
                 const uint32_t t1 = smem_u32(sT + s * STAGE), t2 = t1 + T_BYTES, u1 = t2 + T_BYTES, u2 = u1 + U_BYTES;
                 // X = R1 T1^T, Y = R2 T2^T   (their TMEM columns are free: the operands of tile t-1 were published,
                 // i.e. X/Y of tile t-1 were fully read)
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    mma_tf32(tmem_X, umma_desc_k128(r1 + k * 32), umma_desc_k128(t1 + k * 32), idesc_x, k != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k)
+                        mma_tf32(tmem_X, umma_desc_k128(r1 + k * 32), umma_desc_k128(t1 + k * 32), idesc_x, k != 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    mma_tf32(tmem_Y, umma_desc_k128(r2 + k * 32), umma_desc_k128(t2 + k * 32), idesc_x, k != 0 ? 1u : 0u);
-                tc_commit(s_full);
+                    for (int k = 0; k < 4; ++k)
+                        mma_tf32(tmem_Y, umma_desc_k128(r2 + k * 32), umma_desc_k128(t2 + k * 32), idesc_x, k != 0 ? 1u : 0u);
+                    tc_commit(s_full);
+                }
+                __syncwarp();
                 // accumulate: acc0 += A0 U1, (acc1 += A1 U2)
                 mbar_wait(p_full, tp);
                 tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma_tf32(tmem_A0, umma_desc_k128(a0 + c * (BR * 32 * 4) + k * 32),
-                                 umma_desc_k128(u1 + c * (BD * 32 * 4) + k * 32), idesc_a, (t | c | k) != 0 ? 1u : 0u);
-                if (DKV) {
+                if (leader) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            mma_tf32(tmem_A1, umma_desc_k128(a1 + c * (BR * 32 * 4) + k * 32),
-                                     umma_desc_k128(u2 + c * (BD * 32 * 4) + k * 32), idesc_a, (t | c | k) != 0 ? 1u : 0u);
+                            mma_tf32(tmem_A0, umma_desc_k128(a0 + c * (BR * 32 * 4) + k * 32),
+                                     umma_desc_k128(u1 + c * (BD * 32 * 4) + k * 32), idesc_a, (t | c | k) != 0 ? 1u : 0u);
+                    if (DKV) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                mma_tf32(tmem_A1, umma_desc_k128(a1 + c * (BR * 32 * 4) + k * 32),
+                                         umma_desc_k128(u2 + c * (BD * 32 * 4) + k * 32), idesc_a, (t | c | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&t_empty[s]);
                 }
-                tc_commit(&t_empty[s]);
+                __syncwarp();
             }
-            tc_commit(acc_full);
+            if (leader) tc_commit(acc_full);
+            __syncwarp();
         }
     } else {
         // ================================ element-wise warps ================================

@@ -62,7 +62,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* o_free = bars + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int head = blockIdx.y, frame = blockIdx.z;
     const int64_t q0 = (int64_t)blockIdx.x * AQ;
 
@@ -89,26 +89,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AK;
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(q_full, Q_BYTES);
-            for (int kb = 0; kb < DB; ++kb)
-                tma_load_2d(&tmQ, q_full, sQ + kb * (AQ * 128), head * AD + kb * 32, (int)(frame * p.L + q0));
+        {   // whole warp runs the loop, the elected lane issues (tc_common.cuh: elect_one)
+            const bool leader = elect_one();
+            if (leader) {
+                mbar_expect_tx(q_full, Q_BYTES);
+                for (int kb = 0; kb < DB; ++kb)
+                    tma_load_2d(&tmQ, q_full, sQ + kb * (AQ * 128), head * AD + kb * 32, (int)(frame * p.L + q0));
+            }
+            __syncwarp();
             for (int t = 0; t < p.num_tiles; ++t) {
                 const int s = t % KV_STAGES;
                 const uint32_t ph = (uint32_t)(t / KV_STAGES) & 1u;
                 mbar_wait(&kv_empty[s], ph ^ 1u);
-                mbar_expect_tx(&kv_full[s], K_BYTES + VT_BYTES);
                 uint8_t* kd = sKV + s * (K_BYTES + VT_BYTES);
                 const int key0 = (int)(frame * p.S + (int64_t)t * AK);
-                for (int kb = 0; kb < DB; ++kb)
-                    tma_load_2d(&tmK, &kv_full[s], kd + kb * (AK * 128), head * AD + kb * 32, key0);
+                if (leader) {
+                    mbar_expect_tx(&kv_full[s], K_BYTES + VT_BYTES);
 #pragma unroll
-                for (int c = 0; c < KC; ++c)  // V^T chunk c: rows head*AD..+AD-1, keys key0+32c..+31
-                    tma_load_2d(&tmVt, &kv_full[s], kd + K_BYTES + c * (AD * 32 * 4), key0 + c * 32, head * AD);
+                    for (int kb = 0; kb < DB; ++kb)
+                        tma_load_2d(&tmK, &kv_full[s], kd + kb * (AK * 128), head * AD + kb * 32, key0);
+#pragma unroll
+                    for (int c = 0; c < KC; ++c)  // V^T chunk c: rows head*AD..+AD-1, keys key0+32c..+31
+                        tma_load_2d(&tmVt, &kv_full[s], kd + K_BYTES + c * (AD * 32 * 4), key0 + c * 32, head * AD);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc_s = umma_idesc(2, AQ, AK);   // 128 x 128
             constexpr uint32_t idesc_o = umma_idesc(2, AQ, AD);   // 128 x AD
             mbar_wait(q_full, 0);
@@ -123,25 +132,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t k_addr = smem_u32(sKV + s * (K_BYTES + VT_BYTES));
                 const uint32_t v_addr = k_addr + K_BYTES;
                 // S = Q K^T   (S columns are free: P(t-1) was published, i.e. S(t-1) fully read)
+                if (leader) {
 #pragma unroll
-                for (int kb = 0; kb < DB; ++kb)
+                    for (int kb = 0; kb < DB; ++kb)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma_tf32(tmem_S, umma_desc_k128(q_addr + kb * (AQ * 128) + k * 32),
-                                 umma_desc_k128(k_addr + kb * (AK * 128) + k * 32), idesc_s, (kb | k) != 0 ? 1u : 0u);
-                tc_commit(s_full);
+                        for (int k = 0; k < 4; ++k)
+                            mma_tf32(tmem_S, umma_desc_k128(q_addr + kb * (AQ * 128) + k * 32),
+                                     umma_desc_k128(k_addr + kb * (AK * 128) + k * 32), idesc_s, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(s_full);
+                }
+                __syncwarp();
                 // O_t = P V
                 mbar_wait(p_full, tp);
                 if (t > 0) mbar_wait(o_free, tp ^ 1u);
                 tc_fence_after();
+                if (leader) {
 #pragma unroll
-                for (int c = 0; c < KC; ++c)
+                    for (int c = 0; c < KC; ++c)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma_tf32(tmem_O, umma_desc_k128(p_addr + c * (AQ * 32 * 4) + k * 32),
-                                 umma_desc_k128(v_addr + c * (AD * 32 * 4) + k * 32), idesc_o, (c | k) != 0 ? 1u : 0u);
-                tc_commit(o_full);
-                tc_commit(&kv_empty[s]);
+                        for (int k = 0; k < 4; ++k)
+                            mma_tf32(tmem_O, umma_desc_k128(p_addr + c * (AQ * 32 * 4) + k * 32),
+                                     umma_desc_k128(v_addr + c * (AD * 32 * 4) + k * 32), idesc_o, (c | k) != 0 ? 1u : 0u);
+                    tc_commit(o_full);
+                    tc_commit(&kv_empty[s]);
+                }
+                __syncwarp();
             }
         }
     } else {

@@ -188,6 +188,12 @@ bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int KH, int KW, i
 int conv_tc_launch(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int KH, int KW, int stride, int pad,
                    float* y, const Epilogue& ep, int engine, cudaStream_t st);
 
+// persistent 3xTF32 engine with pre-split weights (gemm_x3.cu)
+int gemm_x3_launch(const float* A, int64_t lda, const float* W2, float* C, int64_t ldc, int64_t M, int N, int K,
+                   const Epilogue& ep, cudaStream_t st, float* stat_out);
+int conv_x3_launch(const float* x, int B, int H, int W, int Cin, const float* w2, int Cout, int KH, int KW, int stride, int pad,
+                   float* y, const Epilogue& ep, cudaStream_t st);
+
 }  // namespace cofi
 
 using namespace cofi;
@@ -203,6 +209,11 @@ extern "C" int cofi_gemm(const float* A, int64_t lda, const float* W, int64_t ld
     if (M == 0) return COFI_OK;
     Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, accumulate, act, nullptr, nullptr, 0.0f};
     if (engine == COFI_GEMM_FP32) return gemm_simt_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, (cudaStream_t)stream);
+    if (engine == COFI_GEMM_TF32X3S) {
+        COFI_REQUIRE(ldw == K && gemm_tc_supported(lda, ldw, ldc, M, N, K, A, W, C),
+                     "cofi_gemm: COFI_GEMM_TF32X3S needs W = cofi_split_tf32 output (ldw == K), N >= 16, 16-byte aligned operands");
+        return gemm_x3_launch(A, lda, W, C, ldc, M, N, K, ep, (cudaStream_t)stream, nullptr);
+    }
     if (engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3) {
         if (!gemm_tc_supported(lda, ldw, ldc, M, N, K, A, W, C))
             return gemm_simt_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, (cudaStream_t)stream);
@@ -222,6 +233,11 @@ extern "C" int cofi_conv2d_nhwc(const float* x, int B, int H, int W, int Cin, co
     COFI_REQUIRE((scale == nullptr) == (shift == nullptr), "cofi_conv2d_nhwc: scale and shift go together");
     COFI_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0, "cofi_conv2d_nhwc: 16-byte alignment");
     Epilogue ep{nullptr, nullptr, scale, shift, residual, Cout, 0, act, nullptr, nullptr, 0.0f};
+    if (engine == COFI_GEMM_TF32X3S) {
+        COFI_REQUIRE(conv_tc_supported(B, H, W, Cin, Cout, KH, KW, stride, pad),
+                     "cofi_conv2d_nhwc: shape unsupported by the COFI_GEMM_TF32X3S engine");
+        return conv_x3_launch(x, B, H, W, Cin, w, Cout, KH, KW, stride, pad, y, ep, (cudaStream_t)stream);
+    }
     if ((engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3) && conv_tc_supported(B, H, W, Cin, Cout, KH, KW, stride, pad))
         return conv_tc_launch(x, B, H, W, Cin, w, Cout, KH, KW, stride, pad, y, ep, engine, (cudaStream_t)stream);
     return conv_simt_launch(x, B, H, W, Cin, w, Cout, KH, KW, stride, pad, y, ep, (cudaStream_t)stream);
@@ -239,6 +255,12 @@ extern "C" int cofi_gemm_ln(const float* A, int64_t lda, const float* W, int64_t
     COFI_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K && ldc >= N, "cofi_gemm_ln: bad leading dimension");
     COFI_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "cofi_gemm_ln: A and W must be 16-byte aligned");
     if (M == 0) return COFI_OK;
+    if (engine == COFI_GEMM_TF32X3S) {
+        COFI_REQUIRE(ldw == K && N <= 128 && N % 32 == 0 && gemm_tc_supported(lda, ldw, ldc, M, N, K, A, W, C),
+                     "cofi_gemm_ln: COFI_GEMM_TF32X3S needs split weights (ldw == K), N <= 128, N % 32 == 0");
+        Epilogue ep{bias, nullptr, nullptr, nullptr, residual, ldr, 0, act, gamma, beta, eps};
+        return gemm_x3_launch(A, lda, W, C, ldc, M, N, K, ep, (cudaStream_t)stream, nullptr);
+    }
     if ((engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3) && N <= 128 && N % 32 == 0 &&
         gemm_tc_supported(lda, ldw, ldc, M, N, K, A, W, C)) {
         Epilogue ep{bias, nullptr, nullptr, nullptr, residual, ldr, 0, act, gamma, beta, eps};
@@ -269,9 +291,14 @@ extern "C" int cofi_gemm_colstats(const float* A, int64_t lda, const float* W, i
     COFI_REQUIRE(A && W && C && stats, "cofi_gemm_colstats: null pointer");
     COFI_REQUIRE(M > 0 && M % 128 == 0 && N >= 16 && K > 0, "cofi_gemm_colstats: M must be a positive multiple of 128, N >= 16");
     COFI_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K && ldc >= N, "cofi_gemm_colstats: bad leading dimension");
-    COFI_REQUIRE(engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3, "cofi_gemm_colstats: tensor-core engines only");
+    COFI_REQUIRE(engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3 || engine == COFI_GEMM_TF32X3S,
+                 "cofi_gemm_colstats: tensor-core engines only");
     COFI_REQUIRE(gemm_tc_supported(lda, ldw, ldc, M, N, K, A, W, C), "cofi_gemm_colstats: shape/alignment unsupported");
     Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, 0, COFI_ACT_NONE, nullptr, nullptr, 0.0f};
+    if (engine == COFI_GEMM_TF32X3S) {
+        COFI_REQUIRE(ldw == K, "cofi_gemm_colstats: COFI_GEMM_TF32X3S needs W = cofi_split_tf32 output (ldw == K)");
+        return gemm_x3_launch(A, lda, W, C, ldc, M, N, K, ep, (cudaStream_t)stream, stats);
+    }
     return gemm_tc_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, engine, (cudaStream_t)stream, stats);
 }
 

@@ -145,6 +145,11 @@ const CUtensorMap* get_tmap_f16(const void* base, int rank, const uint64_t* dims
                                 const uint32_t* box) {
     return get_tmap_any(base, rank, dims, strides_bytes, box, 1);
 }
+// fp32, K-major, with element strides (strided convolutions); used by gemm_x3.cu
+const CUtensorMap* get_tmap_f32_es(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                   const uint32_t* box, const uint32_t* elem_strides) {
+    return get_tmap_any(base, rank, dims, strides_bytes, box, 0, elem_strides, 0);
+}
 
 // ---------------------------------------------------------------------------------------------- kernel
 constexpr int TM = 128;   // tile rows (UMMA M)
@@ -212,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s_beta = s_gamma + BN;                                    // [BN] fused-LayerNorm bias
     float* s_col = s_beta + BN;                                      // [4 quarters][BN][2] column statistics
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
     // tile origin
     int64_t m0 = 0;
@@ -245,31 +250,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0 && !(p.dbg & 2)) {
+        if (!(p.dbg & 2)) {
+            const bool leader = elect_one();  // whole warp runs the loop, the elected lane issues (tc_common.cuh)
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 const int s = kb % C::NS;
                 const uint32_t ph = (uint32_t)(kb / C::NS) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
-                mbar_expect_tx(&full[s], C::STAGE);
                 uint8_t* a_dst = smem + s * C::STAGE;
                 uint8_t* b_dst = a_dst + A_BYTES;
                 if (CONV) {
                     const int tap = kb / p.cpt, cc = kb - tap * p.cpt;
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                    // strided conv: the tensor map carries elementStrides {1, s, s, 1}, coordinates are in input pixels
-                    tma_load_4d(&tmA, &full[s], a_dst, cc * TK, cw0 * p.cstride + kw - p.pad, ch0 * p.cstride + kh - p.pad, cb);
-                    tma_load_2d(&tmB, &full[s], b_dst, tap * p.Cin + cc * TK, n0);
-                } else {
+                    if (leader) {
+                        mbar_expect_tx(&full[s], C::STAGE);
+                        // strided conv: the tensor map carries elementStrides {1, s, s, 1}, coordinates are in input pixels
+                        tma_load_4d(&tmA, &full[s], a_dst, cc * TK, cw0 * p.cstride + kw - p.pad, ch0 * p.cstride + kh - p.pad, cb);
+                        tma_load_2d(&tmB, &full[s], b_dst, tap * p.Cin + cc * TK, n0);
+                    }
+                } else if (leader) {
                     // k-block = 128 bytes of K: 32 fp32 or 64 fp16 elements
+                    mbar_expect_tx(&full[s], C::STAGE);
                     tma_load_2d(&tmA, &full[s], a_dst, kb * (HALF ? 64 : TK), (int)m0);
                     tma_load_2d(&tmB, &full[s], b_dst, kb * (HALF ? 64 : TK), n0);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0 && !(p.dbg & 2)) {
+        if (!(p.dbg & 2)) {
             constexpr uint32_t idesc = umma_idesc(HALF ? 0 /*f16*/ : 2 /*tf32*/, TM, BN);
+            const bool leader = elect_one();
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 const int s = kb % C::NS;
                 const uint32_t ph = (uint32_t)(kb / C::NS) & 1u;
@@ -277,25 +288,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * C::STAGE);
                 const uint32_t b_addr = a_addr + A_BYTES;
+                const uint32_t alo = X3 ? smem_u32(lo_base + s * C::STAGE) : 0u;
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < TK / 8; ++k) {
-                    const uint64_t ad = umma_desc_k128(a_addr + k * 32);
-                    const uint64_t bd = umma_desc_k128(b_addr + k * 32);
-                    if (HALF)
-                        mma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-                    else
-                        mma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-                    if (X3) {
-                        const uint32_t alo = smem_u32(lo_base + s * C::STAGE);
-                        const uint64_t ald = umma_desc_k128(alo + k * 32);
-                        const uint64_t bld = umma_desc_k128(alo + A_BYTES + k * 32);
-                        mma_tf32(tmem_base, ald, bd, idesc, 1u);
-                        mma_tf32(tmem_base, ad, bld, idesc, 1u);
+                    for (int k = 0; k < TK / 8; ++k) {
+                        const uint64_t ad = umma_desc_k128(a_addr + k * 32);
+                        const uint64_t bd = umma_desc_k128(b_addr + k * 32);
+                        if (HALF)
+                            mma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else
+                            mma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (X3) {
+                            const uint64_t ald = umma_desc_k128(alo + k * 32);
+                            const uint64_t bld = umma_desc_k128(alo + A_BYTES + k * 32);
+                            mma_tf32(tmem_base, ald, bd, idesc, 1u);
+                            mma_tf32(tmem_base, ad, bld, idesc, 1u);
+                        }
                     }
+                    tc_commit(&empty[s]);
                 }
-                tc_commit(&empty[s]);
+                __syncwarp();
             }
-            tc_commit(tmem_full);
+            if (leader) tc_commit(tmem_full);
+            __syncwarp();
         }
     } else if (warp < 2 + 4 * C::EPI_SETS) {
         // ================================ epilogue ====================================
@@ -668,7 +683,7 @@ bool gemm_tc_supported(int64_t lda, int64_t ldw, int64_t ldc, int64_t M, int N, 
 // Output tensor map for the TMA-store epilogue: [M, N] fp32 with row pitch ldc, 32 x 32 boxes, SWIZZLE_128B.  nullptr when
 // the rows are not 16-byte aligned (the kernel then stores from registers through its transposing staging area) or when
 // COFI_TMA_STORE=0.
-static const CUtensorMap* c_tmap(const float* C, int64_t ldc, int64_t M, int N) {
+const CUtensorMap* gemm_c_tmap(const float* C, int64_t ldc, int64_t M, int N) {
     static const bool on = [] {
         const char* e = getenv("COFI_TMA_STORE");
         return !(e && e[0] == '0');
@@ -703,7 +718,7 @@ int gemm_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, flo
     p.stat_out = stat_out;
     p.dbg = tc_debug();
     dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
-    return dispatch<false>(ta, tb, c_tmap(C, ldc, M, N), p, bn, engine == COFI_GEMM_TF32X3, grid, st);
+    return dispatch<false>(ta, tb, gemm_c_tmap(C, ldc, M, N), p, bn, engine == COFI_GEMM_TF32X3, grid, st);
 }
 
 // fp16-operand GEMM (A [M,K] half, W [N,K] half, fp32 accumulate/output): KPConv weight-apply on the tf32 engine.
@@ -729,7 +744,7 @@ int gemm_tc_f16_launch(const void* A, int64_t lda, const void* W, int64_t ldw, f
     p.stat_out = stat_out;
     p.dbg = tc_debug();
     dim3 grid((unsigned)ceil_div(M, TM), (unsigned)ceil_div(N, bn));
-    const CUtensorMap* tc_map = c_tmap(C, ldc, M, N);
+    const CUtensorMap* tc_map = gemm_c_tmap(C, ldc, M, N);
     if (bn == 32) return launch_one<32, false, false, true>(ta, tb, tc_map, p, grid, st);
     if (bn == 64) return launch_one<64, false, false, true>(ta, tb, tc_map, p, grid, st);
     return launch_one<128, false, false, true>(ta, tb, tc_map, p, grid, st);

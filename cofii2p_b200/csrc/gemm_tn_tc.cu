@@ -61,7 +61,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tmem_full = empty + C::NS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
     const int64_t r_begin = (int64_t)blockIdx.z * p.per;
     const int64_t r_end = r_begin + p.per < p.R ? r_begin + p.per : p.R;
@@ -84,38 +84,45 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp runs the loop, the elected lane issues (tc_common.cuh: elect_one)
+            const bool leader = elect_one();
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % C::NS;
                 mbar_wait(&empty[s], (((uint32_t)(kb / C::NS)) & 1u) ^ 1u);
-                mbar_expect_tx(&full[s], C::STAGE);
                 uint8_t* a_dst = smem + s * C::STAGE;
                 uint8_t* b_dst = a_dst + C::A_BYTES;
                 const int64_t r = r_begin + (int64_t)kb * TN_KB;
+                if (leader) {
+                    mbar_expect_tx(&full[s], C::STAGE);
 #pragma unroll
-                for (int mb = 0; mb < 4; ++mb) tma_load_2d(&tmA, &full[s], a_dst + mb * TN_BLK, m0 + 32 * mb, (int)r);
+                    for (int mb = 0; mb < 4; ++mb) tma_load_2d(&tmA, &full[s], a_dst + mb * TN_BLK, m0 + 32 * mb, (int)r);
+                }
                 if (p.conv) {
                     const int64_t g = r / TN_KB;
                     const int wc = (int)(g % p.wchunks);
                     const int ho = (int)((g / p.wchunks) % p.Ho);
                     const int b = (int)(g / ((int64_t)p.wchunks * p.Ho));
+                    if (leader) {
 #pragma unroll
-                    for (int nb = 0; nb < BN / 32; ++nb) {
-                        const int n = n0 + 32 * nb;
-                        const int tap = n / p.Cin, ci0 = n - tap * p.Cin;
-                        const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                        tma_load_4d(&tmB, &full[s], b_dst + nb * TN_BLK, ci0, wc * TN_KB * p.stride - p.pad + kw,
-                                    ho * p.stride - p.pad + kh, b);
+                        for (int nb = 0; nb < BN / 32; ++nb) {
+                            const int n = n0 + 32 * nb;
+                            const int tap = n / p.Cin, ci0 = n - tap * p.Cin;
+                            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                            tma_load_4d(&tmB, &full[s], b_dst + nb * TN_BLK, ci0, wc * TN_KB * p.stride - p.pad + kw,
+                                        ho * p.stride - p.pad + kh, b);
+                        }
                     }
-                } else {
+                } else if (leader) {
 #pragma unroll
                     for (int nb = 0; nb < BN / 32; ++nb)
                         tma_load_2d(&tmB, &full[s], b_dst + nb * TN_BLK, n0 + 32 * nb, (int)r);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = umma_idesc(2 /*tf32*/, 128, BN) | (1u << 15) | (1u << 16);  // A and B MN-major
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % C::NS;
@@ -123,13 +130,17 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * C::STAGE);
                 const uint32_t b_addr = a_addr + C::A_BYTES;
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < TN_KB / 8; ++k)
-                    mma_tf32(tmem_base, umma_desc_mn128(a_addr + k * 1024, TN_BLK), umma_desc_mn128(b_addr + k * 1024, TN_BLK),
-                             idesc, (kb | k) != 0 ? 1u : 0u);
-                tc_commit(&empty[s]);
+                    for (int k = 0; k < TN_KB / 8; ++k)
+                        mma_tf32(tmem_base, umma_desc_mn128(a_addr + k * 1024, TN_BLK), umma_desc_mn128(b_addr + k * 1024, TN_BLK),
+                                 idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(&empty[s]);
+                }
+                __syncwarp();
             }
-            tc_commit(tmem_full);
+            if (leader) tc_commit(tmem_full);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;

@@ -43,7 +43,7 @@ sim_argmin_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t* s_empty = s_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int frame = blockIdx.y;
     const int64_t m0 = (int64_t)blockIdx.x * SM_M;
 
@@ -68,22 +68,30 @@ sim_argmin_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(a_full, p.kb * SM_SLOT);
-            for (int kb = 0; kb < p.kb; ++kb)
-                tma_load_2d(&tmA, a_full, sA + kb * SM_SLOT, kb * SM_K, (int)(frame * p.Npt + m0));
+        {   // whole warp runs the loop, the elected lane issues (tc_common.cuh: elect_one)
+            const bool leader = elect_one();
+            if (leader) {
+                mbar_expect_tx(a_full, p.kb * SM_SLOT);
+                for (int kb = 0; kb < p.kb; ++kb)
+                    tma_load_2d(&tmA, a_full, sA + kb * SM_SLOT, kb * SM_K, (int)(frame * p.Npt + m0));
+            }
+            __syncwarp();
             int it = 0;
             for (int j = 0; j < p.num_tiles; ++j)
                 for (int kb = 0; kb < p.kb; ++kb, ++it) {
                     const int s = it % SM_RING;
                     const uint32_t ph = (uint32_t)(it / SM_RING) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
-                    mbar_expect_tx(&full[s], SM_SLOT);
-                    tma_load_2d(&tmB, &full[s], sB + s * SM_SLOT, kb * SM_K, (int)(frame * p.Npx + (int64_t)j * SM_N));
+                    if (leader) {
+                        mbar_expect_tx(&full[s], SM_SLOT);
+                        tma_load_2d(&tmB, &full[s], sB + s * SM_SLOT, kb * SM_K, (int)(frame * p.Npx + (int64_t)j * SM_N));
+                    }
+                    __syncwarp();
                 }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = umma_idesc(2, SM_M, SM_N);
             mbar_wait(a_full, 0);
             const uint32_t a_addr = smem_u32(sA);
@@ -97,13 +105,17 @@ sim_argmin_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     mbar_wait(&full[s], (uint32_t)(it / SM_RING) & 1u);
                     tc_fence_after();
                     const uint32_t b_addr = smem_u32(sB + s * SM_SLOT);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < SM_K / 8; ++k)
-                        mma_tf32(tmem_base + b * SM_N, umma_desc_k128(a_addr + kb * SM_SLOT + k * 32),
-                                 umma_desc_k128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc_commit(&empty[s]);
+                        for (int k = 0; k < SM_K / 8; ++k)
+                            mma_tf32(tmem_base + b * SM_N, umma_desc_k128(a_addr + kb * SM_SLOT + k * 32),
+                                     umma_desc_k128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_commit(&empty[s]);
+                    }
+                    __syncwarp();
                 }
-                tc_commit(&s_full[b]);
+                if (leader) tc_commit(&s_full[b]);
+                __syncwarp();
             }
         }
     } else {

@@ -85,7 +85,7 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t li_s = lv_s + S16_CAP * S16_ROWS * 4;
     constexpr uint32_t SLOT_B = S16_ROWS * 4;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int frame = blockIdx.y;
     const int64_t m0 = (int64_t)blockIdx.x * (2 * S16_MH);
     const int t0 = blockIdx.z * p.tiles_per_split;
@@ -113,24 +113,32 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(a_full, 2 * p.kb * S16_SLOT);
-            for (int h = 0; h < 2; ++h)
-                for (int kb = 0; kb < p.kb; ++kb)
-                    tma_load_2d(&tmA, a_full, sA + (h * S16_MAXKB + kb) * S16_SLOT, kb * S16_K,
-                                (int)(frame * p.Npt + m0 + h * S16_MH));
+        {   // whole warp runs the loop, the elected lane issues (tc_common.cuh: elect_one)
+            const bool leader = elect_one();
+            if (leader) {
+                mbar_expect_tx(a_full, 2 * p.kb * S16_SLOT);
+                for (int h = 0; h < 2; ++h)
+                    for (int kb = 0; kb < p.kb; ++kb)
+                        tma_load_2d(&tmA, a_full, sA + (h * S16_MAXKB + kb) * S16_SLOT, kb * S16_K,
+                                    (int)(frame * p.Npt + m0 + h * S16_MH));
+            }
+            __syncwarp();
             int it = 0;
             for (int j = 0; j < ntl; ++j)
                 for (int kb = 0; kb < p.kb; ++kb, ++it) {
                     const int s = it % S16_RING;
                     mbar_wait(&empty[s], ((uint32_t)(it / S16_RING) & 1u) ^ 1u);
-                    mbar_expect_tx(&full[s], S16_SLOT);
-                    tma_load_2d(&tmB, &full[s], sB + s * S16_SLOT, kb * S16_K,
-                                (int)(frame * p.Npx + (int64_t)(t0 + j) * S16_N));
+                    if (leader) {
+                        mbar_expect_tx(&full[s], S16_SLOT);
+                        tma_load_2d(&tmB, &full[s], sB + s * S16_SLOT, kb * S16_K,
+                                    (int)(frame * p.Npx + (int64_t)(t0 + j) * S16_N));
+                    }
+                    __syncwarp();
                 }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = umma_idesc(0 /*f16*/, S16_MH, S16_N);
             mbar_wait(a_full, 0);
             const uint32_t a_addr = smem_u32(sA);
@@ -144,16 +152,20 @@ sim_argmin_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     mbar_wait(&full[s], (uint32_t)(it / S16_RING) & 1u);
                     tc_fence_after();
                     const uint32_t b_addr = smem_u32(sB + s * S16_SLOT);
+                    if (leader) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                        for (int h = 0; h < 2; ++h)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)  // UMMA_K = 16 fp16 = 32 bytes per step
-                            mma_f16(tmem_base + (uint32_t)((h * 2 + b) * S16_N),
-                                    umma_desc_k128(a_addr + (h * S16_MAXKB + kb) * S16_SLOT + k * 32),
-                                    umma_desc_k128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc_commit(&empty[s]);
+                            for (int k = 0; k < 4; ++k)  // UMMA_K = 16 fp16 = 32 bytes per step
+                                mma_f16(tmem_base + (uint32_t)((h * 2 + b) * S16_N),
+                                        umma_desc_k128(a_addr + (h * S16_MAXKB + kb) * S16_SLOT + k * 32),
+                                        umma_desc_k128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_commit(&empty[s]);
+                    }
+                    __syncwarp();
                 }
-                tc_commit(&s_full[b]);
+                if (leader) tc_commit(&s_full[b]);
+                __syncwarp();
             }
         }
     } else {

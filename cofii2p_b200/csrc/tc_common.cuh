@@ -12,6 +12,18 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (elect.sync).  Issue pattern for every UTCHMMA / UTMALDG in this library: the WHOLE warp runs
+// the loop (warp index taken through __shfl_sync so that the compiler can prove control flow and operands warp-uniform and
+// keep them in uniform registers) and the elected lane issues.  A lone thread inside divergent code (`if (lane == 0)`) makes
+// ptxas wrap every tcgen05.mma in an R2UR + ELECT loop: 214 clk per MMA instead of the 64 clk an M128 x N128 instruction
+// executes in (tools/micro/mma_rate.cu, profiles/r2_mma_issue_rate.jsonl).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ------------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -29,6 +29,8 @@ SIGNATURES = {
     "cofi_knn_table_workspace": (_l, [_l, _l, _i]),
     "cofi_knn_table": (_i, [_vp, _l, _vp, _l, _i, _i, _i, _vp, _vp, _vp]),
     "cofi_gemm": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "cofi_split_tf32": (_i, [_vp, _l, _i, _i, _vp, _vp]),
+    "cofi_debug_x3_profile": (_i, [_vp]),
     "cofi_gemm_f16": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _vp]),
     "cofi_gemm_colstats": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "cofi_gemm_f16_colstats": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _vp, _vp]),

@@ -86,6 +86,6 @@ class KPConv(nn.Module):
         agg, cnt = ops.kpconv_aggregate(s_feats, packed, q_points, neighbor_indices, self.kernel_points, self.sigma,
                                         frames, self.kp_reach())
         if want_stats and ops.colstats_ok(q_points.shape[0], frames, self.out_channels):
-            return ops.gemm_colstats(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt)
-        out = ops.gemm(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt)
+            return ops.gemm_colstats(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt, const_w=True)
+        out = ops.gemm(agg, self.packed_weight(), bias=self.bias, rowdiv=cnt, const_w=True)
         return (out, None) if want_stats else out

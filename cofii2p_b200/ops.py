@@ -29,6 +29,7 @@ _lib = _Lib()
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 ENGINE_FP32, ENGINE_TF32, ENGINE_TF32X3 = 0, 1, 2
+ENGINE_TF32X3S = 3   # C-ABI only: 3xTF32 with pre-split weights (selected automatically, see _x3_weights)
 _ENGINES = {"fp32": ENGINE_FP32, "tf32": ENGINE_TF32, "tf32x3": ENGINE_TF32X3}
 _engine = ENGINE_FP32
 
@@ -128,6 +129,8 @@ def _chk(rc: int, name: str) -> None:
 # events on the launching stream and annotated with the algorithmic flops / bytes of that launch.
 _prof = None
 _prof_meta = (0.0, 0.0)
+_prof_tag = ""
+_prof_calls = None      # raw per-call records of the last profile_stop: [(name, ms, launches, flops, bytes, tag)]
 
 
 def profile_start() -> None:
@@ -140,12 +143,13 @@ def profile_stop(ridge: Optional[float] = None, raw: bool = False):
     HBM roof) the contraction entry points are split per call into "<op>|tensor" (arithmetic intensity above the ridge) and
     "<op>|hbm": one entry point serves both the K <= 128 streaming contractions and the large-K ones, and a single
     roofline for the mix would describe neither."""
-    global _prof
+    global _prof, _prof_calls
     rec, _prof = _prof, None
     torch.cuda.synchronize()
     out = {}
     calls = []
-    for name, e0, e1, nl, fl, by in rec:
+    _prof_calls = [(name, e0.elapsed_time(e1), nl, fl, by, tag) for name, e0, e1, nl, fl, by, tag in rec]
+    for name, e0, e1, nl, fl, by, _tag in rec:
         if ridge is not None and (name.startswith("cofi_gemm") or name.startswith("cofi_conv2d")) and by > 0:
             name = name + ("|tensor" if fl / by > ridge else "|hbm")
         calls.append((name, nl))
@@ -157,14 +161,15 @@ def profile_stop(ridge: Optional[float] = None, raw: bool = False):
     return (out, calls) if raw else out   # calls: [(op name, kernels launched)] in launch order (tools/ncu_traffic.py)
 
 
-def _meta(flops: float = 0.0, nbytes: float = 0.0) -> None:
-    """Algorithmic work of the NEXT _call (consumed by the profiler only)."""
-    global _prof_meta
+def _meta(flops: float = 0.0, nbytes: float = 0.0, tag: str = "") -> None:
+    """Algorithmic work (and a shape tag) of the NEXT _call (consumed by the profiler only)."""
+    global _prof_meta, _prof_tag
     _prof_meta = (float(flops), float(nbytes))
+    _prof_tag = tag
 
 
 def _call(name: str, *args) -> None:
-    global _prof_meta
+    global _prof_meta, _prof_tag
     if _prof is None:
         rc = getattr(_lib, name)(*args)
     else:
@@ -173,8 +178,9 @@ def _call(name: str, *args) -> None:
         e0.record()
         rc = getattr(_lib, name)(*args)
         e1.record()
-        _prof.append((name, e0, e1, _libmod.launch_count() - n0) + _prof_meta)
+        _prof.append((name, e0, e1, _libmod.launch_count() - n0) + _prof_meta + (_prof_tag,))
     _prof_meta = (0.0, 0.0)
+    _prof_tag = ""
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {_libmod.last_error()}")
 
@@ -282,7 +288,7 @@ def gemm_f16(a_half, w_half, bias=None, rowdiv=None, act: int = ACT_NONE):
     M, K = a_half.shape
     N = w_half.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=a_half.device)
-    _meta(2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N)
+    _meta(2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N, f"{M}x{N}x{K} f16")
     _call("cofi_gemm_f16", _p(a_half), K, _p(w_half), K, _p(out), N, M, N, K, _p(bias), _p(rowdiv), act, _st())
     return out
 
@@ -334,34 +340,73 @@ def gather_rows(x, idx: Optional[torch.Tensor], idx_stride: int = 1, frames: int
 
 
 # ------------------------------------------------------------------------------------------ contractions
-def gemm(a, w, bias=None, rowdiv=None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
-         accumulate: bool = False, engine: Optional[int] = None):
-    """act((a @ w.T) / rowdiv[:,None] + bias (+ out if accumulate)); w is [N,K] (nn.Linear layout)."""
-    a, lda = _rows(a, "a")
+# 3xTF32 with pre-split weights (csrc/gemm_x3.cu): the weight operand of a contraction is a constant of the forward pass, so
+# its two tf32-exact planes [2, N, K] are computed once (cofi_split_tf32) and cached per (storage, view, weights epoch).
+_split_cache: dict = {}
+_split_epoch = -1
+
+
+def _is_weight(w: torch.Tensor) -> bool:
+    """True for nn.Parameters and views of them (w1[:, :C]); activations used as the W operand are split in the kernel."""
+    base = w._base if w._base is not None else w
+    return isinstance(w, torch.nn.Parameter) or isinstance(base, torch.nn.Parameter)
+
+
+def split_tf32(w: torch.Tensor) -> torch.Tensor:
+    """[2, N, K] fp32: plane 0 = w rounded to tf32, plane 1 = (w - plane 0) rounded to tf32 (cached, see above)."""
+    global _split_epoch
+    if _split_epoch != _weights_epoch:
+        _split_cache.clear()
+        _split_epoch = _weights_epoch
     w, ldw = _rows(w, "w")
+    key = (w.data_ptr(), tuple(w.shape), ldw, getattr(w, "_version", 0))
+    hit = _split_cache.get(key)
+    if hit is not None:
+        return hit[0]
+    N, K = w.shape
+    out = torch.empty((2, N, K), dtype=torch.float32, device=w.device)
+    _call("cofi_split_tf32", _p(w), ldw, N, K, _p(out), _st())
+    _split_cache[key] = (out, w)   # keep the source alive: the key holds its address
+    return out
+
+
+def _x3_weights(w: torch.Tensor, eng: int, const_w: Optional[bool]):
+    """(W pointer tensor, ldw, engine) for a contraction: under 3xTF32 a constant weight operand is replaced by its cached
+    split planes and the persistent TF32X3S kernel is selected."""
+    if eng == ENGINE_TF32X3 and (const_w if const_w is not None else _is_weight(w)) and w.shape[0] >= 16 and w.shape[1] % 4 == 0:
+        return split_tf32(w), w.shape[1], ENGINE_TF32X3S
+    w, ldw = _rows(w, "w")
+    return w, ldw, eng
+
+
+def gemm(a, w, bias=None, rowdiv=None, act: int = ACT_NONE, out: Optional[torch.Tensor] = None,
+         accumulate: bool = False, engine: Optional[int] = None, const_w: Optional[bool] = None):
+    """act((a @ w.T) / rowdiv[:,None] + bias (+ out if accumulate)); w is [N,K] (nn.Linear layout).  const_w: w is a
+    constant of the forward pass (default: decided by _is_weight)."""
+    a, lda = _rows(a, "a")
     M, K = a.shape
     N = w.shape[0]
     if w.shape[1] != K:
         raise RuntimeError(f"gemm: K mismatch {a.shape} x {w.shape}")
+    w, ldw, eng = _x3_weights(w, _eng() if engine is None else engine, const_w)
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     ldc = out.stride(0) if M > 1 else max(N, out.stride(0))
-    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
-    _call("cofi_gemm", _p(a), lda, _p(w), ldw, _p(out), ldc, M, N, K, _p(bias), _p(rowdiv), int(accumulate), act,
-                        _eng() if engine is None else engine, _st())
+    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N), f"{M}x{N}x{K}")
+    _call("cofi_gemm", _p(a), lda, _p(w), ldw, _p(out), ldc, M, N, K, _p(bias), _p(rowdiv), int(accumulate), act, eng, _st())
     return out
 
 
-def gemm_colstats(a, w, bias=None, rowdiv=None):
+def gemm_colstats(a, w, bias=None, rowdiv=None, const_w: Optional[bool] = None):
     """tensor-core GEMM that also returns the per-128-row-tile column statistics of its output (for norm_rows_pre)."""
     a, lda = _rows(a, "a")
-    w, ldw = _rows(w, "w")
     M, K = a.shape
     N = w.shape[0]
+    w, ldw, eng = _x3_weights(w, _eng(), const_w)
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     stats = torch.empty((M // 128, N, 2), dtype=torch.float32, device=a.device)
-    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
-    _call("cofi_gemm_colstats", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(rowdiv), _eng(), _p(stats), _st())
+    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N), f"{M}x{N}x{K}")
+    _call("cofi_gemm_colstats", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(rowdiv), eng, _p(stats), _st())
     return out, stats
 
 
@@ -371,7 +416,7 @@ def gemm_f16_colstats(a_half, w_half, bias=None, rowdiv=None):
     N = w_half.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=a_half.device)
     stats = torch.empty((M // 128, N, 2), dtype=torch.float32, device=a_half.device)
-    _meta(2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N)
+    _meta(2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N, f"{M}x{N}x{K} f16")
     _call("cofi_gemm_f16_colstats", _p(a_half), K, _p(w_half), K, _p(out), N, M, N, K, _p(bias), _p(rowdiv), _p(stats), _st())
     return out, stats
 
@@ -403,9 +448,10 @@ def gemm_ln(a, w, gamma, beta, eps: float = 1e-5, bias=None, act: int = ACT_NONE
     """act(LayerNorm(a @ w.T + bias)) + residual, one kernel on the tensor-core engines when N <= 128.
     `out`: optional contiguous [M, N] destination (e.g. a row slice of a larger buffer)."""
     a, lda = _rows(a, "a")
-    w, ldw = _rows(w, "w")
     M, K = a.shape
     N = w.shape[0]
+    fused = N <= 128 and N % 32 == 0   # unfused shapes (GEMM, then LayerNorm) keep the in-kernel split path
+    w, ldw, eng = _x3_weights(w, _eng() if engine is None else engine, None if fused else False)
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     elif tuple(out.shape) != (M, N) or not out.is_contiguous() or out.dtype != torch.float32:
@@ -413,9 +459,9 @@ def gemm_ln(a, w, gamma, beta, eps: float = 1e-5, bias=None, act: int = ACT_NONE
     ldr = 0
     if residual is not None:
         residual, ldr = _rows(residual, "residual")
-    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (2 if residual is not None else 1)))
+    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (2 if residual is not None else 1)), f"{M}x{N}x{K} ln")
     _call("cofi_gemm_ln", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(gamma), _p(beta), float(eps), act,
-          _p(residual), ldr, _eng() if engine is None else engine, _st())
+          _p(residual), ldr, eng, _st())
     return out
 
 
@@ -431,9 +477,13 @@ def conv2d_nhwc(x, w_packed, kh: int, kw: int, stride: int, pad: int, scale=None
     y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
     if residual is not None:
         residual = residual.contiguous()
-    _meta(2.0 * B * Ho * Wo * Cout * kh * kw * Cin, 4.0 * (x.numel() + w_packed.numel() + y.numel()))
+    eng = _eng() if engine is None else engine
+    if eng == ENGINE_TF32X3 and Cout >= 16 and stride in (1, 2) and Wo % 64 == 0 and Ho % 2 == 0:
+        w_packed, eng = split_tf32(w_packed), ENGINE_TF32X3S   # packed conv weights are constants (imagenet.py caches them)
+    _meta(2.0 * B * Ho * Wo * Cout * kh * kw * Cin, 4.0 * (x.numel() + w_packed.numel() + y.numel()),
+          f"{B}x{H}x{W}x{Cin}->{Cout} k{kh}s{stride}")
     _call("cofi_conv2d_nhwc", _p(x), B, H, W, Cin, _p(w_packed), Cout, kh, kw, stride, pad, _p(scale), _p(shift),
-                               _p(residual), act, _p(y), _eng() if engine is None else engine, _st())
+                               _p(residual), act, _p(y), eng, _st())
     return y
 
 

@@ -41,6 +41,8 @@ extern "C" {
 #define COFI_GEMM_FP32 0   /* SIMT fp32 FMA: exact-order parity engine */
 #define COFI_GEMM_TF32 1   /* tcgen05 kind::tf32, fp32 operands read by TMA, fp32 accumulate in TMEM */
 #define COFI_GEMM_TF32X3 2 /* tcgen05 3xTF32 split (hi*hi + hi*lo + lo*hi): fp32-grade accuracy on tensor cores */
+#define COFI_GEMM_TF32X3S 3 /* 3xTF32 with PRE-SPLIT weights: W points to the [2][N][K] output of cofi_split_tf32 (ldw == K);
+                             * persistent kernel, A split in registers into tensor memory (csrc/gemm_x3.cu) */
 
 int cofi_version(void);
 const char* cofi_last_error(void);
@@ -154,6 +156,16 @@ int cofi_knn_table(const float* src, int64_t ns, const float* qry, int64_t nq, i
 int cofi_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
               int64_t M, int N, int K, const float* bias, const float* rowdiv, int accumulate, int act,
               int engine, void* stream);
+
+/* out[2][N][K] (dense): plane 0 = W rounded to tf32, plane 1 = (W - plane 0) rounded to tf32 -- the weight operand of the
+ * COFI_GEMM_TF32X3S engine (cofi_gemm, cofi_gemm_ln, cofi_gemm_colstats, cofi_conv2d_nhwc).  Weights are constants of
+ * the forward pass (model/network.py:15-43), so the host splits them once per weights epoch. */
+int cofi_split_tf32(const float* w, int64_t ldw, int N, int K, float* out, void* stream);
+
+/* Perf triage of the COFI_GEMM_TF32X3S kernel (environment COFI_X3_PROFILE=1): 16 counters accumulated over all launches
+ * since the last call -- clocks the TMA / MMA / epilogue / splitter roles spent waiting on each barrier, k-blocks, CTA
+ * clocks (csrc/gemm_x3.cu).  Not part of the reference-facing surface. */
+int cofi_debug_x3_profile(unsigned long long* out16);
 
 /* fp16-operand variant of cofi_gemm on tcgen05 (kind::f16, fp32 accumulate and output): A [M,K] and W [N,K] are fp16,
  * K-major; K, lda, ldw multiples of 8; N >= 16. */

@@ -21,7 +21,10 @@ SHAPES = [  # (M, N, K, where it occurs in an 8-frame step)
 ]
 engines = sys.argv[1:] or ["tf32", "tf32x3"]
 for eng in engines:
-    ops.set_engine(eng)
+    # "tf32x3s" = the persistent 3xTF32 kernel with pre-split weights (csrc/gemm_x3.cu; what the model's Linear layers run
+    # under the parity preset); "tf32x3" = the one-tile-per-CTA kernel that splits both operands in shared memory
+    const_w = eng == "tf32x3s"
+    ops.set_engine("tf32x3" if const_w else eng)
     for (m, n, k, where) in SHAPES:
         per = 4.0 * (m * k + m * n)
         copies = max(2, int(400e6 // per) + 1)
@@ -30,13 +33,13 @@ for eng in engines:
         w = torch.randn(n, k, device="cuda")
         b = torch.randn(n, device="cuda")
         for i in range(copies):
-            ops.gemm(a[i], w, bias=b, out=o[i])
+            ops.gemm(a[i], w, bias=b, out=o[i], const_w=const_w)
         reps = max(copies, 30)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()          # replayed as a graph: no host launch latency between the kernels
         with torch.cuda.graph(g):
             for i in range(reps):
-                ops.gemm(a[i % copies], w, bias=b, out=o[i % copies])
+                ops.gemm(a[i % copies], w, bias=b, out=o[i % copies], const_w=const_w)
         g.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
