@@ -160,21 +160,38 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
             w = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsqrt_rn(sq), sigma)), 0.0f);
         }
         unsigned mask = __ballot_sync(0xffffffffu, w > 0.0f);
+        // The influencing pairs are consumed in order (the accumulation order of a dense h loop), but their feature rows are
+        // fetched UNR at a time: the gathers are the latency of this kernel (L2 round trips), the FMAs are not.
+        constexpr int UNR = (NCH * VEC >= 16) ? 2 : 4;
         while (mask) {
-            const int l = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int ek = __shfl_sync(0xffffffffu, pk, l);
-            const int er = __shfl_sync(0xffffffffu, prow, l);
-            const float ew = __shfl_sync(0xffffffffu, w, l);
-            while (cur_k < ek) store_row(cur_k++);  // finished rows (zeros when nothing influenced them)
-            if (lane_active) {
-                const float* row = fbase + (int64_t)er * ldf;
+            int ek[UNR], er[UNR];
+            float ew[UNR];
+            V f[UNR][NCH];
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    const V f = __ldg(reinterpret_cast<const V*>(row + (c * 32 + lane) * VEC));
-                    const float* fv = reinterpret_cast<const float*>(&f);
+            for (int u = 0; u < UNR; ++u) {
+                const bool valid = mask != 0u;
+                const int l = valid ? __ffs(mask) - 1 : 0;
+                mask &= mask - 1;   // 0 stays 0
+                ek[u] = valid ? __shfl_sync(0xffffffffu, pk, l) : -1;
+                er[u] = __shfl_sync(0xffffffffu, prow, l);
+                ew[u] = __shfl_sync(0xffffffffu, w, l);
+                if (valid && lane_active) {
+                    const float* row = fbase + (int64_t)er[u] * ldf;
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(ew, fv[v], acc[c][v]);
+                    for (int c = 0; c < NCH; ++c) f[u][c] = __ldg(reinterpret_cast<const V*>(row + (c * 32 + lane) * VEC));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (ek[u] < 0) break;   // warp-uniform
+                while (cur_k < ek[u]) store_row(cur_k++);  // finished rows (zeros when nothing influenced them)
+                if (lane_active) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const float* fv = reinterpret_cast<const float*>(&f[u][c]);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[c][v] = fmaf(ew[u], fv[v], acc[c][v]);
+                    }
                 }
             }
         }

@@ -322,18 +322,27 @@ cast_f16_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C, _
 // across groups), d = 1 - total.  One warp per point row; lanes take the row's candidates (or, after a list overflow / an
 // empty list, every pixel) and the warp keeps the lexicographic minimum of (d, pixel index).
 __device__ __forceinline__ float sim_exact_d(const float* __restrict__ spt, const float* __restrict__ r, int C) {
+    // 64 channels (16 independent 16-byte loads) are fetched before the strictly ordered arithmetic starts: two L2 round
+    // trips per 128-channel row instead of one per group of 16 (the re-rank is a latency chain, not a throughput problem)
     float tot = 0.0f;
-    for (int c0 = 0; c0 < C; c0 += 16) {
-        float g = 0.0f;
+    for (int c0 = 0; c0 < C; c0 += 64) {
+        float4 a[16];
 #pragma unroll
-        for (int c = 0; c < 16; c += 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(r + c0 + c));
-            g = __fadd_rn(g, __fmul_rn(a.x, spt[c0 + c + 0]));
-            g = __fadd_rn(g, __fmul_rn(a.y, spt[c0 + c + 1]));
-            g = __fadd_rn(g, __fmul_rn(a.z, spt[c0 + c + 2]));
-            g = __fadd_rn(g, __fmul_rn(a.w, spt[c0 + c + 3]));
+        for (int i = 0; i < 16; ++i) a[i] = __ldg(reinterpret_cast<const float4*>(r + c0 + 4 * i));
+#pragma unroll
+        for (int gI = 0; gI < 4; ++gI) {
+            float g = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = a[gI * 4 + i];
+                const float* sp = spt + c0 + gI * 16 + i * 4;
+                g = __fadd_rn(g, __fmul_rn(v.x, sp[0]));
+                g = __fadd_rn(g, __fmul_rn(v.y, sp[1]));
+                g = __fadd_rn(g, __fmul_rn(v.z, sp[2]));
+                g = __fadd_rn(g, __fmul_rn(v.w, sp[3]));
+            }
+            tot = __fadd_rn(tot, g);
         }
-        tot = __fadd_rn(tot, g);
     }
     return __fsub_rn(1.0f, tot);
 }
@@ -347,49 +356,83 @@ sim_rerank_kernel(const float* __restrict__ pt, int64_t ldpt, const float* __res
                   const float* __restrict__ cand_val, const int32_t* __restrict__ cand_cnt,
                   int64_t* __restrict__ best_idx, float* __restrict__ best_val, int32_t* __restrict__ stats) {
     __shared__ float spt_all[RR_WARPS][RR_MAXC];
+    __shared__ int s_need[RR_WARPS];
+    __shared__ float s_bd[RR_WARPS][RR_WARPS];
+    __shared__ int s_bi[RR_WARPS][RR_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * RR_WARPS + warp;
-    if (row >= rows) return;
+    const bool live = row < rows;
     float* spt = spt_all[warp];
-    const int64_t frame = row / Npt;
+    const int64_t frame = live ? row / Npt : 0;
     const float* pxb = px + frame * Npx * ldpx;
-    for (int c = lane; c < C; c += 32) spt[c] = __ldg(pt + row * ldpt + c);
-    __syncwarp();
-    float gmax = -INFINITY;
-    bool ovf = false;
-    for (int s = 0; s < nsplit; ++s) {
-        gmax = fmaxf(gmax, part_best[(int64_t)s * rows + row]);
-        ovf |= cand_cnt[(int64_t)s * rows + row] < 0;
-    }
-    const float thr = gmax - sim_margin(margin_base, bound2);
     float bd = INFINITY;
     int bi = 0x7fffffff;
     int evaluated = 0;
-    if (!ovf) {
-        for (int slot = lane; slot < nsplit * S16_CAP; slot += 32) {
-            const int s = slot / S16_CAP, k = slot - s * S16_CAP;
-            const int64_t o = (int64_t)s * rows + row;
-            if (k < cand_cnt[o] && cand_val[o * S16_CAP + k] > thr) {
-                const int x = cand_idx[o * S16_CAP + k];
-                const float d = sim_exact_d(spt, pxb + (int64_t)x * ldpx, C);
-                ++evaluated;
-                if (d < bd || (d == bd && x < bi)) {
-                    bd = d;
-                    bi = x;
+    bool scan = false;
+    if (live) {
+        for (int c = lane; c < C; c += 32) spt[c] = __ldg(pt + row * ldpt + c);
+        __syncwarp();
+        float gmax = -INFINITY;
+        bool ovf = false;
+        for (int s = 0; s < nsplit; ++s) {
+            gmax = fmaxf(gmax, part_best[(int64_t)s * rows + row]);
+            ovf |= cand_cnt[(int64_t)s * rows + row] < 0;
+        }
+        const float thr = gmax - sim_margin(margin_base, bound2);
+        if (!ovf) {
+            for (int slot = lane; slot < nsplit * S16_CAP; slot += 32) {
+                const int s = slot / S16_CAP, k = slot - s * S16_CAP;
+                const int64_t o = (int64_t)s * rows + row;
+                if (k < cand_cnt[o] && cand_val[o * S16_CAP + k] > thr) {
+                    const int x = cand_idx[o * S16_CAP + k];
+                    const float d = sim_exact_d(spt, pxb + (int64_t)x * ldpx, C);
+                    ++evaluated;
+                    if (d < bd || (d == bd && x < bi)) {
+                        bd = d;
+                        bi = x;
+                    }
                 }
             }
         }
+        // nothing evaluated anywhere in the warp (non-finite scores) or an overflowed list: exact scan of the whole row
+        scan = ovf || __ballot_sync(0xffffffffu, evaluated > 0) == 0u;
     }
-    // nothing evaluated anywhere in the warp (non-finite scores) or an overflowed list: exact scan of the whole row
-    const bool scan = ovf || __ballot_sync(0xffffffffu, evaluated > 0) == 0u;
-    if (scan) {
-        for (int64_t x = lane; x < Npx; x += 32) {
-            const float d = sim_exact_d(spt, pxb + x * ldpx, C);
-            if (d < bd) {  // x ascending per lane: strict < keeps the lowest index
-                bd = d;
-                bi = (int)x;
+    if (lane == 0) s_need[warp] = scan ? 1 : 0;
+    __syncthreads();
+    // full scans are rare (about one row in ten thousand) but long: the whole block shares each of them, warp w taking the
+    // pixels w*32 + lane, +256, ...; the lexicographic minimum of (d, pixel) does not depend on how the pixels are dealt out
+    for (int w = 0; w < RR_WARPS; ++w) {
+        if (!s_need[w]) continue;   // block-uniform
+        const int64_t srow = (int64_t)blockIdx.x * RR_WARPS + w;
+        const float* sb = px + (srow / Npt) * Npx * ldpx;
+        float d0 = INFINITY;
+        int i0 = 0x7fffffff;
+        for (int64_t x = warp * 32 + lane; x < Npx; x += RR_WARPS * 32) {
+            const float d = sim_exact_d(spt_all[w], sb + x * ldpx, C);
+            if (d < d0) {  // x ascending per lane: strict < keeps the lowest index
+                d0 = d;
+                i0 = (int)x;
             }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, d0, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i0, o);
+            if (ov < d0 || (ov == d0 && oi < i0)) {
+                d0 = ov;
+                i0 = oi;
+            }
+        }
+        if (lane == 0) {
+            s_bd[w][warp] = d0;
+            s_bi[w][warp] = i0;
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    if (scan) {   // combine the eight partial minima of this warp's row
+        bd = lane < RR_WARPS ? s_bd[warp][lane] : INFINITY;
+        bi = lane < RR_WARPS ? s_bi[warp][lane] : 0x7fffffff;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
