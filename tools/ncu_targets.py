@@ -36,6 +36,12 @@ elif t == "gemmx3":
         a, w = torch.randn(m, k, device="cuda"), torch.randn(n, k, device="cuda")
         for _ in range(2):
             ops.gemm(a, w)
+elif t == "gemmx3s":   # persistent 3xTF32 kernel with pre-split weights (csrc/gemm_x3.cu): HBM-bound and tensor-bound shapes
+    ops.set_engine("tf32x3")
+    for (m, n, k) in ((163840, 128, 32), (20480, 1024, 3072), (20480, 128, 128)):
+        a, w, b = torch.randn(m, k, device="cuda"), torch.randn(n, k, device="cuda"), torch.randn(n, device="cuda")
+        for _ in range(2):
+            ops.gemm(a, w, bias=b, const_w=True)
 elif t == "knn":
     from cofii2p_b200.frames import make_frame, stack_frames
     batch = stack_frames([make_frame(i, cache_dir="/tmp/cofi_frames", device="cuda") for i in range(8)])
