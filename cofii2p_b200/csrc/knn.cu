@@ -25,6 +25,8 @@
 // bounding that noise is added.
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace cofi {
@@ -63,7 +65,7 @@ struct JobDesc {
 struct QueryParams {
     SetDesc set[MAX_SETS];
     JobDesc job[MAX_JOBS];
-    int njobs, cull;
+    int njobs, cull, fast;
 };
 
 __device__ __forceinline__ uint32_t spread10(uint32_t v) {
@@ -399,9 +401,217 @@ __device__ __forceinline__ bool knn_box_pass(const WarpState& w, float d, float 
     return !(d > td + 4e-6f * (qq + smax) + 1e-12f);
 }
 
+// ---- 256 keys of a warp in registers (element e = lane * 8 + r): the final sort of the fast path ----
+struct Keys8 {
+    u64 v[8];
+};
+template <int J, int K>
+__device__ __forceinline__ void bitonic_stage_reg8(Keys8& x, int lane) {
+    if constexpr (J >= 8) {
+        const bool keep_min = ((lane & (J >> 3)) == 0) == (((lane << 3) & K) == 0);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const u64 p = __shfl_xor_sync(0xffffffffu, x.v[r], J >> 3);
+            x.v[r] = ((x.v[r] < p) == keep_min) ? x.v[r] : p;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if ((r & J) == 0) {
+                const bool asc = ((((lane << 3) | r) & K) == 0);
+                const u64 a = x.v[r], b = x.v[r | J];
+                const bool sw = (a > b) == asc;
+                x.v[r] = sw ? b : a;
+                x.v[r | J] = sw ? a : b;
+            }
+    }
+}
+template <int J, int K>
+__device__ __forceinline__ void bitonic_stages_reg8(Keys8& x, int lane) {
+    bitonic_stage_reg8<J, K>(x, lane);
+    if constexpr (J > 1) bitonic_stages_reg8<J / 2, K>(x, lane);
+}
+template <int K>
+__device__ __forceinline__ void bitonic_sort_reg8(Keys8& x, int lane) {
+    if constexpr (K > 2) bitonic_sort_reg8<K / 2>(x, lane);
+    bitonic_stages_reg8<K / 2, K>(x, lane);
+}
+
+constexpr int FCAP = 512;    // candidate capacity of the fast path
+constexpr int FSORT = 256;   // keys the final register sort takes (k <= 128 plus ties / slack)
+constexpr int FSLACK = 48;   // a tightening stops as soon as k <= count <= k + FSLACK
+constexpr int FTRIG = 96;    // tighten again once k + FTRIG candidates are pending
+
+// Fast path of a k > 1 query: select by THRESHOLD instead of by repeated sorting.
+//   * candidates are 64-bit keys (distance bits << 32 | index) appended to a shared-memory list when distance <= t1
+//     (t1 = +inf at the start);
+//   * `tighten`: a bisection on the distance bit pattern over the pending list finds the smallest window t with
+//     k <= #{d <= t} <= k + FSLACK (one count per step: <= 16 compares per lane and one redux), the list is compacted to the
+//     survivors and t1 = t.  t1 is an upper bound of the final k-th distance at all times, because the list holds every
+//     point seen so far with d <= t1 and at least k of them survive;
+//   * order of work: the <= 12 tiles around the query's position in the source order, tighten, then every other tile whose
+//     box can hold a distance <= t1 (group boxes first), tightening whenever k + FTRIG candidates are pending;
+//   * ONE register sort (128 or 256 keys) puts the survivors in (distance, index) order; the first k are the table row.
+// Every point of the true result has d <= final k-th distance <= t1 when its tile is tested, and the box test is exact, so
+// the survivor set contains the result: identical output to the iterative path.  Returns false (nothing written) when more
+// than FSORT keys tie inside the last window or the frame has fewer than k points; the caller then runs the iterative path.
+template <int MODE>
+__device__ __forceinline__ bool knn_fast_path(const JobDesc& J, const SetDesc& S, u64* cand, int lane, int frame, int qi, int qn,
+                                              float qx, float qy, float qz, float qq, int r0, int r1) {
+    const int ns = S.n, T = S.npad >> 5, k = J.k;
+    if (ns < k) return false;
+    const float4* ssort = S.sorted + (size_t)frame * S.npad;
+    const float4* tmin = S.tmin + (size_t)frame * T;
+    const float4* tmax = S.tmax + (size_t)frame * T;
+    const float4* gmin = S.smin + (size_t)frame * S.nsup;
+    const float4* gmax = S.smax + (size_t)frame * S.nsup;
+    int cnt = 0;
+    unsigned t1 = 0xffffffffu;
+    WarpState w;   // only .thresh is used (knn_box_pass)
+    w.thresh = KMAX;
+
+    auto open = [&](int t) {
+        const float4 s = __ldg(ssort + ((size_t)t << 5) + lane);
+        const int si = __float_as_int(s.w);
+        const unsigned db = __float_as_uint(dist2<MODE>(qx, qy, qz, qq, s));
+        const bool keep = si >= 0 && db <= t1;
+        const unsigned pm = __ballot_sync(0xffffffffu, keep);
+        if (keep) cand[cnt + __popc(pm & ((1u << lane) - 1u))] = ((u64)db << 32) | (unsigned)si;
+        cnt += __popc(pm);
+    };
+    // shrink the list to the smallest prefix-by-distance holding >= k keys (<= hard_max), false if ties make that impossible.
+    // NS = register slots per lane (8 covers lists of <= 256 keys, the common case; 16 the full capacity).
+    auto tighten_n = [&](int hard_max, auto ns_tag) -> bool {
+        constexpr int NS = decltype(ns_tag)::value;
+        __syncwarp();
+        unsigned d[NS];
+        unsigned hi = 0u;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int e = i * 32 + lane;
+            d[i] = e < cnt ? (unsigned)(cand[e] >> 32) : 0xffffffffu;
+            if (e < cnt) hi = max(hi, d[i]);
+        }
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        auto count_le = [&](unsigned t) {
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) c += d[i] <= t ? 1 : 0;
+            return (int)__reduce_add_sync(0xffffffffu, c);
+        };
+        // smallest-t search for count >= k, stopped inside the slack window; the search starts 2^-8 below the largest
+        // pending distance and falls back to [0, that) when even that holds k keys
+        unsigned lo = hi > (8u << 23) ? hi - (8u << 23) : 0u;
+        int c_hi = cnt;
+        if (lo > 0u) {
+            const int c = count_le(lo);
+            if (c >= k) {
+                hi = lo;
+                c_hi = c;
+                lo = 0u;
+            } else {
+                ++lo;
+            }
+        }
+        const int want = min(k + FSLACK, hard_max);
+        while (lo < hi && c_hi > want) {
+            const unsigned mid = lo + ((hi - lo) >> 1);
+            const int c = count_le(mid);
+            if (c >= k) {
+                hi = mid;
+                c_hi = c;
+            } else {
+                lo = mid + 1;
+            }
+        }
+        if (c_hi > hard_max) return false;
+        int ncnt = 0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            if (i * 32 < cnt) {   // warp-uniform
+                const int e = i * 32 + lane;
+                const bool keep = d[i] <= hi;   // slots past cnt hold 0xffffffff > hi
+                const u64 key = e < cnt ? cand[e] : 0ull;
+                __syncwarp();   // every lane has read its slot of this chunk before any lane overwrites one
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) cand[ncnt + __popc(m & ((1u << lane) - 1u))] = key;
+                ncnt += __popc(m);
+                __syncwarp();
+            }
+        }
+        cnt = ncnt;
+        t1 = hi;
+        w.thresh = ((u64)t1 << 32) | 0xffffffffull;
+        return true;
+    };
+    auto tighten = [&](int hard_max) -> bool {
+        if (cnt <= 256) return tighten_n(hard_max, std::integral_constant<int, 8>());
+        return tighten_n(hard_max, std::integral_constant<int, FCAP / 32>());
+    };
+
+    for (int t = r0; t < r1; ++t) open(t);   // <= 12 tiles, 384 keys
+    if (cnt >= k && !tighten(FCAP - 64)) return false;
+    for (int gb = 0; gb < S.nsup; gb += 32) {
+        bool gok = gb + lane < S.nsup;
+        if (gok) {
+            float smax;
+            const float d = knn_box_dist(gmin, gmax, gb + lane, qx, qy, qz, smax);
+            gok = knn_box_pass<MODE>(w, d, qq, smax);
+        }
+        unsigned gm = __ballot_sync(0xffffffffu, gok);
+        while (gm) {
+            const int rd = gb + __ffs(gm) - 1;
+            gm &= gm - 1;
+            const int t = (rd << 5) + lane;
+            bool ok = t < T && (t < r0 || t >= r1);
+            if (ok) {
+                float smax;
+                const float d = knn_box_dist(tmin, tmax, t, qx, qy, qz, smax);
+                ok = knn_box_pass<MODE>(w, d, qq, smax);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, ok);
+            while (m) {
+                const int tt = (rd << 5) + __ffs(m) - 1;
+                m &= m - 1;
+                if (tt < r0 || tt >= r1) {
+                    // the box test above used the threshold of the start of this batch of 32: a tightening in between only
+                    // makes it conservative
+                    open(tt);
+                    if (cnt >= k + FTRIG || cnt > FCAP - 32) {
+                        if (cnt < k || !tighten(FCAP - 64)) return false;
+                    }
+                }
+            }
+        }
+    }
+    if (cnt < k) return false;
+    if (cnt > FSORT && !tighten(FSORT)) return false;
+    __syncwarp();
+    int64_t* out = J.out + ((size_t)frame * qn + qi) * k;
+    if (cnt <= KB) {  // at most 128 survivors: the 128-key network is enough
+        Keys4 c;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) c.v[r] = (lane * 4 + r) < cnt ? cand[lane * 4 + r] : KMAX;
+        bitonic_sort_reg<KB>(c, lane);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (lane * 4 + r < k) out[lane * 4 + r] = (int64_t)(unsigned)c.v[r];
+    } else {
+        Keys8 c;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) c.v[r] = (lane * 8 + r) < cnt ? cand[lane * 8 + r] : KMAX;
+        bitonic_sort_reg8<FSORT>(c, lane);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (lane * 8 + r < k) out[lane * 8 + r] = (int64_t)(unsigned)c.v[r];
+    }
+    __syncwarp();
+    return true;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(QWARPS * 32) knn_query_kernel(const __grid_constant__ QueryParams P) {
-    __shared__ unsigned long long s_cand[QWARPS][KB];
+    __shared__ unsigned long long s_cand[QWARPS][FCAP];
     int j = 0;
     while (j + 1 < P.njobs && (int)blockIdx.x >= P.job[j + 1].block_begin) ++j;
     const JobDesc& J = P.job[j];
@@ -492,6 +702,11 @@ __global__ void __launch_bounds__(QWARPS * 32) knn_query_kernel(const __grid_con
         if (lane == 0)
             J.out[(size_t)frame * Q.n + qi] = w.thresh == KMAX ? (int64_t)ns : (int64_t)(unsigned)w.thresh;
         return;
+    }
+
+    // threshold selection + one sort (see knn_fast_path); the iterative path below is the general fallback
+    if (P.fast) {
+        if (knn_fast_path<MODE>(J, S, w.cand, lane, frame, qi, Q.n, qx, qy, qz, qq, r0, r1)) return;
     }
 
     // Four phases through one loop body (the unrolled merge network exists twice in the code: overflow and phase end):
@@ -663,6 +878,7 @@ extern "C" int cofi_knn_pyramid(const float* const* points, const int64_t* n_per
     }
     Q.njobs = 0;
     Q.cull = (mode & COFI_KNN_NOCULL) ? 0 : 1;
+    Q.fast = (mode & (COFI_KNN_NOCULL | COFI_KNN_NOFAST)) ? 0 : 1;
     auto add = [&](int src, int qry, int64_t* out, int kk) {
         if (!out) return;
         JobDesc& J = Q.job[Q.njobs++];
@@ -701,6 +917,7 @@ extern "C" int cofi_knn_table(const float* src, int64_t ns, const float* qry, in
     if (!same) carve_set(Q.set[1], qry, nq, frames, w);
     Q.njobs = 1;
     Q.cull = (mode & COFI_KNN_NOCULL) ? 0 : 1;
+    Q.fast = (mode & (COFI_KNN_NOCULL | COFI_KNN_NOFAST)) ? 0 : 1;
     Q.job[0].src = 0;
     Q.job[0].qry = same ? 0 : 1;
     Q.job[0].out = out;

@@ -739,6 +739,7 @@ def select_matches(score, best_idx, frames: int, grid_h: int, grid_w: int, thres
 
 
 KNN_DIRECT, KNN_EXPANDED, KNN_NOCULL = 0, 1, 0x100
+KNN_NOFAST = 0x200   # test/debug: iterative sort/merge selection for every query (no threshold-selection fast path)
 
 
 def knn_pyramid(points, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT, want=("neighbors", "subsampling", "upsampling"),

@@ -111,6 +111,8 @@ int cofi_gather_rows(const float* x, int64_t ldx, int C, const int64_t* idx, int
 #define COFI_KNN_EXPANDED 1 /* ((-2 q.s + |q|^2) + |s|^2) clamped at 1e-12: `knn()` / `square_distance()` of
                                model/kpconv/preprocess_data.py:110-143 (precompute_point_cloud_cuda) */
 #define COFI_KNN_NOCULL 0x100 /* OR-ed into `mode`: open every tile (brute force; same result, test/debug only) */
+#define COFI_KNN_NOFAST 0x200 /* OR-ed into `mode`: skip the threshold-selection fast path of the query kernel and run the
+                               * iterative sort/merge path for every query (same result, test/debug only) */
 
 /* Random half-sampling of the pyramid on the device (model/kpconv/preprocess_data.py:52-68: level l+1 = level l at
  * n/2 indices drawn WITH replacement).  The draw is counter-based so that the host oracle restates it exactly:

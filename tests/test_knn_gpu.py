@@ -46,7 +46,7 @@ def test_knn_table_vs_oracle(kind, mode):
         if nq <= ns and kind != "far":
             qry[: nq // 2] = src[rng.permutation(ns)[: nq // 2]]     # half the queries are members of the source
         want = ok.knn_table(src, qry, k, mode)
-        for flags in (0, ops.KNN_NOCULL):
+        for flags in (0, ops.KNN_NOCULL, ops.KNN_NOFAST):   # fast (threshold selection), brute force, iterative selection
             got = ops.knn_table(_cuda(src), _cuda(qry), 1, k, mode | flags).cpu().numpy()
             assert np.array_equal(got, want), (kind, mode, ns, nq, k, flags, int((got != want).sum()))
 
@@ -135,12 +135,14 @@ def test_knn_full_size_frame():
     levels = [p.cuda() for p in d["points"]]
     got = ops.knn_pyramid(levels, frames=1, k=128, mode=0)
     nocull = ops.knn_pyramid(levels, frames=1, k=128, mode=ops.KNN_NOCULL)
+    nofast = ops.knn_pyramid(levels, frames=1, k=128, mode=ops.KNN_NOFAST)
     g = torch.Generator().manual_seed(0)
     for name, pairs in (("neighbors", [(l, l) for l in range(5)]), ("subsampling", [(l, l + 1) for l in range(4)]),
                         ("upsampling", [(l + 1, l) for l in range(4)])):
         for i, (s, q) in enumerate(pairs):
             t = got[name][i]
             assert torch.equal(t, nocull[name][i]), (name, i)
+            assert torch.equal(t, nofast[name][i]), (name, i)
             rows = torch.randperm(levels[q].shape[0], generator=g)[:256].cuda()
             dv, di = _torch_direct_rows(levels[s], levels[q], rows)
             assert torch.equal(t[rows], di[:, :128]), (name, i)

@@ -41,7 +41,12 @@ def main():
     out_bytes = 8 * 128 * (sum(n) + sum(n[1:]) + sum(n[:-1]))
     ws = ops._ws(ops._lib.cofi_knn_pyramid_workspace((__import__("ctypes").c_int64 * 5)(*n), 5, B), levels[0].device)
     res = {"frames": B, "num_pc": args.num_pc, "pairs_per_frame": pairs, "table_bytes_per_frame": out_bytes}
-    for name, mode in (("direct", 0), ("expanded", 1), ("direct_nocull", ops.KNN_NOCULL)):
+    for name, mode in (("direct", 0), ("expanded", 1), ("direct_iterative_selection", ops.KNN_NOFAST),
+                       ("direct_engine_tables_k_up_1", -1), ("direct_nocull", ops.KNN_NOCULL)):
+        if mode == -1:   # what the engine builds: up-sampling tables reduced to their single live column
+            ms = timed(lambda: ops.knn_pyramid(levels, frames=B, k=128, k_up=1, mode=0, workspace=ws), 10)
+            res[name] = {"ms_per_batch": ms, "ms_per_frame": ms / B}
+            continue
         ms = timed(lambda: ops.knn_pyramid(levels, frames=B, k=128, mode=mode, workspace=ws), 10 if mode < 256 else 3)
         res[name] = {"ms_per_batch": ms, "ms_per_frame": ms / B, "gpairs_per_s": pairs * B / ms / 1e6,
                      "table_write_GBps": out_bytes * B / ms / 1e6}
