@@ -1,16 +1,18 @@
 // attention_tc.cu -- tcgen05 flash attention for the LoFTR encoder layer
 // (reference model/transformer/linear_attention.py:69-77: softmax(Q K^T / sqrt(D)) V per head; D = 32).
 //
-// One CTA = 128 query rows of one (frame, head).  Keys are walked in tiles of 128:
-//   warp 0   TMA producer: Q tile once; per key tile the K tile [128 keys x 32] and the V^T tile
-//            [32 d x 128 keys] (V^T comes straight out of the v_proj GEMM with swapped operands, so both MMA
-//            operands are K-major and use the same SWIZZLE_128B descriptors as the GEMM engine).
-//   warp 1   MMA issuer:  S[128x128] = Q K^T  (kind::tf32, 4 x K=8) into TMEM columns [0,128);
-//            O_t[128x32] = P V  (16 x K=8) into TMEM columns [128,160), fresh accumulator per tile.
-//   warps 2-5 softmax: one query row per thread. tcgen05.ld of the S row, online max / exp / sum in fp32
-//            registers, P written to shared memory in the swizzled K-major operand layout (tf32), then the
-//            tile's O_t is read back from TMEM and folded into the running output in registers with the usual
-//            exp(m_old - m_new) correction -- no TMEM stores and no rescaling of TMEM accumulators.
+// One CTA = 128 query rows of one (frame, head).  Keys are walked in tiles of AK = 64:
+//   warp 0   TMA producer: Q tile once; per key tile the K tile [64 keys x 32] and the V^T tile
+//            [32 d x 64 keys] (V^T comes straight out of the v_proj GEMM with swapped operands, so both MMA
+//            operands are K-major and use the same SWIZZLE_128B descriptors as the GEMM engine); 3-stage ring.
+//   warp 1   MMA issuer:  S[128x64] = Q K^T  (kind::tf32, 4 x K=8) into one of TWO S buffers in TMEM;
+//            O_t[128x32] = P V  (8 x K=8), fresh accumulator per tile.  S(t+1) is issued before P V(t), so the next
+//            score tile is computed while the softmax warps still work on tile t (software pipeline).
+//   warps 2-5 softmax: one query row per thread. tcgen05.ld of the S row, online max / exp2 / sum in fp32
+//            registers (log2 domain, scale folded), O_(t-1) is read back from TMEM and folded into the running output
+//            in registers with the usual exp(m_old - m_new) correction (that read also proves P V(t-1) finished
+//            with the P buffer), then P is written to shared memory in the swizzled K-major operand layout (tf32)
+//            -- no TMEM stores and no rescaling of TMEM accumulators.
 // The [L,S,heads] score tensor of the reference never exists; HBM traffic is Q, K, V once per CTA row.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -22,8 +24,8 @@ constexpr int AQ = 128;   // queries per CTA
 constexpr int AK = 64;    // keys per tile (64: 81 KB of smem -> 2 CTAs per SM hide the MMA->softmax->MMA latency chain)
 constexpr int P_BYTES = AQ * AK * 4;        // AK/32 k-blocks of [128 rows x 32 keys]
 constexpr int KC = AK / 32;                 // 32-key chunks per tile
-constexpr int KV_STAGES = 2;
-constexpr int TMEM_COLS = 128;              // S: [0,AK)  O_t: [AK,AK+AD), AD <= 64
+constexpr int KV_STAGES = 3;                // S(t+1) reads K(t+1) while P V(t) still reads V(t): three stages keep one load ahead
+constexpr int TMEM_COLS = 256;              // S double-buffered: [0,AK) and [AK,2AK);  O_t: [2AK, 2AK+AD), AD <= 64
 template <int AD>
 struct ACfg {                               // AD = head dimension (32: the reference's 128/4; 64: BASELINE config 4's 256/4)
     static constexpr int DB = AD / 32;                 // 32-float k-blocks of the head dimension
@@ -54,13 +56,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint8_t* sP = sKV + KV_STAGES * (K_BYTES + VT_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;            // [2]
-    uint64_t* kv_empty = bars + 3;           // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_full = bars + 6;
-    uint64_t* o_full = bars + 7;
-    uint64_t* o_free = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* kv_full = bars + 1;            // [KV_STAGES]
+    uint64_t* kv_empty = bars + 4;           // [KV_STAGES]
+    uint64_t* s_full = bars + 7;             // [2]  one per S buffer
+    uint64_t* p_full = bars + 9;
+    uint64_t* o_full = bars + 10;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int head = blockIdx.y, frame = blockIdx.z;
@@ -75,10 +76,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
         }
-        mbar_init(s_full, 1);
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
         mbar_init(p_full, 4);
         mbar_init(o_full, 1);
-        mbar_init(o_free, 4);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -86,7 +87,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AK;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * AK;   // S buffer b at tmem_S + b * AK
 
     if (warp == 0) {
         {   // whole warp runs the loop, the elected lane issues (tc_common.cuh: elect_one)
@@ -117,35 +118,41 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
     } else if (warp == 1) {
         {
+            // Software pipeline: S(t+1) = Q K(t+1)^T is issued BEFORE P V(t), into the other S buffer, so the tensor pipe
+            // works on the next score tile while the softmax warps are still busy with tile t.
             const bool leader = elect_one();
-            constexpr uint32_t idesc_s = umma_idesc(2, AQ, AK);   // 128 x 128
+            constexpr uint32_t idesc_s = umma_idesc(2, AQ, AK);   // 128 x AK
             constexpr uint32_t idesc_o = umma_idesc(2, AQ, AD);   // 128 x AD
             mbar_wait(q_full, 0);
             const uint32_t q_addr = smem_u32(sQ);
             const uint32_t p_addr = smem_u32(sP);
-            for (int t = 0; t < p.num_tiles; ++t) {
+            auto issue_s = [&](int t) {
                 const int s = t % KV_STAGES;
-                const uint32_t ph = (uint32_t)(t / KV_STAGES) & 1u;
-                const uint32_t tp = (uint32_t)t & 1u;
-                mbar_wait(&kv_full[s], ph);
+                mbar_wait(&kv_full[s], (uint32_t)(t / KV_STAGES) & 1u);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(sKV + s * (K_BYTES + VT_BYTES));
-                const uint32_t v_addr = k_addr + K_BYTES;
-                // S = Q K^T   (S columns are free: P(t-1) was published, i.e. S(t-1) fully read)
+                const uint32_t d = tmem_S + (uint32_t)(t & 1) * AK;
                 if (leader) {
 #pragma unroll
                     for (int kb = 0; kb < DB; ++kb)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            mma_tf32(tmem_S, umma_desc_k128(q_addr + kb * (AQ * 128) + k * 32),
+                            mma_tf32(d, umma_desc_k128(q_addr + kb * (AQ * 128) + k * 32),
                                      umma_desc_k128(k_addr + kb * (AK * 128) + k * 32), idesc_s, (kb | k) != 0 ? 1u : 0u);
-                    tc_commit(s_full);
+                    tc_commit(&s_full[t & 1]);
                 }
                 __syncwarp();
-                // O_t = P V
+            };
+            issue_s(0);
+            for (int t = 0; t < p.num_tiles; ++t) {
+                const int s = t % KV_STAGES;
+                const uint32_t tp = (uint32_t)t & 1u;
+                // S buffer (t+1)&1 held tile t-1, whose P was published one iteration ago: free
+                if (t + 1 < p.num_tiles) issue_s(t + 1);
+                // O_t = P V   (P(t) published also means O(t-1) was folded: the O columns are free)
                 mbar_wait(p_full, tp);
-                if (t > 0) mbar_wait(o_free, tp ^ 1u);
                 tc_fence_after();
+                const uint32_t v_addr = smem_u32(sKV + s * (K_BYTES + VT_BYTES)) + K_BYTES;
                 if (leader) {
 #pragma unroll
                     for (int c = 0; c < KC; ++c)
@@ -171,50 +178,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         uint8_t* prow = sP + r * 128;                // row r of each [128 x 32] k-block (128-byte rows)
         const int sw = r & 7;                        // SWIZZLE_128B: 16-byte chunk index ^= (row & 7)
-        for (int t = 0; t < p.num_tiles; ++t) {
-            const uint32_t tp = (uint32_t)t & 1u;
-            const int valid = (int)((p.S - (int64_t)t * AK) < AK ? (p.S - (int64_t)t * AK) : AK);
-            mbar_wait(s_full, tp);
-            tc_fence_after();
-            float sv[AK];
-            float tmax = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < KC; ++c) {
-                uint32_t raw[32];
-                tmem_ld32(tmem_S + lane_off + c * 32, raw);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float x = (c * 32 + j < valid) ? __uint_as_float(raw[j]) * p.scale : -INFINITY;
-                    sv[c * 32 + j] = x;
-                    tmax = fmaxf(tmax, x);
-                }
-            }
-            const float mnew = fmaxf(mrun, tmax);
-            const float corr = expf(mrun - mnew);
-            float psum = 0.0f;
-#pragma unroll
-            for (int c = 0; c < KC; ++c) {
-                uint8_t* blk = prow + c * (AQ * 32 * 4);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 pv;
-                    pv.x = expf(sv[c * 32 + j] - mnew);
-                    pv.y = expf(sv[c * 32 + j + 1] - mnew);
-                    pv.z = expf(sv[c * 32 + j + 2] - mnew);
-                    pv.w = expf(sv[c * 32 + j + 3] - mnew);
-                    psum += (pv.x + pv.y) + (pv.z + pv.w);
-                    *reinterpret_cast<float4*>(blk + ((((j >> 2) ^ sw) & 7) << 4)) = pv;
-                }
-            }
-            lrun = lrun * corr + psum;
-            mrun = mnew;
-            tc_fence_before();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-            // fold O_t into the running output
-            mbar_wait(o_full, tp);
+        // scores are kept in the log2 domain: x = S * scale * log2(e), p = exp2(x - m)  (one FMUL + one MUFU per score)
+        const float scale2 = p.scale * 1.4426950408889634f;
+        float corr_prev = 1.0f;
+        auto fold_o = [&](int t, float corr) {   // o = o * corr + O_t, then hand the O columns (and the P buffer) back
+            mbar_wait(o_full, (uint32_t)t & 1u);
             tc_fence_after();
 #pragma unroll
             for (int db = 0; db < DB; ++db) {
@@ -225,16 +193,62 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 for (int d = 0; d < 32; ++d) o[db * 32 + d] = fmaf(o[db * 32 + d], corr, __uint_as_float(raw[d]));
             }
             tc_fence_before();
+        };
+        for (int t = 0; t < p.num_tiles; ++t) {
+            const int valid = (int)((p.S - (int64_t)t * AK) < AK ? (p.S - (int64_t)t * AK) : AK);
+            mbar_wait(&s_full[t & 1], (uint32_t)(t >> 1) & 1u);
+            tc_fence_after();
+            uint32_t raw[KC][32];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) tmem_ld32(tmem_S + (uint32_t)(t & 1) * AK + lane_off + c * 32, raw[c]);
+            tmem_ld_wait();
+            float tmax = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < KC; ++c)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float x = (c * 32 + j < valid) ? __uint_as_float(raw[c][j]) * scale2 : -INFINITY;
+                    raw[c][j] = __float_as_uint(x);
+                    tmax = fmaxf(tmax, x);
+                }
+            const float mnew = fmaxf(mrun, tmax);
+            const float corr = exp2f(mrun - mnew);
+            float psum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < KC; ++c)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float e = exp2f(__uint_as_float(raw[c][j]) - mnew);
+                    raw[c][j] = __float_as_uint(e);
+                    psum += e;
+                }
+            // the P buffer is still the A operand of P V(t-1): fold O(t-1) (its completion) before overwriting it
+            if (t > 0) fold_o(t - 1, corr_prev);
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                uint8_t* blk = prow + c * (AQ * 32 * 4);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(blk + ((((j >> 2) ^ sw) & 7) << 4)) =
+                        make_float4(__uint_as_float(raw[c][j]), __uint_as_float(raw[c][j + 1]), __uint_as_float(raw[c][j + 2]),
+                                    __uint_as_float(raw[c][j + 3]));
+            }
+            lrun = lrun * corr + psum;
+            mrun = mnew;
+            corr_prev = corr;
+            tc_fence_before();
+            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(o_free);
+            if (lane == 0) mbar_arrive(p_full);
         }
+        fold_o(p.num_tiles - 1, corr_prev);
         if (row_ok) {
             const float inv = 1.0f / lrun;
             float* op = p.out + ((int64_t)frame * p.L + q0 + r) * ((int64_t)p.heads * AD) + head * AD;
 #pragma unroll
             for (int d = 0; d < AD; d += 4)
                 *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
-            if (p.lse) p.lse[((int64_t)frame * p.L + q0 + r) * p.heads + head] = mrun + logf(lrun);
+            if (p.lse) p.lse[((int64_t)frame * p.L + q0 + r) * p.heads + head] = (mrun + log2f(lrun)) * 0.6931471805599453f;
         }
     }
     __syncthreads();
