@@ -51,18 +51,22 @@ namespace x3 {
 
 constexpr int TM = 128, TK = 32, A_BYTES = TM * TK * 4;
 constexpr int CONV_TW = 64, CONV_TH = 2;
-constexpr int NSA = 4;        // shared-memory A stages (raw fp32 tiles)
 constexpr int NT = 4;         // TMEM A slots
 constexpr int A_COL0 = 256;   // first TMEM column of the A slots
 constexpr int EPI_WARPS = 8, SPLIT_WARPS = 8;
 constexpr int THREADS = 32 * (2 + EPI_WARPS + SPLIT_WARPS);
-constexpr int STAGE_PER_WARP = 5120;  // 4096 B swizzled TMA-store box, or a [32][36] fp32 transposing area (4608 B)
+constexpr int STAGE_PER_WARP = 8192;  // two 4096 B swizzled TMA-store boxes (alternating), or one [32][36] fp32 transposing area
 
 template <int BN>
 struct Cfg {
     static constexpr int B_PLANE = BN * TK * 4;
     static constexpr int B_STAGE = 2 * B_PLANE;  // hi tile + lo tile
     static constexpr int NSB = BN == 128 ? 3 : (BN == 64 ? 4 : 6);
+    // shared-memory A stages (raw fp32 tiles; a stage is free again as soon as the splitters have read it, the TMEM slots
+    // buffer the rest).  MUST be even: the two splitter sets alternate over the k-blocks, and a set that saw only every
+    // other phase of a barrier could not tell a completed phase from the one two before it (mbarrier parity).
+    static constexpr int NSA = BN == 128 ? 2 : 4;
+    static_assert(NSA % 2 == 0 && NT % 2 == 0, "splitter sets own the even / odd slots");
     static constexpr int OFF_B = NSA * A_BYTES;
     static constexpr int OFF_STG = OFF_B + NSB * B_STAGE;
     static constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STAGE_PER_WARP;
@@ -158,7 +162,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-    uint64_t* a_full = bars;              // [NSA]  TMA -> splitters
+    uint64_t* a_full = bars;              // [NSA <= 4]  TMA -> splitters
     uint64_t* a_empty = bars + 4;         // [NSA]  splitters -> TMA
     uint64_t* b_full = bars + 8;          // [NSB<=6] TMA -> MMA
     uint64_t* b_empty = bars + 14;        // [NSB]  MMA commit -> TMA
@@ -182,7 +186,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < NSA; ++s) {
+        for (int s = 0; s < C::NSA; ++s) {
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 4);
         }
@@ -215,8 +219,8 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const Tile tl = decode<CONV>(p, (int)blockIdx.x + i * (int)gridDim.x);
                 const int n0 = tl.n0 * BN;
                 for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
-                    const uint32_t sa = g % NSA, sb = g % C::NSB;
-                    X3_WAIT(&a_empty[sa], ((g / NSA) & 1u) ^ 1u, 0);
+                    const uint32_t sa = g % C::NSA, sb = g % C::NSB;
+                    X3_WAIT(&a_empty[sa], ((g / C::NSA) & 1u) ^ 1u, 0);
                     uint8_t* a_dst = smem + sa * A_BYTES;
                     int kcol;
                     if (CONV) {
@@ -294,8 +298,9 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool has_ln = ep.ln_gamma != nullptr;  // host guarantees n_tiles == 1 and N <= BN
         const bool ln_idle = has_ln && set != 0;     // a fused LayerNorm needs the whole row in one thread
         const bool tma_st = !CONV && p.tma_store != 0;
-        float* stage = reinterpret_cast<float*>(smem + C::OFF_STG + (warp - 2) * STAGE_PER_WARP);
-        bool store_pending = false;
+        float* stage_base = reinterpret_cast<float*>(smem + C::OFF_STG + (warp - 2) * STAGE_PER_WARP);
+        int tbuf = 0;            // TMA-store path: the two staging boxes alternate, so a chunk never waits for the previous store
+        int stores_pending = 0;
         for (int i = 0; i < my_tiles; ++i) {
             const Tile tl = decode<CONV>(p, (int)blockIdx.x + i * (int)gridDim.x);
             const int n0 = tl.n0 * BN;
@@ -368,9 +373,10 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld32(tacc + (uint32_t)c0, acc);
                 tmem_ld_wait();
                 const int nb = n0 + c0;
-                if (tma_st && store_pending) {  // the bulk store issued from this warp's staging box must have read it
-                    if (lane == 0) bulk_wait_read<0>();
-                    store_pending = false;
+                float* stage = stage_base + (tma_st ? tbuf * 1024 : 0);
+                if (tma_st && stores_pending >= 2) {  // the store issued from THIS box two chunks ago must have read it
+                    if (lane == 0) bulk_wait_read<1>();
+                    stores_pending = 1;
                 }
                 __syncwarp();
                 if (row_ok && nb < p.N) {
@@ -474,11 +480,12 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     s_col[(q * BN + c0 + lane) * 2 + 1] = cq;
                 }
                 if (tma_st) {
-                    if (nb < p.N && lane == 0) {
-                        tma_store_2d(&tmC, stage, nb, (int)tl.m0 + q * 32);
+                    if (lane == 0) {   // an empty group when the chunk lies past N keeps the per-thread group count in step
+                        if (nb < p.N) tma_store_2d(&tmC, stage, nb, (int)tl.m0 + q * 32);
                         bulk_commit();
                     }
-                    store_pending = true;
+                    ++stores_pending;
+                    tbuf ^= 1;
                 } else if (nb < p.N) {
                     const bool full = nb + 32 <= p.N;
                     const int cc = (lane & 7) * 4;
@@ -527,7 +534,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 o[1] = cq;
             }
         }
-        if (tma_st && store_pending) {  // shared memory must outlive the reads of the last stores
+        if (tma_st && stores_pending) {  // shared memory must outlive the reads of the last stores
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
         }
@@ -539,8 +546,8 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t total_kb = (uint32_t)my_tiles * (uint32_t)p.num_kb;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         for (uint32_t g = (uint32_t)sset; g < total_kb; g += 2) {
-            const uint32_t sa = g % NSA, st = g % NT;
-            X3_WAIT(&a_full[sa], (g / NSA) & 1u, 0);
+            const uint32_t sa = g % C::NSA, st = g % NT;
+            X3_WAIT(&a_full[sa], (g / C::NSA) & 1u, 0);
             const uint4* row = reinterpret_cast<const uint4*>(smem + sa * A_BYTES + r * 128);
             uint4 x[8];
 #pragma unroll
