@@ -197,7 +197,11 @@ struct Cfg {
     static_assert(!LIGHT || (X3 && BN <= 64), "LIGHT is the short-K 3xTF32 configuration");
 };
 
-template <int BN, bool CONV, bool X3, bool HALF = false, bool LIGHT = false>
+// LEAN: epilogue variant without fused LayerNorm, residual, accumulate and sigmoid (row divisor, bias / per-channel affine,
+// relu / leaky-relu and the column statistics stay): the generic epilogue carries every option as a not-taken branch, about
+// 2000 SASS instructions per 32-column chunk, and the instruction fetch of that sparse walk is what the short contractions
+// paid for (csrc/gemm_x3.cu, PLAIN: 30.9 -> 21.8 us on 163840 x 128 x 32).
+template <int BN, bool CONV, bool X3, bool HALF = false, bool LIGHT = false, bool LEAN = false>
 __global__ void __launch_bounds__(Cfg<BN, X3, LIGHT>::THREADS, Cfg<BN, X3, LIGHT>::MIN_CTAS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const Params p) {
@@ -352,7 +356,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             row_ok = grow < p.M;
         }
         const Epilogue& ep = p.ep;
-        const bool has_rd = ep.rowdiv != nullptr, has_res = ep.residual != nullptr, has_acc = ep.accumulate != 0;
+        const bool has_rd = ep.rowdiv != nullptr, has_res = !LEAN && ep.residual != nullptr, has_acc = !LEAN && ep.accumulate != 0;
         const float rd = (has_rd && row_ok) ? __ldg(ep.rowdiv + grow) : 1.0f;
         float* crow = p.C + grow * p.ldc;
         const float* rrow = has_res ? ep.residual + grow * ep.ldres : nullptr;
@@ -363,9 +367,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool tma_st = !CONV && p.tma_store != 0;
         int tbuf = 0;
         const bool rvec_ok = has_res && ((ep.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
-        const bool has_ln = ep.ln_gamma != nullptr;  // host guarantees gridDim.y == 1 and N <= BN
+        const bool has_ln = !LEAN && ep.ln_gamma != nullptr;  // host guarantees gridDim.y == 1 and N <= BN
         float ln_mean = 0.0f, ln_rstd = 1.0f;
         const bool ln_idle = has_ln && set != 0;  // a fused LayerNorm needs the whole row in one thread: set 0 does it alone
+        if constexpr (!LEAN)
         if (has_ln && !ln_idle) {
             float sum = 0.0f;
 #pragma unroll 1
@@ -471,7 +476,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else if (ep.act == COFI_ACT_LRELU01) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * 0.1f;
-                } else if (ep.act == COFI_ACT_SIGMOID) {
+                } else if (!LEAN && ep.act == COFI_ACT_SIGMOID) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
                 }
@@ -496,13 +501,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // per-tile column statistics for the GroupNorm that follows (host guarantees M % 128 == 0, act none):
                 // lane = column, 32 conflict-free shared loads over this warp's 32 staged rows
                 float cs = 0.0f, cq = 0.0f;
-                if (nb + lane < p.N) {
-#pragma unroll 8
+                if (nb + lane < p.N) {   // four independent partial sums: loads back to back, chains 8 long
+                    float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
                     for (int rr = 0; rr < 32; ++rr) {
                         const float x = tma_st ? tb[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))] : stage[rr * 36 + lane];
-                        cs += x;
-                        cq = fmaf(x, x, cq);
+                        s4[rr & 3] += x;
+                        q4[rr & 3] = fmaf(x, x, q4[rr & 3]);
                     }
+                    cs = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                    cq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
                 }
                 s_col[(q * BN + c0 + lane) * 2 + 0] = cs;
                 s_col[(q * BN + c0 + lane) * 2 + 1] = cq;
@@ -608,16 +616,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-template <int BN, bool CONV, bool X3, bool HALF = false, bool LIGHT = false>
-static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p_in, dim3 grid,
-                      cudaStream_t st) {
+template <int BN, bool CONV, bool X3, bool HALF, bool LIGHT, bool LEAN>
+static int launch_one_v(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p_in, dim3 grid,
+                        cudaStream_t st) {
     Params p = p_in;
     p.tma_store = (c != nullptr && !CONV) ? 1 : 0;
     if (!c) c = a;  // placeholder, never dereferenced by the kernel
     using C = Cfg<BN, X3, LIGHT>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, X3, HALF, LIGHT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, X3, HALF, LIGHT, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::SMEM);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(smem=%d): %s", C::SMEM, cudaGetErrorString(e));
@@ -625,8 +633,17 @@ static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensor
         }
         attr_done = true;
     }
-    gemm_tc_kernel<BN, CONV, X3, HALF, LIGHT><<<grid, C::THREADS, C::SMEM, st>>>(*a, *b, *c, p);
+    gemm_tc_kernel<BN, CONV, X3, HALF, LIGHT, LEAN><<<grid, C::THREADS, C::SMEM, st>>>(*a, *b, *c, p);
     return check_launch(CONV ? "cofi_conv2d_nhwc(tcgen05)" : "cofi_gemm(tcgen05)");
+}
+
+template <int BN, bool CONV, bool X3, bool HALF = false, bool LIGHT = false>
+static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p, dim3 grid,
+                      cudaStream_t st) {
+    const Epilogue& ep = p.ep;
+    const bool lean = !ep.residual && !ep.accumulate && !ep.ln_gamma && ep.act != COFI_ACT_SIGMOID;
+    if (lean) return launch_one_v<BN, CONV, X3, HALF, LIGHT, true>(a, b, c, p, grid, st);
+    return launch_one_v<BN, CONV, X3, HALF, LIGHT, false>(a, b, c, p, grid, st);
 }
 
 constexpr int X3_LIGHT_MAX_KB = 8;  // K <= 256

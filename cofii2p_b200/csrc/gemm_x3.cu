@@ -71,7 +71,7 @@ struct Cfg {
     static constexpr int OFF_STG = OFF_B + NSB * B_STAGE;
     static constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STAGE_PER_WARP;
     static constexpr int OFF_VEC = OFF_BAR + 512;
-    static constexpr int SMEM = OFF_VEC + 12 * BN * 4 + 1024 /* alignment slack */;
+    static constexpr int SMEM = OFF_VEC + 20 * BN * 4 + 1024 /* alignment slack */;   // 4 epilogue vectors + 2 x [4][BN][2] statistics
 };
 
 struct Params {
@@ -86,6 +86,8 @@ struct Params {
     int tma_store;
     float* stat_out;
     unsigned long long* prof;  // COFI_X3_PROFILE: per-role barrier wait clocks (see cofi_debug_x3_profile)
+    int dbg;                   // COFI_X3_DEBUG bits (perf triage only, results become wrong): 1 no column statistics, 2 no stores,
+                               // 4 no proxy fence, 8 no epilogue math, 16 no per-tile epilogue barriers
 };
 
 // wait with optional accounting (perf triage only): slot = which wait of which role
@@ -154,7 +156,10 @@ __device__ __forceinline__ Tile decode(const Params& p, int t) {
     return tl;
 }
 
-template <int BN, bool CONV>
+// PLAIN: the epilogue variant without row divisor, fused LayerNorm, accumulate and sigmoid -- what 60 of the 70
+// point-branch contractions and every convolution use.  The generic epilogue carries every option as a (not taken) branch: 2100 SASS instructions
+// per 32-column chunk against ~350 here, and the chunk loop is what the K <= 128 contractions spend their time in.
+template <int BN, bool CONV, bool PLAIN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const Params p) {
@@ -175,7 +180,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s_shift = s_scale + BN;
     float* s_gamma = s_shift + BN;
     float* s_beta = s_gamma + BN;
-    float* s_col = s_beta + BN;  // [4 quarters][BN][2]
+    float* s_col_base = s_beta + BN;  // [2 tile parities][4 quarters][BN][2]
 
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     unsigned long long pacc[3] = {0ull, 0ull, 0ull};
@@ -292,35 +297,42 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int et = threadIdx.x - 64;
         const Epilogue& ep = p.ep;
-        const bool has_rd = ep.rowdiv != nullptr, has_res = ep.residual != nullptr, has_acc = ep.accumulate != 0;
+        const bool has_rd = !PLAIN && ep.rowdiv != nullptr, has_res = ep.residual != nullptr, has_acc = !PLAIN && ep.accumulate != 0;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         const bool rvec_ok = has_res && ((ep.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
-        const bool has_ln = ep.ln_gamma != nullptr;  // host guarantees n_tiles == 1 and N <= BN
+        const bool has_ln = !PLAIN && ep.ln_gamma != nullptr;  // host guarantees n_tiles == 1 and N <= BN
         const bool ln_idle = has_ln && set != 0;     // a fused LayerNorm needs the whole row in one thread
         const bool tma_st = !CONV && p.tma_store != 0;
         float* stage_base = reinterpret_cast<float*>(smem + C::OFF_STG + (warp - 2) * STAGE_PER_WARP);
         int tbuf = 0;            // TMA-store path: the two staging boxes alternate, so a chunk never waits for the previous store
         int stores_pending = 0;
+        const bool restage = p.n_tiles > 1;
         for (int i = 0; i < my_tiles; ++i) {
             const Tile tl = decode<CONV>(p, (int)blockIdx.x + i * (int)gridDim.x);
             const int n0 = tl.n0 * BN;
             const uint32_t buf = (uint32_t)i & 1u;
-            if (et < BN) {  // per-column epilogue vectors of this tile
-                const int n = n0 + et;
-                float sc = 1.0f, sh = 0.0f;
-                if (n < p.N) {
-                    if (ep.colscale) {
-                        sc = __ldg(ep.colscale + n);
-                        sh = __ldg(ep.colshift + n);
+            // The per-column vectors only change with the column tile: one staging (and one barrier) for the whole kernel when
+            // there is a single column tile.  The column statistics alternate between two buffers, so the reduction of tile i
+            // (after the barrier at its end) never meets the writes of tile i + 1.
+            float* s_col = s_col_base + (i & 1) * (8 * BN);
+            if (i == 0 || restage) {
+                if (et < BN) {  // per-column epilogue vectors of this tile
+                    const int n = n0 + et;
+                    float sc = 1.0f, sh = 0.0f;
+                    if (n < p.N) {
+                        if (ep.colscale) {
+                            sc = __ldg(ep.colscale + n);
+                            sh = __ldg(ep.colshift + n);
+                        }
+                        if (ep.bias) sh += __ldg(ep.bias + n);
                     }
-                    if (ep.bias) sh += __ldg(ep.bias + n);
+                    s_scale[et] = sc;
+                    s_shift[et] = sh;
+                    s_gamma[et] = (has_ln && n < p.N) ? __ldg(ep.ln_gamma + n) : 0.0f;
+                    s_beta[et] = (has_ln && n < p.N) ? __ldg(ep.ln_beta + n) : 0.0f;
                 }
-                s_scale[et] = sc;
-                s_shift[et] = sh;
-                s_gamma[et] = (has_ln && n < p.N) ? __ldg(ep.ln_gamma + n) : 0.0f;
-                s_beta[et] = (has_ln && n < p.N) ? __ldg(ep.ln_beta + n) : 0.0f;
+                if (!(p.dbg & 16)) epi_bar();
             }
-            epi_bar();
             X3_WAIT(&acc_full[buf], ((uint32_t)i >> 1) & 1u, 0);
             tc_fence_after();
             const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
@@ -339,6 +351,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* crow = p.C + grow * p.ldc;
             const float* rrow = has_res ? ep.residual + grow * ep.ldres : nullptr;
             float ln_mean = 0.0f, ln_rstd = 1.0f;
+            if constexpr (!PLAIN)
             if (has_ln && !ln_idle) {
                 float sum = 0.0f;
 #pragma unroll 1
@@ -379,14 +392,16 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     stores_pending = 1;
                 }
                 __syncwarp();
-                if (row_ok && nb < p.N) {
+                if (row_ok && nb < p.N && !(p.dbg & 8)) {
                     const bool full = nb + 32 <= p.N;
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                    if (has_rd) {
+                    if constexpr (!PLAIN) {
+                        if (has_rd) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] / rd;
+                            for (int j = 0; j < 32; ++j) v[j] = v[j] / rd;
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -445,7 +460,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else if (ep.act == COFI_ACT_LRELU01) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * 0.1f;
-                    } else if (ep.act == COFI_ACT_SIGMOID) {
+                    } else if (!PLAIN && ep.act == COFI_ACT_SIGMOID) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
                     }
@@ -463,30 +478,36 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             *reinterpret_cast<float4*>(st + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
                 }
-                if (tma_st) fence_proxy_async_smem();
+                if (tma_st && !(p.dbg & 4)) fence_proxy_async_smem();
                 __syncwarp();
-                if (p.stat_out) {
-                    // per-tile column statistics (host guarantees M % 128 == 0, act none): lane = column
-                    float cs = 0.0f, cq = 0.0f;
-                    if (nb + lane < p.N) {
-#pragma unroll 8
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const float x = tma_st ? stage[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))] : stage[rr * 36 + lane];
-                            cs += x;
-                            cq = fmaf(x, x, cq);
-                        }
-                    }
-                    s_col[(q * BN + c0 + lane) * 2 + 0] = cs;
-                    s_col[(q * BN + c0 + lane) * 2 + 1] = cq;
-                }
-                if (tma_st) {
+                if (tma_st) {   // the bulk store goes first: it reads the staged box while the statistics below read it too
                     if (lane == 0) {   // an empty group when the chunk lies past N keeps the per-thread group count in step
-                        if (nb < p.N) tma_store_2d(&tmC, stage, nb, (int)tl.m0 + q * 32);
+                        if (nb < p.N && !(p.dbg & 2)) tma_store_2d(&tmC, stage, nb, (int)tl.m0 + q * 32);
                         bulk_commit();
                     }
                     ++stores_pending;
                     tbuf ^= 1;
-                } else if (nb < p.N) {
+                }
+                if (p.stat_out && !(p.dbg & 1)) {
+                    // per-tile column statistics (host guarantees M % 128 == 0, act none): lane = column
+                    float cs = 0.0f, cq = 0.0f;
+                    if (nb + lane < p.N) {
+                        // four independent partial sums (rows rr = 4i + u): the 32 shared-memory loads are issued back to
+                        // back and the add / fma chains are 8 long instead of 32
+                        float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float x = tma_st ? stage[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))] : stage[rr * 36 + lane];
+                            s4[rr & 3] += x;
+                            q4[rr & 3] = fmaf(x, x, q4[rr & 3]);
+                        }
+                        cs = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                        cq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+                    }
+                    s_col[(q * BN + c0 + lane) * 2 + 0] = cs;
+                    s_col[(q * BN + c0 + lane) * 2 + 1] = cq;
+                }
+                if (!tma_st && nb < p.N) {
                     const bool full = nb + 32 <= p.N;
                     const int cc = (lane & 7) * 4;
                     float* drow = CONV ? nullptr : p.C + (tl.m0 + q * 32 + (lane >> 3)) * p.ldc + nb + cc;
@@ -520,7 +541,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            epi_bar();
+            if ((p.stat_out || restage) && !(p.dbg & 16)) epi_bar();
             if (p.stat_out && et < BN && n0 + et < p.N) {
                 float cs = 0.0f, cq = 0.0f;
 #pragma unroll
@@ -637,16 +658,24 @@ static int num_sms() {
     return n;
 }
 
-template <int BN, bool CONV>
-static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p_in, cudaStream_t st) {
+template <int BN, bool CONV, bool PLAIN>
+static int launch_one_v(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p_in, cudaStream_t st) {
     Params p = p_in;
     p.tma_store = (c != nullptr && !CONV) ? 1 : 0;
     p.prof = prof_buffer();
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("COFI_X3_DEBUG");
+            dbg = e ? atoi(e) : 0;
+        }
+        p.dbg = dbg;
+    }
     if (!c) c = a;
     using C = Cfg<BN>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_x3_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_x3_kernel<BN, CONV, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm_x3, smem=%d): %s", C::SMEM, cudaGetErrorString(e));
             return COFI_ECUDA;
@@ -655,8 +684,16 @@ static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensor
     }
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
-    gemm_x3_kernel<BN, CONV><<<grid, THREADS, C::SMEM, st>>>(*a, *b, *c, p);
+    gemm_x3_kernel<BN, CONV, PLAIN><<<grid, THREADS, C::SMEM, st>>>(*a, *b, *c, p);
     return check_launch(CONV ? "cofi_conv2d_nhwc(3xTF32)" : "cofi_gemm(3xTF32)");
+}
+
+template <int BN, bool CONV>
+static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p, cudaStream_t st) {
+    const Epilogue& ep = p.ep;
+    const bool plain = !ep.rowdiv && !ep.accumulate && !ep.ln_gamma && ep.act != COFI_ACT_SIGMOID;
+    if (plain) return launch_one_v<BN, CONV, true>(a, b, c, p, st);
+    return launch_one_v<BN, CONV, false>(a, b, c, p, st);
 }
 
 // Tile width: the persistent grid runs ceil(tiles / SMs) rounds of one tile each.  Per tile the kernel is bound by the
