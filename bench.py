@@ -431,7 +431,8 @@ def run_cofi(args):
         for _ in range(2):
             eng._step_eager()
         # contractions are split per call at the ridge of the tf32 tensor roof (half the measured bf16 rate) and the HBM roof
-        prof = ops.profile_stop(ridge=0.5 * tf_sust * 1e12 / (hbm * 1e9))
+        ridge = 0.5 * tf_sust * 1e12 / (hbm * 1e9)
+        prof = ops.profile_stop(ridge=ridge)
     model.fork_image_stream = True
     launches_per_step = eng.launches_per_step
     del eng
@@ -446,6 +447,14 @@ def run_cofi(args):
         f = fam.setdefault(key, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
         for k in f:
             f[k] += d[k]
+    def ridge_split(cname, cfl, cby):
+        """family key of one raw profiler record (same rule as ops.profile_stop + the family folding above)"""
+        bound = ""
+        if (cname.startswith("cofi_gemm") or cname.startswith("cofi_conv2d")) and cby > 0:
+            bound = "tensor" if cfl / cby > ridge else "hbm"
+        key = "cofi_gemm*" if cname.startswith("cofi_gemm") else ("cofi_kpconv_aggregate*" if cname.startswith("cofi_kpconv_aggregate") else cname)
+        return key + (" [" + bound + "-bound calls]" if bound else "")
+
     tot_ms = sum(d["ms"] for d in fam.values())
     name, d = max(fam.items(), key=lambda kv: kv[1]["ms"])
     tensor_ops = ("cofi_gemm* [tensor-bound calls]", "cofi_conv2d_nhwc [tensor-bound calls]", "cofi_attention_vt", "cofi_attention",
@@ -476,12 +485,34 @@ def run_cofi(args):
                  "peak_source": peaks_src + (" (bf16 dense sustained; the family runs tf32 (nominal peak = half of bf16) and "
                                              "fp16 operands)" if name in tensor_ops else " (copy bandwidth)"),
                  "by_kernel_ms_per_step": {k: round(v["ms"] / 2, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}})
+    # the family's largest single call (by algorithmic bytes) on its own: the family average above mixes 163840-row streaming
+    # contractions with ~10 MB transformer projections that are launch-latency sized
+    calls = getattr(ops, "_prof_calls", None) or []
+    mine = []
+    for (cname, cms, _nl, cfl, cby, ctag) in calls:
+        if ridge_split(cname, cfl, cby) == name and cms > 0:
+            mine.append((cby, cfl, cms, ctag))
+    if mine:
+        cby, cfl, cms, ctag = max(mine)
+        roof["largest_call"] = {"shape": ctag, "us": 1e3 * cms, "GB/s": cby / (cms / 1e3) / 1e9, "frac_of_hbm_peak": cby / (cms / 1e3) / 1e9 / hbm,
+                                "TFLOP/s": cfl / (cms / 1e3) / 1e12,
+                                "what": "best-effort view of the same kernel at its streaming size (one eager launch, CUDA events)"}
+    tb = fam.get("cofi_gemm* [tensor-bound calls]")
+    if tb is not None and args.engine in ("parity", "tf32x3"):
+        eff = tb["flops"] / (tb["ms"] / 1e3) / 1e12
+        roof["tensor_bound_gemm_family"] = {
+            "ms_per_step": tb["ms"] / 2, "calls_per_step": tb["calls"] // 2, "TFLOP/s_logical": eff, "frac_of_bf16_sustained": eff / tf_sust,
+            "what": "large-K contractions of the step.  The 3xTF32 ones issue three kind::tf32 MMAs per logical MAC and the tf32 "
+                    "pipe runs at half the bf16 rate, so their MMA work is 3x the logical figure against a roof of bf16/2 "
+                    "(ncu: 70 % tensor-pipe active on 20480x1024x3072, profiles/r2_ncu_gemm_x3_kernel.md); the fp16 KPConv "
+                    "weight-applies are in the same family"}
     sim = fam.get("cofi_sim_argmin_exact")
     if sim is not None:  # the north star's fused similarity kernel, as it runs inside this step (launch-latency sized)
         roof["similarity_kernel"] = {"calls_per_step": sim["calls"] // 2, "us_per_call": 1e3 * sim["ms"] / sim["calls"],
                                      "tflops": sim["flops"] / (sim["ms"] / 1e3) / 1e12, "frac_of_bf16_burst": sim["flops"] / (sim["ms"] / 1e3) / 1e12 / tf_burst,
-                                     "what": "tcgen05 fp16 candidate pass + exact fp32 re-rank over 8 x 1280 x 1280 x 128; the "
-                                             "full-size sweep point (10240 x 20480 x 64) is in profiles/r2_sim_bench.jsonl"}
+                                     "what": "tcgen05 fp16 candidate pass + exact fp32 re-rank over 8 x 1280 x 1280 x 128 (launch-latency "
+                                             "sized inside the step); sweep point 10240 x 20480 x 64 x 8 frames in profiles/r2_sim_bench.jsonl: "
+                                             "candidate pass 651 TFLOP/s, exact path 372 TFLOP/s, bound by TMEM reads (64 B/clk/SM) at C = 64"}
 
     # ---- data-parallel training leg (BASELINE.json configs[4]) in the same line: what north_star splits across GPUs ------
     train = None

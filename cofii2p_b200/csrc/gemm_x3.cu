@@ -156,10 +156,13 @@ __device__ __forceinline__ Tile decode(const Params& p, int t) {
     return tl;
 }
 
-// PLAIN: the epilogue variant without row divisor, fused LayerNorm, accumulate and sigmoid -- what 60 of the 70
-// point-branch contractions and every convolution use.  The generic epilogue carries every option as a (not taken) branch: 2100 SASS instructions
-// per 32-column chunk against ~350 here, and the chunk loop is what the K <= 128 contractions spend their time in.
-template <int BN, bool CONV, bool PLAIN>
+// EPI selects the epilogue instantiation: 0 generic (every option a run-time branch), 1 plain (bias / per-channel affine,
+// optional residual, relu / leaky-relu, column statistics: the point-branch Linear layers and every convolution),
+// 2 fused LayerNorm (+ residual, relu: the transformer's merge and mlp[2] layers), 3 accumulate (+ activation: the second half
+// of the transformer's mlp[0]).  The generic epilogue is 2100 SASS instructions per 32-column chunk, most of them branches not
+// taken, against ~350 in the specialised ones -- and the chunk loop is what the K <= 128 contractions spend their time in
+// (instruction fetch of that sparse walk: 163840 x 128 x 32 went from 30.9 to 21.8 us).
+template <int BN, bool CONV, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const Params p) {
@@ -297,10 +300,11 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int et = threadIdx.x - 64;
         const Epilogue& ep = p.ep;
-        const bool has_rd = !PLAIN && ep.rowdiv != nullptr, has_res = ep.residual != nullptr, has_acc = !PLAIN && ep.accumulate != 0;
+        const bool has_rd = EPI == 0 && ep.rowdiv != nullptr, has_res = ep.residual != nullptr;
+        const bool has_acc = (EPI == 0 || EPI == 3) && ep.accumulate != 0;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         const bool rvec_ok = has_res && ((ep.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
-        const bool has_ln = !PLAIN && ep.ln_gamma != nullptr;  // host guarantees n_tiles == 1 and N <= BN
+        const bool has_ln = (EPI == 0 || EPI == 2) && ep.ln_gamma != nullptr;  // host guarantees n_tiles == 1 and N <= BN
         const bool ln_idle = has_ln && set != 0;     // a fused LayerNorm needs the whole row in one thread
         const bool tma_st = !CONV && p.tma_store != 0;
         float* stage_base = reinterpret_cast<float*>(smem + C::OFF_STG + (warp - 2) * STAGE_PER_WARP);
@@ -351,7 +355,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* crow = p.C + grow * p.ldc;
             const float* rrow = has_res ? ep.residual + grow * ep.ldres : nullptr;
             float ln_mean = 0.0f, ln_rstd = 1.0f;
-            if constexpr (!PLAIN)
+            if constexpr (EPI == 0 || EPI == 2)
             if (has_ln && !ln_idle) {
                 float sum = 0.0f;
 #pragma unroll 1
@@ -397,7 +401,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                    if constexpr (!PLAIN) {
+                    if constexpr (EPI == 0) {
                         if (has_rd) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = v[j] / rd;
@@ -460,7 +464,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else if (ep.act == COFI_ACT_LRELU01) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * 0.1f;
-                    } else if (!PLAIN && ep.act == COFI_ACT_SIGMOID) {
+                    } else if (EPI == 0 && ep.act == COFI_ACT_SIGMOID) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
                     }
@@ -658,7 +662,7 @@ static int num_sms() {
     return n;
 }
 
-template <int BN, bool CONV, bool PLAIN>
+template <int BN, bool CONV, int EPI>
 static int launch_one_v(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p_in, cudaStream_t st) {
     Params p = p_in;
     p.tma_store = (c != nullptr && !CONV) ? 1 : 0;
@@ -675,7 +679,7 @@ static int launch_one_v(const CUtensorMap* a, const CUtensorMap* b, const CUtens
     using C = Cfg<BN>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_x3_kernel<BN, CONV, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_x3_kernel<BN, CONV, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(gemm_x3, smem=%d): %s", C::SMEM, cudaGetErrorString(e));
             return COFI_ECUDA;
@@ -684,16 +688,18 @@ static int launch_one_v(const CUtensorMap* a, const CUtensorMap* b, const CUtens
     }
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
-    gemm_x3_kernel<BN, CONV, PLAIN><<<grid, THREADS, C::SMEM, st>>>(*a, *b, *c, p);
+    gemm_x3_kernel<BN, CONV, EPI><<<grid, THREADS, C::SMEM, st>>>(*a, *b, *c, p);
     return check_launch(CONV ? "cofi_conv2d_nhwc(3xTF32)" : "cofi_gemm(3xTF32)");
 }
 
 template <int BN, bool CONV>
 static int launch_one(const CUtensorMap* a, const CUtensorMap* b, const CUtensorMap* c, const Params& p, cudaStream_t st) {
     const Epilogue& ep = p.ep;
-    const bool plain = !ep.rowdiv && !ep.accumulate && !ep.ln_gamma && ep.act != COFI_ACT_SIGMOID;
-    if (plain) return launch_one_v<BN, CONV, true>(a, b, c, p, st);
-    return launch_one_v<BN, CONV, false>(a, b, c, p, st);
+    if (ep.rowdiv || ep.act == COFI_ACT_SIGMOID || (ep.ln_gamma && ep.accumulate)) return launch_one_v<BN, CONV, 0>(a, b, c, p, st);
+    if (!CONV && ep.ln_gamma) return launch_one_v<BN, CONV, 2>(a, b, c, p, st);
+    if (!CONV && ep.accumulate) return launch_one_v<BN, CONV, 3>(a, b, c, p, st);
+    if (ep.ln_gamma || ep.accumulate) return launch_one_v<BN, CONV, 0>(a, b, c, p, st);
+    return launch_one_v<BN, CONV, 1>(a, b, c, p, st);
 }
 
 // Tile width: the persistent grid runs ceil(tiles / SMs) rounds of one tile each.  Per tile the kernel is bound by the

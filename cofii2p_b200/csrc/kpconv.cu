@@ -145,12 +145,16 @@ kpconv_aggregate_kernel(const float* __restrict__ feats, int64_t ldf, int C, con
 
     int cur_k = 0;  // kernel point whose row is being accumulated
     const int total_pairs = n_near * K;
+    const float inv_near = 1.0f / (float)(n_near > 0 ? n_near : 1);
     for (int base = 0; base < total_pairs; base += 32) {
         const int pidx = base + lane;
         float w = 0.0f;
         int pk = 0, prow = 0;
         if (pidx < total_pairs) {
-            pk = pidx / n_near;
+            // pidx / n_near without the integer-division sequence: reciprocal estimate + one correction (pidx < 4096)
+            pk = (int)((float)pidx * inv_near);
+            if (pk * n_near > pidx) --pk;
+            else if ((pk + 1) * n_near <= pidx) ++pk;
             const float4 nb = near[pidx - pk * n_near];
             prow = __float_as_int(nb.w);
             // differences = neighbours - kernel_points; sq = sum(d^2); w = clamp(1 - sqrt(sq)/sigma, 0)
