@@ -435,6 +435,68 @@ gather_rows_kernel(const float* __restrict__ x, int64_t ldx, int C, const int64_
     }
 }
 
+// instruction-lean fp16 variant (see maxpool_rows_fast_kernel): 8 channels (16 bytes) per lane
+template <int LPR>   // lanes per row group: 8 (C = 64), 16 (C = 128), 32 (C a multiple of 256)
+__global__ void __launch_bounds__(128)
+maxpool_rows_f16_fast_kernel(const uint4* __restrict__ x8, int ldx8, int C8, const int64_t* __restrict__ nbr, int H, int64_t Mq,
+                             int64_t Ns, int64_t total_q, float4* __restrict__ out4, int ldo4) {
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= total_q) return;
+    const uint4* xb = x8 + (m / Mq) * Ns * ldx8;
+    int idx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int h = j * 32 + lane;
+        int64_t id = (h < H) ? __ldcs(nbr + m * H + h) : -2;
+        if (id >= Ns) id = -1;
+        idx[j] = (int)id;
+    }
+    const int first = __shfl_sync(0xffffffffu, idx[0], 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (idx[j] == -2) idx[j] = first;
+    constexpr int GROUPS = 32 / LPR;
+    const int grp = lane / LPR, gl = lane - grp * LPR;
+    for (int c8 = gl; c8 < C8; c8 += LPR) {
+        __half2 mx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx[i] = __float2half2_rn(-65504.0f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int l = 0; l < 32; l += 4 * GROUPS) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int id = __shfl_sync(0xffffffffu, idx[j], l + u * GROUPS + grp);
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);   // shadow row = zeros
+                    if (id >= 0) v[u] = __ldg(xb + id * ldx8 + c8);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const __half2* hv = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) mx[i] = __hmax2(mx[i], hv[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned o = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<unsigned*>(&mx[i]), off);
+                mx[i] = __hmax2(mx[i], *reinterpret_cast<const __half2*>(&o));
+            }
+        }
+        if (grp == 0) {
+            const float2 a = __half22float2(mx[0]), b = __half22float2(mx[1]), c = __half22float2(mx[2]), d = __half22float2(mx[3]);
+            out4[m * ldo4 + c8 * 2] = make_float4(a.x, a.y, b.x, b.y);
+            out4[m * ldo4 + c8 * 2 + 1] = make_float4(c.x, c.y, d.x, d.y);
+        }
+    }
+}
+
 }  // namespace cofi
 
 using namespace cofi;
@@ -575,6 +637,18 @@ extern "C" int cofi_maxpool_rows_f16(const void* x_f16, int64_t ldx, int C, cons
     const int64_t total = Mq * frames;
     if (total == 0) return COFI_OK;
     const int wpb = 4;
+    if ((C == 64 || C == 128 || C % 256 == 0) && Ns * ldx < (1ll << 31)) {
+        const uint4* x8 = reinterpret_cast<const uint4*>(x_f16);
+        float4* o4 = reinterpret_cast<float4*>(out);
+        const unsigned blocks = (unsigned)ceil_div(total, wpb);
+        if (C == 64)
+            maxpool_rows_f16_fast_kernel<8><<<blocks, wpb * 32, 0, (cudaStream_t)stream>>>(x8, (int)(ldx / 8), C / 8, nbr, H, Mq, Ns, total, o4, (int)(ldo / 4));
+        else if (C == 128)
+            maxpool_rows_f16_fast_kernel<16><<<blocks, wpb * 32, 0, (cudaStream_t)stream>>>(x8, (int)(ldx / 8), C / 8, nbr, H, Mq, Ns, total, o4, (int)(ldo / 4));
+        else
+            maxpool_rows_f16_fast_kernel<32><<<blocks, wpb * 32, 0, (cudaStream_t)stream>>>(x8, (int)(ldx / 8), C / 8, nbr, H, Mq, Ns, total, o4, (int)(ldo / 4));
+        return check_launch("cofi_maxpool_rows_f16");
+    }
     maxpool_rows_f16_kernel<<<(unsigned)ceil_div(total, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __half*>(x_f16), ldx, C, nbr, H, Mq, Ns, total, out, ldo);
     return check_launch("cofi_maxpool_rows_f16");
