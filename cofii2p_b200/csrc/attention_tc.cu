@@ -202,23 +202,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int c = 0; c < KC; ++c) tmem_ld32(tmem_S + (uint32_t)(t & 1) * AK + lane_off + c * 32, raw[c]);
             tmem_ld_wait();
+            // max on the raw scores (the scale is positive), then p = exp2(raw * scale2 - m) as one FFMA + one MUFU per score;
+            // only the last key tile of a sequence can be partial
             float tmax = -INFINITY;
+            if (valid < AK) {
+#pragma unroll
+                for (int c = 0; c < KC; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c * 32 + j >= valid) raw[c][j] = 0xff800000u;   // -inf
+            }
 #pragma unroll
             for (int c = 0; c < KC; ++c)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float x = (c * 32 + j < valid) ? __uint_as_float(raw[c][j]) * scale2 : -INFINITY;
-                    raw[c][j] = __float_as_uint(x);
-                    tmax = fmaxf(tmax, x);
-                }
-            const float mnew = fmaxf(mrun, tmax);
+                for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(raw[c][j]));
+            const float mnew = fmaxf(mrun, tmax * scale2);
             const float corr = exp2f(mrun - mnew);
             float psum = 0.0f;
 #pragma unroll
             for (int c = 0; c < KC; ++c)
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float e = exp2f(__uint_as_float(raw[c][j]) - mnew);
+                    const float e = exp2f(fmaf(__uint_as_float(raw[c][j]), scale2, -mnew));
                     raw[c][j] = __float_as_uint(e);
                     psum += e;
                 }

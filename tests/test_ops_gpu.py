@@ -110,6 +110,30 @@ def test_maxpool_and_upsample():
     assert torch.equal(got.cpu(), restate.nearest_upsample(xc, up))
 
 
+@pytest.mark.parametrize("c", [64, 128, 256, 512, 96])
+@pytest.mark.parametrize("H", [128, 100, 33])
+def test_maxpool_lean_kernels(c, H):
+    """The instruction-lean max-pool kernels (fp32: C = 64 / multiples of 128; fp16: C = 64, 128, multiples of 256) and the
+    generic fall-back (C = 96) against the oracle: shadow neighbours (a row of zeros must win over negative features), fewer
+    than 128 neighbours, negative-only rows, two stacked frames with frame-local indices."""
+    ops = _ops()
+    from oracle import restate
+    g = torch.Generator().manual_seed(c * 7 + H)
+    frames, ns, nq = 2, 500, 260
+    x = torch.randn((frames * ns, c), generator=g)
+    x[: ns // 3] = -x[: ns // 3].abs() - 0.5
+    nbr = torch.randint(0, ns, (frames * nq, H), generator=g)
+    nbr[::5, -3:] = ns                      # shadow neighbours
+    nbr[1::9, 0] = ns                       # ... also in slot 0 (the slot the kernels replicate past H)
+    want = torch.cat([restate.maxpool(x[f * ns:(f + 1) * ns], nbr[f * nq:(f + 1) * nq]) for f in range(frames)])
+    got = ops.maxpool_rows(x.cuda(), nbr.cuda(), frames)
+    assert torch.equal(got.cpu(), want)
+    if c % 8 == 0:
+        xh = x.cuda().to(torch.float16)
+        want_h = torch.cat([restate.maxpool(xh.float().cpu()[f * ns:(f + 1) * ns], nbr[f * nq:(f + 1) * nq]) for f in range(frames)])
+        assert torch.equal(ops.maxpool_rows_f16(xh, nbr.cuda(), frames).cpu(), want_h)
+
+
 @pytest.mark.parametrize("rows,c,groups,frames", [(1000, 64, 32, 1), (777, 128, 32, 2), (640, 2048, 32, 1),
                                                   (1280, 64, 64, 1)])
 def test_norm_rows(rows, c, groups, frames):
