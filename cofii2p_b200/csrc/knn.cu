@@ -59,7 +59,10 @@ struct SortParams {
     int nsets;
 };
 struct JobDesc {
-    int64_t* out;  // [frames*nq, k]
+    int64_t* out;             // [frames*nq, k]
+    const int64_t* copy_from; // optional: the finished [frames*ns, k] table of the SOURCE set queried by itself.  A query whose
+                              // coordinates equal a source point's has, by definition, that point's row -- the sub-sampled levels
+                              // of the pyramid are subsets of the level above, so the 4 `subsampling` tables are row copies
     int src, qry, block_begin, k;
 };
 struct QueryParams {
@@ -704,6 +707,23 @@ __global__ void __launch_bounds__(QWARPS * 32) knn_query_kernel(const __grid_con
         return;
     }
 
+    // a query that coincides with a source point copies that point's row of the source's own table (see JobDesc::copy_from):
+    // equal coordinates have equal Morton codes, `home` is the first of that run, so the twin sits in the seed tiles
+    if (P.fast && J.copy_from != nullptr) {
+        int twin = -1;
+        for (int t = s0; t < s1 && twin < 0; ++t) {
+            const float4 s = __ldg(ssort + ((size_t)t << 5) + lane);
+            const bool same = __float_as_int(s.w) >= 0 && s.x == qx && s.y == qy && s.z == qz;
+            const unsigned m = __ballot_sync(0xffffffffu, same);
+            if (m) twin = __shfl_sync(0xffffffffu, __float_as_int(s.w), __ffs(m) - 1);
+        }
+        if (twin >= 0) {
+            const int64_t* srow = J.copy_from + ((size_t)frame * ns + twin) * J.k;
+            int64_t* orow = J.out + ((size_t)frame * Q.n + qi) * J.k;
+            for (int e = lane; e < J.k; e += 32) orow[e] = __ldg(srow + e);
+            return;
+        }
+    }
     // threshold selection + one sort (see knn_fast_path); the iterative path below is the general fallback
     if (P.fast) {
         if (knn_fast_path<MODE>(J, S, w.cand, lane, frame, qi, Q.n, qx, qy, qz, qq, r0, r1)) return;
@@ -812,7 +832,7 @@ char* carve_set(SetDesc& S, const float* pts, int64_t n, int frames, char* w) {
     return w;
 }
 
-int run(QueryParams& Q, int nsets, int frames, int mode, cudaStream_t st) {
+int run_sort(QueryParams& Q, int nsets, int frames, cudaStream_t st) {
     static bool attr_done = false;
     const int smem = SORT_CHUNK * 8;
     if (!attr_done) {
@@ -836,8 +856,11 @@ int run(QueryParams& Q, int nsets, int frames, int mode, cudaStream_t st) {
     int rc = check_launch("cofi_knn: chunk sort");
     if (rc) return rc;
     knn_sort_kernel<<<dim3(nsets, frames), SORT_THREADS, smem, st>>>(SP);
-    rc = check_launch("cofi_knn: sort");
-    if (rc) return rc;
+    return check_launch("cofi_knn: sort");
+}
+
+int run_query(QueryParams& Q, int frames, int mode, cudaStream_t st) {
+    if (Q.njobs == 0) return COFI_OK;
     int blocks = 0;
     for (int j = 0; j < Q.njobs; ++j) {
         Q.job[j].block_begin = blocks;
@@ -848,6 +871,12 @@ int run(QueryParams& Q, int nsets, int frames, int mode, cudaStream_t st) {
     else
         knn_query_kernel<COFI_KNN_EXPANDED><<<dim3(blocks, frames), QWARPS * 32, 0, st>>>(Q);
     return check_launch("cofi_knn: query");
+}
+
+int run(QueryParams& Q, int nsets, int frames, int mode, cudaStream_t st) {
+    int rc = run_sort(Q, nsets, frames, st);
+    if (rc) return rc;
+    return run_query(Q, frames, mode, st);
 }
 
 }  // namespace
@@ -879,24 +908,36 @@ extern "C" int cofi_knn_pyramid(const float* const* points, const int64_t* n_per
     Q.njobs = 0;
     Q.cull = (mode & COFI_KNN_NOCULL) ? 0 : 1;
     Q.fast = (mode & (COFI_KNN_NOCULL | COFI_KNN_NOFAST)) ? 0 : 1;
-    auto add = [&](int src, int qry, int64_t* out, int kk) {
+    // Two query launches.  First: the same-level tables and the up-sampling tables.  Second: the sub-sampling tables, whose
+    // queries (level l+1) are points of level l in every pyramid built by half-sampling -- they copy rows of the finished
+    // `neighbors[l]` (a query without a twin in level l is searched as before, so arbitrary pyramids stay correct).
+    QueryParams Q2 = Q;
+    auto add = [&](QueryParams& T, int src, int qry, int64_t* out, int kk, const int64_t* copy_from) {
         if (!out) return;
-        JobDesc& J = Q.job[Q.njobs++];
+        JobDesc& J = T.job[T.njobs++];
         J.src = src;
         J.qry = qry;
         J.out = out;
+        J.copy_from = copy_from;
         J.block_begin = 0;
         J.k = kk;
     };
     for (int l = 0; l < levels; ++l) {
-        if (neighbors) add(l, l, neighbors[l], k);
+        if (neighbors) add(Q, l, l, neighbors[l], k, nullptr);
         if (l + 1 < levels) {
-            if (subsampling) add(l, l + 1, subsampling[l], k);  // level l+1 points look up level l
-            if (upsampling) add(l + 1, l, upsampling[l], k_up);  // level l points look up level l+1
+            if (upsampling) add(Q, l + 1, l, upsampling[l], k_up, nullptr);  // level l points look up level l+1
+            if (subsampling) {                                                // level l+1 points look up level l
+                const bool can_copy = Q.fast && neighbors && neighbors[l];
+                add(can_copy ? Q2 : Q, l, l + 1, subsampling[l], k, can_copy ? neighbors[l] : nullptr);
+            }
         }
     }
-    if (Q.njobs == 0) return COFI_OK;
-    return run(Q, levels, frames, mode, (cudaStream_t)stream);
+    if (Q.njobs == 0 && Q2.njobs == 0) return COFI_OK;
+    int rc = run_sort(Q, levels, frames, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = run_query(Q, frames, mode, (cudaStream_t)stream);
+    if (rc) return rc;
+    return run_query(Q2, frames, mode, (cudaStream_t)stream);
 }
 
 extern "C" int64_t cofi_knn_table_workspace(int64_t ns, int64_t nq, int frames) {
@@ -921,6 +962,7 @@ extern "C" int cofi_knn_table(const float* src, int64_t ns, const float* qry, in
     Q.job[0].src = 0;
     Q.job[0].qry = same ? 0 : 1;
     Q.job[0].out = out;
+    Q.job[0].copy_from = nullptr;
     Q.job[0].block_begin = 0;
     Q.job[0].k = k;
     return run(Q, same ? 1 : 2, frames, mode, (cudaStream_t)stream);

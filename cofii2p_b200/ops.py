@@ -744,7 +744,7 @@ KNN_NOFAST = 0x200   # test/debug: iterative sort/merge selection for every quer
 
 def knn_pyramid(points, frames: int = 1, k: int = 128, mode: int = KNN_DIRECT, want=("neighbors", "subsampling", "upsampling"),
                 workspace: Optional[torch.Tensor] = None, k_up: Optional[int] = None, out: Optional[dict] = None):
-    """All KNN-k tables of a point pyramid in two launches (reference model/kpconv/preprocess_data.py:75-99,172-190).
+    """All KNN-k tables of a point pyramid in four launches (two sorts, two query passes; reference model/kpconv/preprocess_data.py:75-99,172-190).
     points: list of [frames*n_l, 3] fp32 CUDA tensors -> dict(neighbors, subsampling, upsampling) of int64 tables with
     frame-local indices, rows ascending in (distance, index).  k_up: columns of the upsampling tables (default k; the
     model only reads column 0, reference model/kpconv/functional.py:20, so the engine asks for 1)."""

@@ -123,8 +123,10 @@ int cofi_gather_rows(const float* x, int64_t ldx, int C, const int64_t* idx, int
 int cofi_half_sample_pyramid(const float* pts0, int64_t n0, int frames, int levels, uint64_t seed,
                              float* const* out_levels, int64_t* const* out_index, void* stream);
 
-/* Exact k-nearest-neighbour tables of a whole point pyramid, all frames and all tables in two launches
- * (Morton sort + warp-per-query search).  Replaces the 13 KNNSearch / knn() calls of
+/* Exact k-nearest-neighbour tables of a whole point pyramid, all frames and all tables in four launches
+ * (Morton sort in two steps, then two warp-per-query passes: the same-level and up-sampling tables first, then the sub-sampling
+ * tables, whose queries copy the row of their twin in the finished same-level table when they coincide with a source point --
+ * always the case in a pyramid built by sub-sampling -- and are searched otherwise).  Replaces the 13 KNNSearch / knn() calls of
  * model/kpconv/preprocess_data.py:75-99 (stack mode) and :172-190 (cuda mode).
  *   points[l]       device [frames*n[l], 3] fp32           (host array of `levels` device pointers)
  *   neighbors[l]    device [frames*n[l],   k] int64: level l   looks up level l     (levels entries)
