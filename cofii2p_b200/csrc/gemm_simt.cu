@@ -285,21 +285,34 @@ extern "C" int cofi_gemm_f16(const void* A, int64_t lda, const void* W, int64_t 
 
 // GEMM whose epilogue also emits per-128-row-tile column statistics (sum, sum of squares) of the stored output, so the
 // GroupNorm that follows (cofi_norm_rows_pre) skips its statistics pass.  tensor-core engines only; M % 128 == 0.
-extern "C" int cofi_gemm_colstats(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
-                                  int64_t M, int N, int K, const float* bias, const float* rowdiv, int engine,
-                                  float* stats /* [M/128, N, 2] */, void* stream) {
+static int gemm_colstats_impl(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+                              int64_t M, int N, int K, const float* bias, const float* rowdiv, int accumulate, int engine,
+                              float* stats /* [M/128, N, 2] */, void* stream) {
     COFI_REQUIRE(A && W && C && stats, "cofi_gemm_colstats: null pointer");
     COFI_REQUIRE(M > 0 && M % 128 == 0 && N >= 16 && K > 0, "cofi_gemm_colstats: M must be a positive multiple of 128, N >= 16");
     COFI_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && lda >= K && ldw >= K && ldc >= N, "cofi_gemm_colstats: bad leading dimension");
     COFI_REQUIRE(engine == COFI_GEMM_TF32 || engine == COFI_GEMM_TF32X3 || engine == COFI_GEMM_TF32X3S,
                  "cofi_gemm_colstats: tensor-core engines only");
     COFI_REQUIRE(gemm_tc_supported(lda, ldw, ldc, M, N, K, A, W, C), "cofi_gemm_colstats: shape/alignment unsupported");
-    Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, 0, COFI_ACT_NONE, nullptr, nullptr, 0.0f};
+    Epilogue ep{bias, rowdiv, nullptr, nullptr, nullptr, 0, accumulate, COFI_ACT_NONE, nullptr, nullptr, 0.0f};
     if (engine == COFI_GEMM_TF32X3S) {
         COFI_REQUIRE(ldw == K, "cofi_gemm_colstats: COFI_GEMM_TF32X3S needs W = cofi_split_tf32 output (ldw == K)");
         return gemm_x3_launch(A, lda, W, C, ldc, M, N, K, ep, (cudaStream_t)stream, stats);
     }
     return gemm_tc_launch(A, lda, W, ldw, C, ldc, M, N, K, ep, engine, (cudaStream_t)stream, stats);
+}
+
+extern "C" int cofi_gemm_colstats(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+                                  int64_t M, int N, int K, const float* bias, const float* rowdiv, int engine,
+                                  float* stats /* [M/128, N, 2] */, void* stream) {
+    return gemm_colstats_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, rowdiv, 0, engine, stats, stream);
+}
+
+// C += A W^T + bias (C is read and rewritten), statistics of the stored sum: the second half of a Linear over a concatenated
+// input whose first half was evaluated elsewhere (the decoder: W [up(x_c) | x_f] = up(W_c x_c) + W_f x_f)
+extern "C" int cofi_gemm_colstats_acc(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+                                      int64_t M, int N, int K, const float* bias, int engine, float* stats, void* stream) {
+    return gemm_colstats_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, nullptr, 1, engine, stats, stream);
 }
 
 extern "C" int cofi_gemm_f16_colstats(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc,

@@ -33,6 +33,7 @@ SIGNATURES = {
     "cofi_debug_x3_profile": (_i, [_vp]),
     "cofi_gemm_f16": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _vp]),
     "cofi_gemm_colstats": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "cofi_gemm_colstats_acc": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _i, _vp, _vp]),
     "cofi_gemm_f16_colstats": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _vp, _vp]),
     "cofi_gemm_ln": (_i, [_vp, _l, _vp, _l, _vp, _l, _l, _i, _i, _vp, _vp, _vp, _f, _i, _vp, _l, _i, _vp]),
     "cofi_conv2d_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),

@@ -38,6 +38,25 @@ class KPConvFPN(nn.Module):
         ops.gather_rows(skip, None, frames=frames, out=buf[:, c1:])
         return buf
 
+    def _decode(self, block, coarse, up_table, skip, frames):
+        """block(cat([nearest_upsample(coarse), skip])) (reference kp_backbone.py:100-118).  Inference: a row gather commutes
+        with a row-wise linear map, W [up(x_c) | x_f] = up(W_c x_c) + W_f x_f, so the coarse half of the Linear runs at the
+        coarse resolution (half the rows: a third fewer flops), its result is up-sampled straight into the output buffer and
+        the fine half accumulates onto it -- the concatenated [rows, c1 + c2] buffer never exists."""
+        if ad.active(self):
+            return block(self._up_cat(coarse, up_table, skip, frames), frames)
+        with ops.group("pc_unary"):
+            W, c1 = block.mlp.weight, coarse.shape[1]
+            yc = ops.gemm(coarse, W[:, :c1])
+            y = nearest_upsample(yc, up_table, frames)
+            if isinstance(block, UnaryBlock) and ops.colstats_ok(skip.shape[0], frames, block.out_channels):
+                y, st = ops.gemm_colstats(skip, W[:, c1:], bias=block.mlp.bias, out=y, accumulate=True)
+                return block.norm(y, frames, act=ops.ACT_LRELU if block.leaky_relu is not None else ops.ACT_NONE, tile_stats=st)
+            y = ops.gemm(skip, W[:, c1:], bias=block.mlp.bias, out=y, accumulate=True)
+            if isinstance(block, UnaryBlock):
+                return block.norm(y, frames, act=ops.ACT_LRELU if block.leaky_relu is not None else ops.ACT_NONE)
+            return y
+
     def forward(self, data_dict, frames: int = 1, taps=None):
         feats = data_dict["feats"]
         p, nb = data_dict["points"], data_dict["neighbors"]
@@ -57,9 +76,9 @@ class KPConvFPN(nn.Module):
         f5 = self.encoder5_1(f4, p[4], p[3], sub[3], f)
         f5 = self.encoder5_2(f5, p[4], p[4], nb[4], f)
         f5 = self.encoder5_3(f5, p[4], p[4], nb[4], f)
-        l4 = self.decoder4(self._up_cat(f5, up[3], f4, f), f)
-        l3 = self.decoder3(self._up_cat(l4, up[2], f3, f), f)
-        l2 = self.decoder2(self._up_cat(l3, up[1], f2, f), f)
+        l4 = self._decode(self.decoder4, f5, up[3], f4, f)
+        l3 = self._decode(self.decoder3, l4, up[2], f3, f)
+        l2 = self._decode(self.decoder2, l3, up[1], f2, f)
         if taps is not None:
             taps.update(encoder1_2=f1, encoder2_3=f2, encoder3_3=f3, encoder4_3=f4, encoder5_3=f5,
                         decoder4=l4, decoder3=l3, decoder2=l2)

@@ -397,16 +397,25 @@ def gemm(a, w, bias=None, rowdiv=None, act: int = ACT_NONE, out: Optional[torch.
     return out
 
 
-def gemm_colstats(a, w, bias=None, rowdiv=None, const_w: Optional[bool] = None):
-    """tensor-core GEMM that also returns the per-128-row-tile column statistics of its output (for norm_rows_pre)."""
+def gemm_colstats(a, w, bias=None, rowdiv=None, const_w: Optional[bool] = None, out: Optional[torch.Tensor] = None,
+                  accumulate: bool = False):
+    """tensor-core GEMM that also returns the per-128-row-tile column statistics of its output (for norm_rows_pre).
+    accumulate: `out` (contiguous [M, N]) is read and rewritten, out += a @ w.T + bias; the statistics describe the sum."""
     a, lda = _rows(a, "a")
     M, K = a.shape
     N = w.shape[0]
     w, ldw, eng = _x3_weights(w, _eng(), const_w)
-    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if accumulate:
+        if out is None or rowdiv is not None or tuple(out.shape) != (M, N) or not out.is_contiguous() or out.dtype != torch.float32:
+            raise RuntimeError("gemm_colstats(accumulate): needs a contiguous float32 [M, N] `out` and no rowdiv")
+    else:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     stats = torch.empty((M // 128, N, 2), dtype=torch.float32, device=a.device)
-    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N), f"{M}x{N}x{K}")
-    _call("cofi_gemm_colstats", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(rowdiv), eng, _p(stats), _st())
+    _meta(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (2 if accumulate else 1)), f"{M}x{N}x{K}" + (" acc" if accumulate else ""))
+    if accumulate:
+        _call("cofi_gemm_colstats_acc", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), eng, _p(stats), _st())
+    else:
+        _call("cofi_gemm_colstats", _p(a), lda, _p(w), ldw, _p(out), N, M, N, K, _p(bias), _p(rowdiv), eng, _p(stats), _st())
     return out, stats
 
 

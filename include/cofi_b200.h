@@ -182,6 +182,12 @@ int cofi_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, float*
  * (fp64) and applies.  Tensor-core engines, M % 128 == 0, no activation. */
 int cofi_gemm_colstats(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
                        int K, const float* bias, const float* rowdiv, int engine, float* stats, void* stream);
+/* cofi_gemm_colstats with C += (C is read and rewritten; the statistics describe the stored sum): the second half of a Linear
+ * over a concatenated input.  The point-branch decoder (model/kpconv/kp_backbone.py:100-118) applies Linear(cat[up(x_c), x_f]);
+ * a row gather commutes with a row-wise linear map, so W_c is applied at the COARSE resolution (half the rows), the result is
+ * up-sampled into C and this call adds W_f x_f + bias: a third fewer flops and no concatenated buffer. */
+int cofi_gemm_colstats_acc(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
+                           int K, const float* bias, int engine, float* stats, void* stream);
 int cofi_gemm_f16_colstats(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc, int64_t M, int N,
                            int K, const float* bias, const float* rowdiv, float* stats, void* stream);
 
