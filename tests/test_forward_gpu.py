@@ -291,3 +291,29 @@ def test_kitti_front_end_feeds_the_model(cuda_model, tmp_path):
     assert out[0].shape == (1, 128, 20, 64) and out[4].shape == (n, 64, 4, 4) and out[5].shape == (n, 64)
     assert out_t[6].shape[0] == 2 and out_t[7].shape[1] == 3 and out_t[6].shape[1] == out_t[7].shape[0] >= 4
     assert all(bool(torch.isfinite(t).all()) for t in out[:6])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["fp32", "tf32x3"])
+def test_decoder_split_equals_concatenated_linear(cuda_model, engine):
+    """KPConvFPN._decode evaluates Linear(cat[up(x_c), x_f]) as up(W_c x_c) + W_f x_f (the coarse half at the coarse resolution,
+    reference model/kpconv/kp_backbone.py:100-118).  Against the concatenated form run through the same block: decoder4
+    (UnaryBlock: Linear + GroupNorm + LeakyReLU, statistics from the accumulate GEMM's epilogue) and decoder2 (Linear only),
+    two stacked frames."""
+    from cofii2p_b200 import ops
+    fpn = cuda_model.pc_encoder
+    g = torch.Generator().manual_seed(11)
+    frames, nc, nf = 2, 256, 512
+    up = torch.randint(0, nc, (frames * nf, 128), generator=g).cuda()
+    ops.set_engine(engine)
+    try:
+        with torch.no_grad():
+            for block, c1, c2 in ((fpn.decoder4, 2048, 1024), (fpn.decoder2, 512, 256)):
+                xc = torch.randn((frames * nc, c1), generator=g).cuda()
+                xf = torch.randn((frames * nf, c2), generator=g).cuda()
+                want = block(fpn._up_cat(xc, up, xf, frames), frames)
+                got = fpn._decode(block, xc, up, xf, frames)
+                assert got.shape == want.shape
+                assert rel_err(got, want.cpu()) < 2e-5, (engine, c1, rel_err(got, want.cpu()))
+    finally:
+        ops.set_engine("fp32")
