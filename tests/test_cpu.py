@@ -506,3 +506,23 @@ def test_committed_bench_lines_follow_the_contract():
         assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
         assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_weight_operand_detection_and_decoder_algebra():
+    """Host logic of two round-2 paths, no GPU needed.
+    (1) ops._is_weight decides whether a contraction's W operand is a constant of the forward pass (pre-split once for the
+        3xTF32 engine): nn.Parameters and views of them are, activations are not.
+    (2) The identity behind KPConvFPN._decode: a row gather commutes with a row-wise linear map, so
+        Linear(cat[x_c[idx], x_f]) == (x_c @ W_c.T)[idx] + x_f @ W_f.T + b  (reference model/kpconv/kp_backbone.py:100-118)."""
+    import torch
+    from cofii2p_b200 import ops
+    lin = torch.nn.Linear(12, 8, bias=False)
+    assert ops._is_weight(lin.weight) and ops._is_weight(lin.weight[:, :4]) and ops._is_weight(lin.weight.reshape(8, -1))
+    assert not ops._is_weight(torch.randn(8, 12)) and not ops._is_weight(torch.randn(8, 12)[:, :4])
+    g = torch.Generator().manual_seed(0)
+    xc, xf = torch.randn((40, 6), generator=g, dtype=torch.float64), torch.randn((90, 5), generator=g, dtype=torch.float64)
+    idx = torch.randint(0, 40, (90,), generator=g)
+    W, b = torch.randn((7, 11), generator=g, dtype=torch.float64), torch.randn((7,), generator=g, dtype=torch.float64)
+    want = torch.nn.functional.linear(torch.cat([xc[idx], xf], 1), W, b)
+    got = (xc @ W[:, :6].t())[idx] + xf @ W[:, 6:].t() + b
+    assert torch.allclose(got, want, rtol=1e-12, atol=1e-12)
